@@ -1,0 +1,239 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader for oracle/_ref/libpcaone_ref.so (the
+unmodified reference compiled by oracle/Makefile + our driver oracle/ref_shim.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpcaone_ref.so")
+
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p]
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_time_gandh.restype = C.c_double
+        L.ref_mev.restype = C.c_double
+        L.ref_dataG_cols.restype = C.c_longlong
+        L.ref_perm_size.restype = C.c_longlong
+        L.ref_missing_count.restype = C.c_longlong
+        L.ref_ld_r2.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f(shape):
+    return np.zeros(shape, dtype=np.float64, order="F")
+
+
+class Ref:
+    """One reference run: Param + FileBed (+permutation) + prepare (+ op)."""
+
+    def __init__(self, cmdline: str, threads: int | None = None):
+        L = lib()
+        if threads:
+            L.ref_set_threads(int(threads))
+        self.h = L.ref_open(cmdline.encode())
+        if not self.h:
+            raise RuntimeError("reference failed: " + L.ref_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        d = (C.c_longlong * 10)()
+        L.ref_dims(self.h, d)
+        (self.N, self.M, self.k, self.l, self.nblocks, self.blocksize, self.bandFactor,
+         self.bands, self.out_of_core, self.perm) = [int(x) for x in d]
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError("reference failed: " + lib().ref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().ref_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def new_op(self):
+        self._chk(lib().ref_new_op(self.h))
+        d = (C.c_longlong * 10)()
+        lib().ref_dims(self.h, d)
+        self.N, self.M = int(d[0]), int(d[1])
+
+    def block_plan(self):
+        s = np.zeros(self.nblocks, dtype=np.uint32)
+        e = np.zeros(self.nblocks, dtype=np.uint32)
+        lib().ref_block_plan(self.h, _p(s), _p(e))
+        return s, e
+
+    def F(self):
+        out = np.zeros(self.M)
+        lib().ref_get_F(self.h, _p(out))
+        return out
+
+    def lookup(self):
+        out = _f((4, self.M))
+        lib().ref_get_lookup(self.h, _p(out))
+        return out
+
+    def dataG(self):
+        cols = int(lib().ref_dataG_cols(self.h))
+        out = _f((self.N, cols))
+        lib().ref_get_dataG(self.h, _p(out))
+        return out
+
+    def perm_indices(self):
+        n = int(lib().ref_perm_size(self.h))
+        out = np.zeros(n, dtype=np.int32)
+        if n:
+            lib().ref_get_perm(self.h, _p(out))
+        return out
+
+    def mask(self):
+        out = np.zeros(self.M * self.N, dtype=np.uint8)
+        lib().ref_get_mask(self.h, _p(out))
+        return out.reshape(self.M, self.N)
+
+    def set_flags(self, update, standardize):
+        lib().ref_set_flags(self.h, int(update), int(standardize))
+
+    def omega(self):
+        out = _f((self.N, self.l))
+        lib().ref_get_omg(self.h, _p(out))
+        return out
+
+    def gandh(self, pi):
+        G = _f((self.M, self.l))
+        H = _f((self.N, self.l))
+        self._chk(lib().ref_gandh(self.h, int(pi), _p(G), _p(H)))
+        return G, H
+
+    def time_gandh(self, pi):
+        t = lib().ref_time_gandh(self.h, int(pi))
+        if t < 0:
+            self._chk(1)
+        return t
+
+    def compute_usv(self, maxp, tol):
+        U, S, V = _f((self.N, self.k)), np.zeros(self.k), _f((self.M, self.k))
+        self._chk(lib().ref_compute_usv(self.h, int(maxp), C.c_double(tol), _p(U), _p(S), _p(V)))
+        return U, S, V
+
+    def compute_u(self, G, H):
+        G = np.asfortranarray(G, dtype=np.float64)
+        H = np.asfortranarray(H, dtype=np.float64)
+        U = _f((self.N, self.k))
+        self._chk(lib().ref_compute_u(self.h, _p(G), _p(H), _p(U)))
+        return U
+
+    def run_em(self):
+        U, S, V = _f((self.N, self.k)), np.zeros(self.k), _f((self.M, self.k))
+        it = C.c_int(0)
+        self._chk(lib().ref_run_em(self.h, _p(U), _p(S), _p(V), C.byref(it)))
+        return U, S, V, it.value
+
+    def set_usv(self, U, S, V):
+        U = np.asfortranarray(U, dtype=np.float64)
+        V = np.asfortranarray(V, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        lib().ref_set_usv(self.h, _p(U), _p(S), _p(V))
+
+    def read_block_initial(self, start, stop, standardize):
+        out = _f((self.N, stop - start + 1))
+        self._chk(lib().ref_read_block_initial(self.h, C.c_ulonglong(start), C.c_ulonglong(stop),
+                                               int(standardize), _p(out)))
+        return out
+
+    def read_block_update(self, start, stop, U, S, V, standardize):
+        U = np.asfortranarray(U, dtype=np.float64)
+        V = np.asfortranarray(V, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        out = _f((self.N, stop - start + 1))
+        self._chk(lib().ref_read_block_update(self.h, C.c_ulonglong(start), C.c_ulonglong(stop), _p(U), _p(S),
+                                              _p(V), int(S.shape[0]), int(standardize), _p(out)))
+        return out
+
+    def fit_with_pi(self, U, S, V):
+        U = np.asfortranarray(U, dtype=np.float64)
+        V = np.asfortranarray(V, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        self._chk(lib().ref_fit_with_pi(self.h, _p(U), _p(S), _p(V), int(S.shape[0])))
+
+    def standardize_E(self):
+        self._chk(lib().ref_standardize_E(self.h))
+
+    def ld_r2(self, filebim, ld_bp):
+        nwin = C.c_longlong(0)
+        n = lib().ref_ld_r2(self.h, filebim.encode(), int(ld_bp), None, C.c_longlong(0), None, None,
+                            C.byref(nwin))
+        if n < 0:
+            self._chk(1)
+        out = np.zeros(n)
+        ws = np.zeros(nwin.value, dtype=np.int32)
+        we = np.zeros(nwin.value, dtype=np.int32)
+        lib().ref_ld_r2(self.h, filebim.encode(), int(ld_bp), _p(out), C.c_longlong(n), _p(ws), _p(we),
+                        C.byref(nwin))
+        return out, ws, we
+
+
+def init_omega(rows, cols, seed=112, gaussian=True):
+    out = _f((rows, cols))
+    lib().ref_init_omega(C.c_longlong(rows), C.c_longlong(cols), int(seed), int(gaussian), _p(out))
+    return out
+
+
+def permute_indices(n):
+    out = np.zeros(n, dtype=np.int32)
+    lib().ref_permute_indices(C.c_longlong(n), _p(out))
+    return out
+
+
+def mev(X, Y):
+    X = np.asfortranarray(X, dtype=np.float64)
+    Y = np.asfortranarray(Y, dtype=np.float64)
+    return float(lib().ref_mev(_p(X), _p(Y), C.c_longlong(X.shape[0]), C.c_longlong(X.shape[1])))
+
+
+def flip_uv(U, V):
+    U = np.asfortranarray(U, dtype=np.float64).copy(order="F")
+    V = np.asfortranarray(V, dtype=np.float64).copy(order="F")
+    lib().ref_flip_uv(_p(U), C.c_longlong(U.shape[0]), _p(V), C.c_longlong(V.shape[0]), C.c_longlong(U.shape[1]))
+    return U, V
+
+
+def flip_omg(Omg2, Omg):
+    A = np.asfortranarray(Omg2, dtype=np.float64).copy(order="F")
+    B = np.asfortranarray(Omg, dtype=np.float64).copy(order="F")
+    lib().ref_flip_omg(_p(A), _p(B), C.c_longlong(A.shape[0]), C.c_longlong(A.shape[1]))
+    return A, B
+
+
+def householder_q(A):
+    A = np.asfortranarray(A, dtype=np.float64)
+    Q = _f(A.shape)
+    lib().ref_householder_q(_p(A), C.c_longlong(A.shape[0]), C.c_longlong(A.shape[1]), _p(Q))
+    return Q

@@ -1,0 +1,417 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+//
+// C-ABI shim around the UNMODIFIED PCAone reference classes so that tests and
+// bench.py's cpu_baseline / --impl reference legs can drive the reference's own
+// CPU implementation of the randomized-SVD hot path and read its in-memory
+// doubles (the reference's text writers keep only 6 significant digits,
+// src/Data.cpp:215).
+//
+// The reference sources are compiled where they lie (see oracle/Makefile); this
+// file only includes their headers. Nothing here is copied from the reference:
+// it is a driver that calls the public members of
+//   Param            (src/Cmd.hpp:16-98)
+//   Data / FileBed   (src/Data.hpp:9-59, src/FilePlink.hpp:8-47)
+//   RsvdOpData, NormalRsvdOpData, FancyRsvdOpData (src/Halko.hpp:6-93)
+//   permute_plink    (src/FilePlink.cpp:303)
+//   flip_UV / mev    (src/Utils.cpp:118,194)
+//   PCAone::flipOmg  (src/RSVD.hpp:80)
+//   calc_sds / divide_pos_by_window (src/LD.cpp:48,154)
+#define _DECLARE_TOOLBOX_HERE
+#include <omp.h>
+
+#include <chrono>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "Cmd.hpp"
+#include "Common.hpp"
+#include "Data.hpp"
+#include "FileBinary.hpp"
+#include "FilePlink.hpp"
+#include "Halko.hpp"
+#include "LD.hpp"
+#include "RSVD.hpp"
+#include "Utils.hpp"
+
+namespace {
+
+struct RefCtx {
+  Param* params = nullptr;
+  Data* data = nullptr;
+  RsvdOpData* op = nullptr;
+  Mat2D G, H;  // the locals of RsvdOpData::computeUSV (Halko.cpp:50), kept across epochs
+  std::string err;
+};
+
+thread_local std::string g_err;
+
+std::vector<std::string> split_ws(const char* s) {
+  std::vector<std::string> out;
+  std::istringstream is(s);
+  std::string t;
+  while (is >> t) out.push_back(t);
+  return out;
+}
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void ref_set_threads(int n) { omp_set_num_threads(n); Eigen::setNbThreads(n); }
+int ref_get_threads() { return omp_get_max_threads(); }
+
+// Mirrors the PLINK branch of main(): Main.cpp:48-57 (Param, logger), :121-153
+// (out-of-core permutation or plain FileBed), :168 (Data::prepare).
+void* ref_open(const char* cmdline) {
+  RefCtx* c = new RefCtx();
+  int rc = guarded([&] {
+    auto toks = split_ws(cmdline);
+    std::vector<char*> argv;
+    for (auto& t : toks) argv.push_back(const_cast<char*>(t.c_str()));
+    c->params = new Param((int)argv.size(), argv.data());
+    Param& params = *c->params;
+    if (cao.cao.is_open()) cao.cao.close();
+    cao.cao.open(params.fileout + ".log");
+    cao.is_screen = false;
+    const bool ooc_permutation = params.perm && params.out_of_core;
+    if (params.file_t == FileType::BINARY) {
+      c->data = new FileBin(params);
+    } else if (params.file_t == FileType::PLINK) {
+      if (ooc_permutation) {
+        auto perm = permute_plink(params.filein, params.fileout, params.buffer, params.bands);
+        c->data = new FileBed(params);
+        c->data->perm = perm;
+      } else {
+        c->data = new FileBed(params);
+      }
+    } else {
+      throw std::runtime_error("ref_shim: only --bfile / --binary inputs are driven by the oracle");
+    }
+    c->data->prepare();
+  });
+  if (rc) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void ref_close(void* h) {
+  RefCtx* c = (RefCtx*)h;
+  if (!c) return;
+  delete c->op;
+  delete c->data;
+  delete c->params;
+  delete c;
+}
+
+// Mirrors Halko.cpp:271-288: choose the op and set the initial flags.
+int ref_new_op(void* h) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    const Param& p = *c->params;
+    delete c->op;
+    if (p.svd_t == SvdType::PCAoneAlg2)
+      c->op = new FancyRsvdOpData(c->data, p.k, p.oversamples);
+    else
+      c->op = new NormalRsvdOpData(c->data, p.k, p.oversamples);
+    if (p.genetic)
+      c->op->setFlags(false, p.ld ? false : true);
+    else
+      c->op->setFlags(false, false);
+    c->G = Mat2D::Zero(c->op->rows(), c->op->size());
+    c->H = Mat2D::Zero(c->op->cols(), c->op->size());
+  });
+}
+
+// dims: [nsamples, nsnps, k, l, nblocks, blocksize, bandFactor, bands, out_of_core, perm]
+void ref_dims(void* h, long long* d) {
+  RefCtx* c = (RefCtx*)h;
+  const Param& p = *c->params;
+  d[0] = c->data->nsamples;
+  d[1] = c->data->nsnps;
+  d[2] = p.k;
+  d[3] = p.k + p.oversamples;
+  d[4] = c->data->nblocks;
+  d[5] = c->data->blocksize;
+  d[6] = c->data->bandFactor;
+  d[7] = p.bands;
+  d[8] = p.out_of_core;
+  d[9] = p.perm;
+}
+
+void ref_block_plan(void* h, unsigned* start, unsigned* stop) {
+  RefCtx* c = (RefCtx*)h;
+  for (size_t i = 0; i < c->data->start.size(); ++i) {
+    start[i] = c->data->start[i];
+    stop[i] = c->data->stop[i];
+  }
+}
+
+void ref_get_F(void* h, double* out) {
+  RefCtx* c = (RefCtx*)h;
+  std::memcpy(out, c->data->F.data(), sizeof(double) * c->data->F.size());
+}
+
+void ref_get_lookup(void* h, double* out) {  // 4 x M, column-major (Arr2D)
+  RefCtx* c = (RefCtx*)h;
+  std::memcpy(out, c->data->centered_geno_lookup.data(), sizeof(double) * c->data->centered_geno_lookup.size());
+}
+
+long long ref_dataG_cols(void* h) { return ((RefCtx*)h)->data->G.cols(); }
+void ref_get_dataG(void* h, double* out) {
+  RefCtx* c = (RefCtx*)h;
+  std::memcpy(out, c->data->G.data(), sizeof(double) * c->data->G.size());
+}
+
+long long ref_perm_size(void* h) { return ((RefCtx*)h)->data->perm.indices().size(); }
+void ref_get_perm(void* h, int* out) {
+  RefCtx* c = (RefCtx*)h;
+  for (Eigen::Index i = 0; i < c->data->perm.indices().size(); ++i) out[i] = c->data->perm.indices()[i];
+}
+
+long long ref_missing_count(void* h) { return ((RefCtx*)h)->data->C.count(); }
+void ref_get_mask(void* h, unsigned char* out) {
+  RefCtx* c = (RefCtx*)h;
+  for (Eigen::Index i = 0; i < c->data->C.size(); ++i) out[i] = c->data->C[i];
+}
+
+void ref_set_flags(void* h, int update, int standardize) { ((RefCtx*)h)->op->setFlags(update, standardize); }
+
+void ref_get_omg(void* h, double* out) {
+  RefCtx* c = (RefCtx*)h;
+  std::memcpy(out, c->op->Omg.data(), sizeof(double) * c->op->Omg.size());
+}
+
+// One call of the pure virtual on the path: RsvdOpData::computeGandH (Halko.hpp:27).
+int ref_gandh(void* h, int pi, double* G_out, double* H_out) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    c->op->computeGandH(c->G, c->H, pi);
+    if (G_out) std::memcpy(G_out, c->G.data(), sizeof(double) * c->G.size());
+    if (H_out) std::memcpy(H_out, c->H.data(), sizeof(double) * c->H.size());
+  });
+}
+
+// seconds spent in one computeGandH call (the "power-iteration pass" of the metric)
+double ref_time_gandh(void* h, int pi) {
+  RefCtx* c = (RefCtx*)h;
+  auto t0 = std::chrono::high_resolution_clock::now();
+  int rc = guarded([&] { c->op->computeGandH(c->G, c->H, pi); });
+  auto t1 = std::chrono::high_resolution_clock::now();
+  if (rc) return -1.0;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// RsvdOpData::computeUSV (Halko.cpp:46-97); returns U (N x k), S (k), V (M x k).
+int ref_compute_usv(void* h, int maxp, double tol, double* U, double* S, double* V) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    c->op->computeUSV(maxp, tol);
+    if (U) std::memcpy(U, c->op->U.data(), sizeof(double) * c->op->U.size());
+    if (S) std::memcpy(S, c->op->S.data(), sizeof(double) * c->op->S.size());
+    if (V) std::memcpy(V, c->op->V.data(), sizeof(double) * c->op->V.size());
+  });
+}
+
+// The small dense stage alone (Halko.cpp:55-70) through the reference's computeU
+// on caller-supplied G (M x l) and H (N x l): returns V_B[:, :k] (N x k).
+int ref_compute_u(void* h, const double* G, const double* H, double* Uout) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    Eigen::Map<const Mat2D> Gm(G, c->op->rows(), c->op->size());
+    Eigen::Map<const Mat2D> Hm(H, c->op->cols(), c->op->size());
+    Mat2D U = c->op->computeU(Gm, Hm);
+    std::memcpy(Uout, U.data(), sizeof(double) * U.size());
+  });
+}
+
+// The EM driver of run_pca_with_halko (Halko.cpp:290-319) restated on the public
+// members so that U,S,V stay in memory. Returns the number of EM iterations run.
+int ref_run_em(void* h, double* U, double* S, double* V, int* iters) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    const Param& params = *c->params;
+    RsvdOpData* rsvd = c->op;
+    Mat2D Vpre;
+    rsvd->setFlags(false, false);
+    rsvd->computeUSV(params.maxp, params.tol);
+    flip_UV(rsvd->U, rsvd->V, false);
+    double diff;
+    int it = 0;
+    for (uint i = 0; i < params.maxiter; ++i) {
+      rsvd->setFlags(true, false);
+      Vpre = rsvd->V;
+      rsvd->computeUSV(params.maxp, params.tol);
+      flip_UV(rsvd->U, rsvd->V, false);
+      diff = 1.0 - mev(rsvd->V, Vpre);
+      it = i + 1;
+      if (diff < params.tolem) break;
+    }
+    if (params.emu) {
+      rsvd->setFlags(true, true);
+      rsvd->computeUSV(params.maxp, params.tol);
+      flip_UV(rsvd->U, rsvd->V, false);
+    }
+    if (iters) *iters = it;
+    if (U) std::memcpy(U, rsvd->U.data(), sizeof(double) * rsvd->U.size());
+    if (S) std::memcpy(S, rsvd->S.data(), sizeof(double) * rsvd->S.size());
+    if (V) std::memcpy(V, rsvd->V.data(), sizeof(double) * rsvd->V.size());
+  });
+}
+
+void ref_get_usv(void* h, double* U, double* S, double* V) {
+  RefCtx* c = (RefCtx*)h;
+  if (U) std::memcpy(U, c->op->U.data(), sizeof(double) * c->op->U.size());
+  if (S) std::memcpy(S, c->op->S.data(), sizeof(double) * c->op->S.size());
+  if (V) std::memcpy(V, c->op->V.data(), sizeof(double) * c->op->V.size());
+}
+void ref_set_usv(void* h, const double* U, const double* S, const double* V) {
+  RefCtx* c = (RefCtx*)h;
+  const long long N = c->op->cols(), M = c->op->rows(), k = c->op->ranks();
+  c->op->U = Eigen::Map<const Mat2D>(U, N, k);
+  c->op->S = Eigen::Map<const Mat1D>(S, k);
+  c->op->V = Eigen::Map<const Mat2D>(V, M, k);
+}
+
+// Data virtuals on the path (Data.hpp:16-21), out-of-core mode.
+int ref_read_block_initial(void* h, unsigned long long start, unsigned long long stop, int standardize,
+                           double* out) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    if (start == c->data->start[0]) c->data->check_file_offset_first_var();
+    c->data->read_block_initial(start, stop, standardize);
+    if (out) std::memcpy(out, c->data->G.data(), sizeof(double) * c->data->nsamples * (stop - start + 1));
+  });
+}
+
+int ref_read_block_update(void* h, unsigned long long start, unsigned long long stop, const double* U,
+                          const double* S, const double* V, int k, int standardize, double* out) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    Eigen::Map<const Mat2D> Um(U, c->data->nsamples, k);
+    Eigen::Map<const Mat1D> Sm(S, k);
+    Eigen::Map<const Mat2D> Vm(V, c->data->nsnps, k);
+    if (start == c->data->start[0]) c->data->check_file_offset_first_var();
+    c->data->read_block_update(start, stop, Um, Sm, Vm.transpose(), standardize);
+    if (out) std::memcpy(out, c->data->G.data(), sizeof(double) * c->data->nsamples * (stop - start + 1));
+  });
+}
+
+// Data::fit_with_pi (Data.cpp:293-349) + standardize_E (:351-362), in-core.
+int ref_fit_with_pi(void* h, const double* U, const double* S, const double* V, int k) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    Eigen::Map<const Mat2D> Um(U, c->data->nsamples, k);
+    Eigen::Map<const Mat1D> Sm(S, k);
+    Eigen::Map<const Mat2D> Vm(V, c->data->nsnps, k);
+    c->data->fit_with_pi(Um, Sm, Vm.transpose());
+  });
+}
+int ref_standardize_E(void* h) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] { c->data->standardize_E(); });
+}
+
+// helpers on the path: Utils.cpp:194 (mev), :118 (flip_UV), RSVD.hpp:80 (flipOmg)
+double ref_mev(const double* X, const double* Y, long long rows, long long cols) {
+  Eigen::Map<const Mat2D> Xm(X, rows, cols), Ym(Y, rows, cols);
+  return mev(Xm, Ym);
+}
+void ref_flip_uv(double* U, long long urows, double* V, long long vrows, long long k) {
+  Mat2D Um = Eigen::Map<Mat2D>(U, urows, k), Vm = Eigen::Map<Mat2D>(V, vrows, k);
+  flip_UV(Um, Vm, false);
+  std::memcpy(U, Um.data(), sizeof(double) * Um.size());
+  std::memcpy(V, Vm.data(), sizeof(double) * Vm.size());
+}
+void ref_flip_omg(double* Omg2, double* Omg, long long rows, long long cols) {
+  Mat2D A = Eigen::Map<Mat2D>(Omg2, rows, cols), B = Eigen::Map<Mat2D>(Omg, rows, cols);
+  PCAone::flipOmg(A, B);
+  std::memcpy(Omg2, A.data(), sizeof(double) * A.size());
+  std::memcpy(Omg, B.data(), sizeof(double) * B.size());
+}
+// thin Q of HouseholderQR as used for Omega (Halko.cpp:121-122)
+void ref_householder_q(const double* A, long long rows, long long cols, double* Q) {
+  Mat2D Am = Eigen::Map<const Mat2D>(A, rows, cols);
+  Eigen::HouseholderQR<Mat2D> qr(Am);
+  Mat2D Qm = qr.householderQ() * Mat2D::Identity(rows, cols);
+  std::memcpy(Q, Qm.data(), sizeof(double) * Qm.size());
+}
+
+// Omega exactly as RsvdOpData::initOmg draws it (Halko.cpp:15-23, RSVD.hpp:46-59)
+void ref_init_omega(long long rows, long long cols, int seed, int gaussian, double* out) {
+  auto rng = std::default_random_engine{};
+  rng.seed(seed);
+  Mat2D O;
+  if (gaussian)
+    O = PCAone::StandardNormalRandom<Mat2D, std::default_random_engine>(rows, cols, rng);
+  else
+    O = PCAone::UniformRandom<Mat2D, std::default_random_engine>(rows, cols, rng);
+  std::memcpy(out, O.data(), sizeof(double) * O.size());
+}
+// the in-core column permutation of winSVD (RSVD.hpp:61-78), indices only
+void ref_permute_indices(long long n, int* out) {
+  PermMat P(n);
+  P.setIdentity();
+  auto rng = std::default_random_engine{};
+  std::shuffle(P.indices().data(), P.indices().data() + P.indices().size(), rng);
+  for (long long i = 0; i < n; ++i) out[i] = P.indices()[i];
+}
+
+// LD r2 (LD.cpp:450-473 ld_r2_big) without the gz text writer: windows from
+// divide_pos_by_window (LD.cpp:154-168); r2 values appended in output order.
+// Returns number of pairs, or -1 on error. Pass out=nullptr to count only.
+long long ref_ld_r2(void* h, const char* filebim, int ld_bp, double* out, long long cap, int* ws_out,
+                    int* we_out, long long* nwin) {
+  RefCtx* c = (RefCtx*)h;
+  long long n = 0;
+  int rc = guarded([&] {
+    SNPld snp;
+    get_snp_pos_bim(snp, filebim);
+    divide_pos_by_window(snp, ld_bp);
+    const Mat2D& G = c->data->G;
+    Arr1D sds = 1.0 / calc_sds(G);
+    const double df = 1.0 / (G.rows() - 1);
+    if (nwin) *nwin = (long long)snp.ws.size();
+    for (int w = 0; w < (int)snp.ws.size(); w++) {
+      int i = snp.ws[w];
+      if (ws_out) ws_out[w] = snp.ws[w];
+      if (we_out) we_out[w] = snp.we[w];
+      for (int j = 1; j < snp.we[w]; j++) {
+        int k = i + j;
+        if (out && n < cap) {
+          double r = G.col(i).dot(G.col(k)) * (sds(i) * sds(k) * df);
+          out[n] = r * r;
+        }
+        n++;
+      }
+    }
+  });
+  return rc ? -1 : n;
+}
+
+// Data::write_residuals (Data.cpp:242-291) via the reference writer.
+int ref_write_residuals(void* h) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] { c->data->write_residuals(c->op->S, c->op->U, c->op->V.transpose()); });
+}
+
+}  // extern "C"
