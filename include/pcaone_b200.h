@@ -1,0 +1,165 @@
+/* pcaone_b200 — C-ABI of the B200-native randomized-SVD hot path of PCAone.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / Eigen
+ * types. Every entry point names the reference interface it replaces
+ * (file:line relative to Zilong-Li/PCAone v0.7.2). INTEGRATION.md shows the
+ * `GpuNormalRsvdOpData / GpuFancyRsvdOpData : RsvdOpData` subclasses a PCAone maintainer
+ * would add on top of these calls.
+ *
+ * Conventions
+ *  - every call returns 0 on success, non-zero on failure; pcaone_last_error(ctx) gives
+ *    the message (the reference throws std::runtime_error from cao.error, Logger.hpp:85-94;
+ *    the host shim converts a non-zero status into that throw).
+ *  - host matrices are column-major FP64 exactly as Eigen::MatrixXd::data() lays them out
+ *    (Common.hpp:30-31): G is M x l, H/Omega are N x l, U is N x k, V is M x k.
+ *  - packed genotypes are PLINK bed SNP-major rows of bpr = ceil(N/4) bytes, sample 4q+r in
+ *    bits 2r..2r+1 of byte q (FilePlink.cpp:39-47), WITHOUT the 3-byte file header.
+ *  - all calls are made from one host thread per context (the reference is single-threaded
+ *    at this level). One context drives one GPU.
+ *  - there is NO CPU fallback: creation fails when no CUDA device is usable.
+ */
+#ifndef PCAONE_B200_H_
+#define PCAONE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcaone_ctx pcaone_ctx;
+
+enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cmd.cpp:41-45) */
+enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_BF16X3 = 1 };        /* GEMM arithmetic */
+enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2 };
+
+/* Mirrors the fields of `Param` (Cmd.hpp:16-98) that the hot path reads. */
+typedef struct pcaone_config {
+  uint64_t nsamples;     /* N                                                        */
+  uint64_t nsnps;        /* M owned by this context (the local SNP shard)             */
+  uint64_t nsnps_total;  /* M of the whole job (== nsnps on one GPU); eigvals use it  */
+  uint32_t k;            /* -k                                                       */
+  uint32_t oversamples;  /* already max(oversamples,k) as Cmd.cpp:216 derives it      */
+  uint32_t svd;          /* PCAONE_SVD_*                                             */
+  uint32_t bands;        /* -w/--batches, 64                                         */
+  uint32_t maxp;         /* --maxp 20                                                */
+  double   tol;          /* --tol-rsvd 1e-4                                          */
+  int32_t  ploidy;       /* 2, or 1 with --haploid                                   */
+  int32_t  scale;        /* -C; -9 = standardize by sqrt(ploidy f(1-f))              */
+  int32_t  emu;          /* --emu                                                    */
+  int32_t  out_of_core;  /* -m > 0: walk start[]/stop[] blocks, no flipOmg in sSVD   */
+  int32_t  precision;    /* PCAONE_PREC_*                                            */
+  int32_t  device;       /* CUDA ordinal                                             */
+  int32_t  rank, world;  /* SNP-sharded multi-GPU job: this context's rank / #ranks  */
+  uint32_t maxiter;      /* --maxiter 100 (EM)                                       */
+  double   tolem;        /* --tol-em 1e-5                                            */
+} pcaone_config;
+
+/* Collective hook for SNP-sharded jobs: sum `count` doubles at device pointer `buf`
+ * across ranks, ordered after prior work on `stream` (a cudaStream_t) and before later
+ * work on it. The Python host installs torch.distributed.all_reduce (NCCL) here. */
+typedef int (*pcaone_allreduce_fn)(void* user, void* buf, uint64_t count, void* stream);
+
+/* Block source for out-of-core passes: fill dst (pinned) with the packed rows of SNPs
+ * start..stop inclusive (bpr bytes each). Replaces the ifstream.read of
+ * FileBed::read_block_initial (FilePlink.cpp:125-136). */
+typedef int (*pcaone_read_block_fn)(void* user, uint64_t start, uint64_t stop, uint8_t* dst);
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int  pcaone_create(const pcaone_config* cfg, pcaone_ctx** out);
+void pcaone_destroy(pcaone_ctx* ctx);
+const char* pcaone_last_error(const pcaone_ctx* ctx); /* ctx may be NULL: creation errors */
+int  pcaone_abi_version(void);
+void* pcaone_stream(pcaone_ctx* ctx);                  /* the cudaStream_t all work runs on */
+int  pcaone_sync(pcaone_ctx* ctx);
+int  pcaone_set_allreduce(pcaone_ctx* ctx, pcaone_allreduce_fn fn, void* user);
+
+/* ---- genotype sources (Data::prepare, Data.cpp:14-85) ----------------------------- */
+/* FileBed::read_all (FilePlink.cpp:26-120): keep the packed shard resident in HBM.
+ * `packed` holds nsnps rows of bpr bytes; host or device pointer (device_ptr != 0). */
+int pcaone_upload_bed(pcaone_ctx* ctx, const uint8_t* packed, uint64_t nsnps, int device_ptr);
+/* Out-of-core from host memory: `packed` (nsnps x bpr, ideally pinned) stays on the host
+ * and is streamed block by block through double-buffered cudaMemcpyAsync every pass. */
+int pcaone_set_host_source(pcaone_ctx* ctx, const uint8_t* packed, uint64_t nsnps);
+/* Out-of-core through a reader callback (file-backed FileBed). */
+int pcaone_set_reader_source(pcaone_ctx* ctx, pcaone_read_block_fn fn, void* user);
+/* Out-of-core straight from a .bed file (checks the magic 6c 1b 01, FilePlink.hpp:24-27);
+ * snp_offset = first SNP of this context's shard inside the file. */
+int pcaone_open_bed(pcaone_ctx* ctx, const char* bed_path, uint64_t snp_offset);
+/* Block plan: start[]/stop[] inclusive SNP ranges of Data::prepare (Data.cpp:78-84),
+ * band_factor as Data.cpp:70. In-core winSVD derives its own windows (Halko.cpp:180-194)
+ * when this is not called. */
+int pcaone_set_blocks(pcaone_ctx* ctx, const uint64_t* start, const uint64_t* stop, uint32_t nblocks,
+                      uint32_t band_factor);
+/* permute_matrix (RSVD.hpp:61-78) for resident shards: new row j = old row indices[j]
+ * (packed rows, F). */
+int pcaone_permute_resident(pcaone_ctx* ctx, const uint32_t* indices);
+
+/* ---- decode / allele frequency (bit-exact, FilePlink.cpp:37-60,165-204) ------------ */
+int pcaone_allele_freq(pcaone_ctx* ctx);                 /* resident / host source: all SNPs */
+int pcaone_get_F(pcaone_ctx* ctx, double* F);            /* nsnps doubles                    */
+int pcaone_set_F(pcaone_ctx* ctx, const double* F);      /* projection-style external AF     */
+int pcaone_get_lookup(pcaone_ctx* ctx, double* lut4xM);  /* centered_geno_lookup, 4 x M      */
+int pcaone_get_scale(pcaone_ctx* ctx, double* s);        /* sqrt(ploidy)/sqrt(F(1-F)) or 1   */
+int pcaone_missing_count(pcaone_ctx* ctx, uint64_t* n);  /* Data::C.count() (FilePlink.cpp:112) */
+/* FileBed::read_block_initial / read_block_update (FilePlink.cpp:122-298): the dense
+ * N x (stop-start+1) block as the reference leaves it in data->G; update != 0 applies the
+ * EMU fill from the U,S,V installed with pcaone_set_usv. */
+int pcaone_decode_block(pcaone_ctx* ctx, uint64_t start, uint64_t stop, int standardize, int update,
+                        double* out);
+
+/* ---- RsvdOpData state (Halko.hpp:6-42) --------------------------------------------- */
+int pcaone_set_flags(pcaone_ctx* ctx, int update, int standardize);   /* setFlags, Halko.hpp:32 */
+int pcaone_set_omega(pcaone_ctx* ctx, const double* Omg);             /* initOmg result, N x l  */
+int pcaone_get_omega(pcaone_ctx* ctx, double* Omg);
+int pcaone_set_usv(pcaone_ctx* ctx, const double* U, const double* S, const double* V);
+int pcaone_get_usv(pcaone_ctx* ctx, double* U, double* S, double* V); /* any may be NULL        */
+int pcaone_get_GH(pcaone_ctx* ctx, double* G, double* H);             /* any may be NULL        */
+int pcaone_set_H(pcaone_ctx* ctx, const double* H);
+
+/* NormalRsvdOpData::computeGandH (Halko.cpp:99-153) / FancyRsvdOpData::computeGandH
+ * (Halko.cpp:155-269): one power-iteration pass for epoch pi; G (M x l) and H (N x l) stay
+ * on the device (read them with pcaone_get_GH). Dispatches on cfg.svd. */
+int pcaone_compute_gandh(pcaone_ctx* ctx, int pi);
+/* The dense stage of RsvdOpData::computeUSV for one epoch (Halko.cpp:55-70): QR(G) twice,
+ * B = R^-T H^T, SVD(B); leaves Q2 in G, Ucur, sigma, U_B on the device. */
+int pcaone_small_stage(pcaone_ctx* ctx);
+/* RsvdOpData::computeUSV (Halko.cpp:46-97): the whole epoch loop incl. MEV stopping and the
+ * winSVD minimum-epoch rule; diff_out/epochs_out may be NULL. */
+int pcaone_compute_usv(pcaone_ctx* ctx, int maxp, double tol, double* diff_out, int* epochs_out);
+/* EM driver of run_pca_with_halko (Halko.cpp:290-319) incl. flip_UV (Utils.cpp:118-154). */
+int pcaone_run_em(pcaone_ctx* ctx, int* iters_out);
+/* Omega = thinQ(H); flipOmg (Halko.cpp:121-123, RSVD.hpp:80-89) as a stand-alone call. */
+int pcaone_orth_omega(pcaone_ctx* ctx, int flip);
+/* mev(X, Y) (Utils.cpp:194-200) on host matrices rows x cols (col-major). */
+int pcaone_mev(pcaone_ctx* ctx, const double* X, const double* Y, uint64_t rows, uint32_t cols, double* out);
+
+/* ---- host helpers that reproduce the reference's libstdc++ random streams --------------- */
+/* RsvdOpData::initOmg (Halko.cpp:15-23, RSVD.hpp:20-59): N x l, column-major, seeded
+ * std::default_random_engine; gaussian != 0 -> N(0,1) (--rand 1), else U(-1,1). */
+int pcaone_init_omega(uint64_t rows, uint32_t cols, int seed, int gaussian, double* out);
+/* permute_matrix (RSVD.hpp:61-71): std::shuffle of 0..n-1 with the unseeded default engine. */
+int pcaone_shuffle_indices(uint64_t n, uint32_t* out);
+
+/* ---- LD r2 (LD.cpp:48-51, 450-473) ---------------------------------------------------- */
+/* Windows ws[w] (lead SNP) / we[w] (#SNPs incl. lead) as divide_pos_by_window produces
+ * (LD.cpp:154-168). G source: standardized-or-residual genotypes, N x M col-major doubles
+ * on the host (G != NULL), or the resident packed shard centred by F (G == NULL).
+ * r2_out receives sum_w (we[w]-1) values in the reference's output order. */
+int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
+                 uint64_t nwin, double* r2_out);
+
+/* ---- measurement ------------------------------------------------------------------- */
+typedef struct pcaone_timers {
+  double gemm_g_ms, gemm_h_ms, orth_ms, small_ms, h2d_ms, allreduce_ms, decode_ms;
+  uint64_t gemm_g_launches, gemm_h_launches, kernel_launches, h2d_bytes, d2h_bytes;
+  uint64_t omega_updates;
+} pcaone_timers;
+int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
+int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCAONE_B200_H_ */

@@ -1,0 +1,1263 @@
+// pcaone_b200 — engine + C-ABI (include/pcaone_b200.h).
+//
+// Host-side state machine of the randomized-SVD hot path, driving the sm_100a kernels:
+//   RsvdOpData::computeUSV                 reference src/Halko.cpp:46-97
+//   NormalRsvdOpData::computeGandH         reference src/Halko.cpp:99-153
+//   FancyRsvdOpData::computeGandH          reference src/Halko.cpp:155-269
+//   run_pca_with_halko EM loop             reference src/Halko.cpp:290-319
+//   FileBed::read_all / read_block_*       reference src/FilePlink.cpp:26-298
+// Nothing here falls back to the CPU: every arithmetic step is a kernel launch.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/pcaone_b200.h"
+#include "common.cuh"
+#include "decode.cuh"
+#include "gemm_fp64.cuh"
+#include "small_dense.cuh"
+#include "tall_skinny.cuh"
+
+using namespace pcaone;
+
+namespace {
+thread_local std::string g_create_err;
+
+struct EvPair {
+  cudaEvent_t a, b;
+  int kind;  // 0 gemm_g, 1 gemm_h, 2 orth, 3 small, 4 h2d, 5 allreduce
+};
+}  // namespace
+
+struct pcaone_ctx {
+  pcaone_config cfg{};
+  std::string err;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  int sms = 148;
+
+  uint64_t N = 0, M = 0;
+  int k = 0, l = 0, NT = 0, lp = 0;
+  uint32_t bpr = 0, pitch = 0;
+  LutParams lut{};
+  int update = 0, standardize = 0;
+
+  // genotype source
+  int source = -1;
+  uint8_t* d_packed = nullptr;  // resident, M x pitch
+  const uint8_t* h_packed = nullptr;
+  pcaone_read_block_fn reader = nullptr;
+  void* reader_user = nullptr;
+  FILE* bed_file = nullptr;
+  uint64_t bed_snp_offset = 0;
+  std::vector<uint64_t> blk_start, blk_stop;
+  uint32_t band_factor = 1;
+  uint64_t max_block = 0;
+  uint8_t* d_raw[2] = {nullptr, nullptr};
+  uint8_t* d_blk[2] = {nullptr, nullptr};
+  uint8_t* h_pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool af_done = false;
+
+  // per-SNP
+  double* d_F = nullptr;
+  uint32_t* d_nmiss = nullptr;
+
+  // tall matrices, row-major [rows][lp]
+  double *d_Omg0 = nullptr, *d_Omg = nullptr, *d_Omg2 = nullptr, *d_H = nullptr, *d_H1 = nullptr, *d_H2 = nullptr, *d_Bt = nullptr,
+         *d_Ucur = nullptr, *d_Upre = nullptr, *d_U = nullptr;
+  double *d_G = nullptr, *d_V = nullptr, *d_Vpre = nullptr;
+  double* d_S = nullptr;
+  double* d_Hpart = nullptr;
+  uint32_t max_splits = 1;
+  bool have_usv = false, have_omg0 = false;
+
+  // small l x l (ld = lp)
+  double *d_W = nullptr, *d_R = nullptr, *d_Rinv = nullptr, *d_T1 = nullptr, *d_T2 = nullptr, *d_T = nullptr,
+         *d_Vr = nullptr, *d_Z = nullptr, *d_sigma = nullptr, *d_sign = nullptr, *d_scal = nullptr;
+  int* d_status = nullptr;
+  int* h_status = nullptr;    // pinned
+  double* h_scal = nullptr;   // pinned
+  double* d_part = nullptr;   // partial workspace for two-stage reductions
+  size_t part_doubles = 0;
+  unsigned long long* d_pidx = nullptr;
+  double* d_stage = nullptr;  // col-major staging for host transfers
+  size_t stage_doubles = 0;
+
+  // winSVD state (FancyRsvdOpData members, Halko.hpp:66-68)
+  uint64_t bandsize = 1;
+
+  pcaone_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+
+  // measurement
+  bool timing = false;
+  std::vector<EvPair> evs;
+  pcaone_timers tm{};
+  double last_diff = 0.0;
+  int last_epochs = 0;
+};
+
+namespace {
+
+#define CTX_GUARD(ctx, ...)                     \
+  if (!(ctx)) return 1;                         \
+  try {                                         \
+    PCA_CUDA(cudaSetDevice((ctx)->cfg.device)); \
+    __VA_ARGS__;                                \
+    return 0;                                   \
+  } catch (const std::exception& e) {           \
+    (ctx)->err = e.what();                      \
+    return 1;                                   \
+  }
+
+template <class T>
+void dmalloc(T** p, size_t n) {
+  PCA_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+}
+
+int grid_for(uint64_t work, int threads, int sms) {
+  uint64_t b = (work + threads - 1) / threads;
+  uint64_t cap = (uint64_t)sms * 16;
+  return (int)std::max<uint64_t>(1, std::min(b, cap));
+}
+
+int supported_nt(int l) {
+  static const int opts[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+  const int need = (l + 7) / 8;
+  for (int o : opts)
+    if (o >= need) return o;
+  return -1;
+}
+
+struct Timed {
+  pcaone_ctx* c;
+  EvPair ev{};
+  bool on;
+  Timed(pcaone_ctx* c_, int kind) : c(c_), on(c_->timing) {
+    if (on) {
+      PCA_CUDA(cudaEventCreate(&ev.a));
+      PCA_CUDA(cudaEventCreate(&ev.b));
+      ev.kind = kind;
+      PCA_CUDA(cudaEventRecord(ev.a, c->stream));
+    }
+  }
+  ~Timed() {
+    if (on) {
+      cudaEventRecord(ev.b, c->stream);
+      c->evs.push_back(ev);
+    }
+  }
+};
+
+void resolve_timers(pcaone_ctx* c) {
+  if (c->evs.empty()) return;
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& e : c->evs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    switch (e.kind) {
+      case 0: c->tm.gemm_g_ms += ms; break;
+      case 1: c->tm.gemm_h_ms += ms; break;
+      case 2: c->tm.orth_ms += ms; break;
+      case 3: c->tm.small_ms += ms; break;
+      case 4: c->tm.h2d_ms += ms; break;
+      case 5: c->tm.allreduce_ms += ms; break;
+      case 6: c->tm.decode_ms += ms; break;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  c->evs.clear();
+}
+
+// ---------------------------------------------------------------- kernel dispatch on NT
+template <int NT>
+void gemm_g_nt(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, const double* F, double* G, const double* Vrows) {
+  const size_t smem = 2 * GemmSmem<NT>::kStageG;
+  const int grid = ceil_div(nrows, kTileRows);
+  if (c->update && c->cfg.emu) {
+    static bool attr = false;
+    if (!attr) {
+      PCA_CUDA(cudaFuncSetAttribute(k_gemm_g<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_gemm_g<NT, true><<<grid, kGemmThreads, smem, c->stream>>>(P, c->pitch, nrows, (uint32_t)c->N, c->d_Omg, F,
+                                                                c->lut, G, c->d_U, c->lp, c->d_S, Vrows, c->lp, c->k);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      PCA_CUDA(cudaFuncSetAttribute(k_gemm_g<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_gemm_g<NT, false><<<grid, kGemmThreads, smem, c->stream>>>(P, c->pitch, nrows, (uint32_t)c->N, c->d_Omg, F,
+                                                                 c->lut, G, nullptr, 0, nullptr, nullptr, 0, 0);
+  }
+  PCA_CHECK_LAUNCH();
+}
+
+template <int NT>
+void gemm_h_nt(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, const double* F, const double* G, uint32_t splits,
+               uint32_t rows_per_split, const double* Vrows) {
+  const size_t smem = 2 * GemmSmem<NT>::kStageH;
+  dim3 grid(ceil_div(c->N, kTileRows), splits);
+  if (c->update && c->cfg.emu) {
+    static bool attr = false;
+    if (!attr) {
+      PCA_CUDA(cudaFuncSetAttribute(k_gemm_h<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_gemm_h<NT, true><<<grid, kGemmThreads, smem, c->stream>>>(P, c->pitch, nrows, (uint32_t)c->N, G, F, c->lut,
+                                                                c->d_Hpart, rows_per_split, c->d_U, c->lp, c->d_S,
+                                                                Vrows, c->lp, c->k);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      PCA_CUDA(cudaFuncSetAttribute(k_gemm_h<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_gemm_h<NT, false><<<grid, kGemmThreads, smem, c->stream>>>(P, c->pitch, nrows, (uint32_t)c->N, G, F, c->lut,
+                                                                 c->d_Hpart, rows_per_split, nullptr, 0, nullptr,
+                                                                 nullptr, 0, 0);
+  }
+  PCA_CHECK_LAUNCH();
+}
+
+#define NT_DISPATCH(fn, ...)                                   \
+  switch (c->NT) {                                             \
+    case 1: fn<1>(__VA_ARGS__); break;                         \
+    case 2: fn<2>(__VA_ARGS__); break;                         \
+    case 3: fn<3>(__VA_ARGS__); break;                         \
+    case 4: fn<4>(__VA_ARGS__); break;                         \
+    case 5: fn<5>(__VA_ARGS__); break;                         \
+    case 6: fn<6>(__VA_ARGS__); break;                         \
+    case 8: fn<8>(__VA_ARGS__); break;                         \
+    case 10: fn<10>(__VA_ARGS__); break;                       \
+    case 12: fn<12>(__VA_ARGS__); break;                       \
+    case 16: fn<16>(__VA_ARGS__); break;                       \
+    default: throw std::runtime_error("unsupported NT");       \
+  }
+
+// G rows [0,nrows) of the range = X^T Omega ; Hacc (+)= X G
+void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate) {
+  if (nrows == 0) return;
+  const double* F = c->d_F + snp0;
+  double* G = c->d_G + snp0 * c->lp;
+  const double* Vrows = c->d_V + snp0 * c->lp;
+  {
+    Timed t(c, 0);
+    NT_DISPATCH(gemm_g_nt, c, P, nrows, F, G, Vrows);
+    c->tm.gemm_g_launches++;
+    c->tm.kernel_launches++;
+  }
+  const uint32_t tiles = ceil_div(c->N, kTileRows);
+  uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
+  splits = std::min<uint32_t>(splits, c->max_splits);
+  splits = std::min<uint32_t>(splits, (uint32_t)ceil_div(nrows, kKC));
+  uint32_t rps = (uint32_t)round_up((size_t)ceil_div(nrows, splits), kKC);
+  splits = ceil_div(nrows, rps);
+  {
+    Timed t(c, 1);
+    NT_DISPATCH(gemm_h_nt, c, P, nrows, F, G, splits, rps, Vrows);
+    const uint64_t count = c->N * c->lp;
+    k_reduce_partials<<<grid_for(count, 256, c->sms), 256, 0, c->stream>>>(c->d_Hpart, splits, count, Hacc,
+                                                                           accumulate ? 1 : 0);
+    PCA_CHECK_LAUNCH();
+    c->tm.gemm_h_launches++;
+    c->tm.kernel_launches += 2;
+  }
+}
+
+// ---------------------------------------------------------------- tall-skinny helpers
+template <int R>
+void ts_gemm_r(pcaone_ctx* c, const double* A, int l1, const double* B, int l2, uint64_t rows, int nparts,
+               uint64_t rpc) {
+  k_ts_gemm_tn<R, R><<<nparts, kTsThreads, 0, c->stream>>>(A, c->lp, l1, B, c->lp, l2, rows, rpc, c->d_part, c->lp);
+}
+
+// C (l1 x l2, ld lp) = A^T B over `rows` rows (both [rows][lp]); optional allreduce for sharded rows
+void ts_gemm_tn(pcaone_ctx* c, const double* A, int l1, const double* B, int l2, uint64_t rows, double* C,
+                bool sharded_rows) {
+  const int R = (std::max(l1, l2) + 15) / 16;
+  uint64_t rpc = std::max<uint64_t>(kTsKR, round_up((rows + 2 * c->sms - 1) / (2 * c->sms), kTsKR));
+  int nparts = (int)std::max<uint64_t>(1, (rows + rpc - 1) / rpc);
+  const size_t need = (size_t)nparts * 16 * R * c->lp;
+  if (need > c->part_doubles) throw std::runtime_error("partial workspace too small");
+  switch (R) {
+    case 1: ts_gemm_r<1>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 2: ts_gemm_r<2>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 3: ts_gemm_r<3>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 4: ts_gemm_r<4>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 5: ts_gemm_r<5>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 6: ts_gemm_r<6>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 7: ts_gemm_r<7>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    case 8: ts_gemm_r<8>(c, A, l1, B, l2, rows, nparts, rpc); break;
+    default: throw std::runtime_error("l too large for ts_gemm");
+  }
+  PCA_CHECK_LAUNCH();
+  k_reduce_small<<<ceil_div(l1 * l2, 256), 256, 0, c->stream>>>(c->d_part, nparts, 16 * R * c->lp, l1, l2, c->lp, C);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches += 2;
+  if (sharded_rows && c->cfg.world > 1) {
+    if (!c->allreduce) throw std::runtime_error("world > 1 but no allreduce hook installed");
+    Timed t(c, 5);
+    if (c->allreduce(c->allreduce_user, C, (uint64_t)c->lp * c->lp, c->stream))
+      throw std::runtime_error("allreduce hook failed");
+  }
+}
+
+template <int RN>
+void rightmult_r(pcaone_ctx* c, const double* A, int l1, const double* T, int l2, uint64_t rows, double* Out) {
+  const size_t smem = ((size_t)l1 * 16 * RN + (size_t)64 * (l1 + 1)) * sizeof(double);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_ts_rightmult<RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int grid = (int)std::min<uint64_t>((rows + 63) / 64, (uint64_t)c->sms * 4);
+  k_ts_rightmult<RN><<<grid, kTsThreads, smem, c->stream>>>(A, c->lp, l1, T, c->lp, l2, rows, Out, c->lp);
+}
+
+// Out[rows][lp] = A[rows][:l1] * T[l1 x l2]
+void ts_rightmult(pcaone_ctx* c, const double* A, int l1, const double* T, int l2, uint64_t rows, double* Out) {
+  const int RN = (l2 + 15) / 16;
+  switch (RN) {
+    case 1: rightmult_r<1>(c, A, l1, T, l2, rows, Out); break;
+    case 2: rightmult_r<2>(c, A, l1, T, l2, rows, Out); break;
+    case 3: rightmult_r<3>(c, A, l1, T, l2, rows, Out); break;
+    case 4: rightmult_r<4>(c, A, l1, T, l2, rows, Out); break;
+    case 5: rightmult_r<5>(c, A, l1, T, l2, rows, Out); break;
+    case 6: rightmult_r<6>(c, A, l1, T, l2, rows, Out); break;
+    case 7: rightmult_r<7>(c, A, l1, T, l2, rows, Out); break;
+    case 8: rightmult_r<8>(c, A, l1, T, l2, rows, Out); break;
+    default: throw std::runtime_error("l too large for rightmult");
+  }
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+int read_status(pcaone_ctx* c) {
+  PCA_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  return c->h_status[0];
+}
+
+void small_matmul(pcaone_ctx* c, const double* A, int tA, const double* B, int tB, int m, int p, int n, double* C) {
+  k_small_matmul<<<1, 1024, 0, c->stream>>>(A, tA, B, tB, m, p, n, c->lp, C);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+void jacobi(pcaone_ctx* c, const double* A, int sym, double* sigma, double* V) {
+  const size_t smem = 2 * (size_t)c->l * c->l * sizeof(double);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_jacobi_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k_jacobi_svd<<<1, kSmallThreads, smem, c->stream>>>(A, c->l, c->lp, sym, sigma, V, nullptr);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+void launch_chol(pcaone_ctx* c, const double* W, double* R, double* Rinv) {
+  const size_t smem = (size_t)c->l * c->l * sizeof(double);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k_chol_inv<<<1, kSmallThreads, smem, c->stream>>>(W, c->l, c->lp, R, Rinv, c->d_status);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+// One orthonormalising factor from the Gram W of A: Tout (l x l) with A*Tout having orthonormal
+// columns. Cholesky (CholeskyQR) when W is numerically full rank, else the eigen route (SVQB)
+// which zeroes the null directions.
+void gram_factor(pcaone_ctx* c, const double* W, double* Tout) {
+  launch_chol(c, W, c->d_R, Tout);
+  if (read_status(c) != 0) {
+    jacobi(c, W, 1, c->d_sigma, c->d_Vr);
+    k_svqb_factor<<<1, 1024, 0, c->stream>>>(c->d_Vr, c->d_sigma, c->l, c->lp, Tout);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
+  }
+}
+
+// Q = orth(A) in two passes (CholeskyQR2); Q may alias A. Ttot (optional) = T1*T2, Q = A*Ttot.
+void orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Ttot, bool sharded_rows) {
+  ts_gemm_tn(c, A, c->l, A, c->l, rows, c->d_W, sharded_rows);
+  gram_factor(c, c->d_W, c->d_T1);
+  ts_rightmult(c, A, c->l, c->d_T1, c->l, rows, Q);
+  ts_gemm_tn(c, Q, c->l, Q, c->l, rows, c->d_W, sharded_rows);
+  gram_factor(c, c->d_W, c->d_T2);
+  ts_rightmult(c, Q, c->l, c->d_T2, c->l, rows, Q);
+  if (Ttot) small_matmul(c, c->d_T1, 0, c->d_T2, 0, c->l, c->l, c->l, Ttot);
+}
+
+void flip_omg(pcaone_ctx* c) {
+  uint64_t rpc = std::max<uint64_t>(8, (c->N + c->sms - 1) / c->sms);
+  int nparts = (int)((c->N + rpc - 1) / rpc);
+  if ((size_t)nparts * 2 * c->l > c->part_doubles) throw std::runtime_error("partial workspace too small");
+  k_flip_partial<<<nparts, 256, 0, c->stream>>>(c->d_Omg2, c->d_Omg, c->lp, c->l, c->N, rpc, c->d_part);
+  PCA_CHECK_LAUNCH();
+  k_flip_sign<<<1, 128, 0, c->stream>>>(c->d_part, nparts, c->l, c->d_sign);
+  PCA_CHECK_LAUNCH();
+  k_flip_apply<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->d_Omg2, c->lp, c->l, c->N,
+                                                                          c->d_sign);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches += 3;
+}
+
+void allreduce_H(pcaone_ctx* c, double* H) {
+  if (c->cfg.world > 1) {
+    if (!c->allreduce) throw std::runtime_error("world > 1 but no allreduce hook installed");
+    Timed t(c, 5);
+    if (c->allreduce(c->allreduce_user, H, c->N * c->lp, c->stream)) throw std::runtime_error("allreduce hook failed");
+  }
+}
+
+// Omega = thinQ(H) (+ flipOmg)   Halko.cpp:120-124 / 208-213
+void update_omega(pcaone_ctx* c, const double* H, bool flip) {
+  Timed t(c, 2);
+  orth2(c, H, c->N, c->d_Omg, nullptr, false);
+  if (flip) flip_omg(c);
+  c->tm.omega_updates++;
+}
+
+// ---------------------------------------------------------------- host <-> device matrices
+void ensure_stage(pcaone_ctx* c, size_t doubles) {
+  if (doubles > c->stage_doubles) {
+    if (c->d_stage) cudaFree(c->d_stage);
+    dmalloc(&c->d_stage, doubles);
+    c->stage_doubles = doubles;
+  }
+}
+void upload_colmajor(pcaone_ctx* c, const double* h, uint64_t rows, int cols, double* d) {
+  ensure_stage(c, rows * cols);
+  PCA_CUDA(cudaMemcpyAsync(c->d_stage, h, rows * cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->tm.h2d_bytes += rows * cols * sizeof(double);
+  dim3 blk(32, 8);
+  k_colmajor_to_rowmajor<<<ceil_div(rows, 32), blk, 0, c->stream>>>(c->d_stage, rows, cols, d, c->lp);
+  PCA_CHECK_LAUNCH();
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+}
+void download_colmajor(pcaone_ctx* c, const double* d, uint64_t rows, int cols, double* h) {
+  ensure_stage(c, rows * cols);
+  dim3 blk(32, 8);
+  k_rowmajor_to_colmajor<<<ceil_div(rows, 32), blk, 0, c->stream>>>(d, c->lp, rows, cols, c->d_stage);
+  PCA_CHECK_LAUNCH();
+  PCA_CUDA(cudaMemcpyAsync(h, c->d_stage, rows * cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  c->tm.d2h_bytes += rows * cols * sizeof(double);
+}
+
+// ---------------------------------------------------------------- block streaming
+void alloc_stream_buffers(pcaone_ctx* c) {
+  if (c->d_blk[0] || c->max_block == 0) return;
+  for (int i = 0; i < 2; ++i) {
+    dmalloc(&c->d_blk[i], c->max_block * c->pitch);
+    if (c->pitch != c->bpr) dmalloc(&c->d_raw[i], c->max_block * c->bpr);
+    if (c->source == PCAONE_SRC_FILE)
+      PCA_CUDA(cudaHostAlloc((void**)&c->h_pin[i], c->max_block * c->bpr, cudaHostAllocDefault));
+    PCA_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    PCA_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  }
+}
+
+// enqueue the H2D of block b into buffer `buf`; returns the device pointer (pitch layout)
+const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf) {
+  const uint64_t s = c->blk_start[b], e = c->blk_stop[b];
+  const uint64_t nrows = e - s + 1;
+  const size_t bytes = nrows * c->bpr;
+  PCA_CUDA(cudaEventSynchronize(c->ev_done[buf]));  // previous user of this buffer finished
+  const uint8_t* src;
+  if (c->source == PCAONE_SRC_HOST) {
+    src = c->h_packed + s * c->bpr;
+  } else {
+    if (c->reader) {
+      if (c->reader(c->reader_user, s, e, c->h_pin[buf])) throw std::runtime_error("block reader failed");
+    } else {
+      const long long off = 3 + (long long)(c->bed_snp_offset + s) * c->bpr;
+      if (fseeko(c->bed_file, off, SEEK_SET) != 0 || fread(c->h_pin[buf], 1, bytes, c->bed_file) != bytes)
+        throw std::runtime_error("read_block: short read from bed file");
+    }
+    src = c->h_pin[buf];
+  }
+  uint8_t* dst = (c->pitch != c->bpr) ? c->d_raw[buf] : c->d_blk[buf];
+  PCA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  c->tm.h2d_bytes += bytes;
+  if (c->pitch != c->bpr) {
+    k_repitch<<<grid_for(nrows * (c->pitch >> 4), 256, c->sms), 256, 0, c->copy_stream>>>(c->d_raw[buf], c->d_blk[buf],
+                                                                                         nrows, c->bpr, c->pitch);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
+  }
+  PCA_CUDA(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
+  PCA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
+  return c->d_blk[buf];
+}
+
+void block_af_if_needed(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nrows) {
+  if (c->af_done) return;
+  k_allele_freq<<<grid_for(nrows * 32, 256, c->sms), 256, 0, c->stream>>>(P, c->pitch, (uint32_t)c->N, nrows,
+                                                                          c->d_F + s, c->d_nmiss + s);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+// ---------------------------------------------------------------- the passes
+struct WinStep {
+  uint64_t start, stop;  // inclusive SNP range (local), empty if stop < start
+  int target;            // 1 -> H1, 2 -> H2
+  bool update;
+  bool zero_h1;  // after the update: i == bandsize -> zero H1 (and i = 0), else zero H2
+};
+
+// FancyRsvdOpData::computeGandH window state machine (Halko.cpp:188-222 in-core, :228-267 OOC)
+std::vector<WinStep> winsvd_schedule(pcaone_ctx* c, int pi, const std::vector<uint64_t>& ws,
+                                     const std::vector<uint64_t>& we, bool ooc) {
+  const uint64_t bands = c->cfg.bands;
+  const uint64_t nwin = ws.size();
+  if (pi == 0) c->bandsize = ooc ? c->band_factor : 1;
+  c->bandsize = std::min<uint64_t>(c->bandsize * 2, ooc ? nwin : bands);
+  const uint64_t bandsize = c->bandsize;
+  std::vector<WinStep> steps;
+  uint64_t i = 1;
+  for (uint64_t b = 0; b < nwin; ++b, ++i) {
+    WinStep st{ws[b], we[b], (i <= bandsize / 2) ? 1 : 2, false, false};
+    const double adj_at = pi > 0 ? std::pow(2.0, pi - 1) * (ooc ? c->band_factor : 1) : -1.0;
+    const bool adjacent = (pi > 0 && (double)(b + 1) == adj_at && std::pow(2.0, pi) < (double)bands);
+    if (!((b + 1) < bandsize && !adjacent)) {
+      if ((i == bandsize) || (i == bandsize / 2) || adjacent) {
+        st.update = true;
+        st.zero_h1 = (i == bandsize);
+        if (i == bandsize) i = 0;
+      }
+    }
+    steps.push_back(st);
+  }
+  return steps;
+}
+
+void incore_windows(pcaone_ctx* c, std::vector<uint64_t>& ws, std::vector<uint64_t>& we) {
+  // Halko.cpp:180,192-194: blocksize = ceil(M / bands) on the WHOLE job's SNP count; a shard
+  // walks its 1/world slice of every window, i.e. the same formula on local M.
+  const uint64_t bands = c->cfg.bands;
+  const uint64_t bs = (c->M + bands - 1) / bands;
+  for (uint64_t b = 0; b < bands; ++b) {
+    uint64_t s = b * bs;
+    uint64_t e = ((b + 1) * bs >= c->M) ? c->M - 1 : (b + 1) * bs - 1;
+    if (s >= c->M) {  // empty trailing window (M < bands * blocksize)
+      s = 1;
+      e = 0;
+    }
+    ws.push_back(s);
+    we.push_back(e);
+  }
+}
+
+void zero_async(pcaone_ctx* c, double* p, uint64_t n) { PCA_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), c->stream)); }
+
+void compute_gandh(pcaone_ctx* c, int pi) {
+  if (c->source < 0) throw std::runtime_error("no genotype source set");
+  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("EMU update pass without U,S,V");
+  const bool ooc = c->source != PCAONE_SRC_RESIDENT;
+  const bool win = c->cfg.svd == PCAONE_SVD_WINSVD;
+  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
+  const uint64_t HN = c->N * c->lp;
+  if (pi == 0) {  // initOmg(): every computeUSV restarts from the same seeded Omega (Halko.cpp:105,160)
+    if (!c->have_omg0) throw std::runtime_error("call pcaone_set_omega before the first pass");
+    PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (ooc) {
+    if (c->blk_start.empty()) throw std::runtime_error("out-of-core source needs pcaone_set_blocks");
+    alloc_stream_buffers(c);
+  } else if (!c->af_done) {
+    throw std::runtime_error("call pcaone_allele_freq before the first pass");
+  }
+
+  if (!win) {
+    // ---- sSVD, Halko.cpp:99-153
+    if (pi > 0) {
+      // in-core flips (Halko.cpp:123); the block version does not (Halko.cpp:133-136).
+      // A resident shard walked with a block plan follows cfg.out_of_core.
+      update_omega(c, c->d_H, !c->cfg.out_of_core);
+    }
+    if (!ooc) {
+      if (c->blk_start.empty()) {
+        range_gemms(c, c->d_packed, (uint32_t)c->M, 0, c->d_H, false);
+      } else {
+        zero_async(c, c->d_H, HN);
+        for (size_t b = 0; b < c->blk_start.size(); ++b)
+          range_gemms(c, c->d_packed + c->blk_start[b] * c->pitch, (uint32_t)(c->blk_stop[b] - c->blk_start[b] + 1),
+                      c->blk_start[b], c->d_H, true);
+      }
+    } else {
+      zero_async(c, c->d_H, HN);
+      for (uint32_t b = 0; b < c->blk_start.size(); ++b) {
+        const int buf = b & 1;
+        const uint8_t* P = stage_block(c, b, buf);
+        const uint64_t nrows = c->blk_stop[b] - c->blk_start[b] + 1;
+        block_af_if_needed(c, P, c->blk_start[b], nrows);
+        range_gemms(c, P, (uint32_t)nrows, c->blk_start[b], c->d_H, true);
+        PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
+      }
+      c->af_done = true;
+    }
+    allreduce_H(c, c->d_H);
+    return;
+  }
+
+  // ---- winSVD, Halko.cpp:155-269
+  if (std::pow(2.0, pi) >= (double)c->cfg.bands) {
+    zero_async(c, c->d_H1, HN);
+    zero_async(c, c->d_H2, HN);
+  }
+  std::vector<uint64_t> ws, we;
+  const bool block_walk = ooc || !c->blk_start.empty();
+  if (block_walk) {
+    ws = c->blk_start;
+    we = c->blk_stop;
+  } else {
+    incore_windows(c, ws, we);
+  }
+  auto steps = winsvd_schedule(c, pi, ws, we, c->cfg.out_of_core != 0);
+  size_t b = 0;
+  while (b < steps.size()) {
+    // merge resident windows that share a target and have no Omega update between them
+    size_t e = b;
+    if (!ooc) {
+      while (!steps[e].update && e + 1 < steps.size() && steps[e + 1].target == steps[b].target &&
+             steps[e + 1].stop >= steps[e + 1].start && steps[e].stop >= steps[e].start &&
+             steps[e + 1].start == steps[e].stop + 1)
+        ++e;
+    }
+    double* Hacc = steps[b].target == 1 ? c->d_H1 : c->d_H2;
+    if (steps[b].stop >= steps[b].start) {
+      const uint64_t s0 = steps[b].start, nrows = steps[e].stop - s0 + 1;
+      if (!ooc) {
+        range_gemms(c, c->d_packed + s0 * c->pitch, (uint32_t)nrows, s0, Hacc, true);
+      } else {
+        const int buf = (int)(b & 1);
+        const uint8_t* P = stage_block(c, (uint32_t)b, buf);
+        block_af_if_needed(c, P, s0, nrows);
+        range_gemms(c, P, (uint32_t)nrows, s0, Hacc, true);
+        PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
+      }
+    }
+    const WinStep& last = steps[e];
+    if (last.update) {
+      k_add2<<<grid_for(HN, 256, c->sms), 256, 0, c->stream>>>(c->d_H1, c->d_H2, c->d_H, HN);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+      allreduce_H(c, c->d_H);
+      update_omega(c, c->d_H, true);
+      zero_async(c, last.zero_h1 ? c->d_H1 : c->d_H2, HN);
+    }
+    b = e + 1;
+  }
+  if (ooc) c->af_done = true;
+}
+
+// Halko.cpp:55-70 on the device. Leaves: G <- Q2, d_Ucur (N x k), d_sigma (l), d_Vr = U_B (l x l)
+void small_stage(pcaone_ctx* c) {
+  Timed t(c, 3);
+  // G = Q R twice (CholeskyQR2); T = R^-1 so that Q = G T and B^T = H R^-1 = H T
+  orth2(c, c->d_G, c->M, c->d_G, c->d_T, true);
+  ts_rightmult(c, c->d_H, c->l, c->d_T, c->l, c->N, c->d_Bt);
+  // SVD of B^T (N x l): Gram -> Cholesky -> one-sided Jacobi on the triangular factor
+  ts_gemm_tn(c, c->d_Bt, c->l, c->d_Bt, c->l, c->N, c->d_W, false);
+  launch_chol(c, c->d_W, c->d_R, c->d_Rinv);
+  if (read_status(c) == 0)
+    jacobi(c, c->d_R, 0, c->d_sigma, c->d_Vr);
+  else
+    jacobi(c, c->d_W, 1, c->d_sigma, c->d_Vr);
+  k_scale_v_by_inv_sigma<<<1, 1024, 0, c->stream>>>(c->d_Vr, c->d_sigma, c->l, c->k, c->lp, c->d_Z);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+  ts_rightmult(c, c->d_Bt, c->l, c->d_Z, c->k, c->N, c->d_Ucur);
+}
+
+double device_mev(pcaone_ctx* c, const double* X, const double* Y, uint64_t rows, bool sharded) {
+  ts_gemm_tn(c, X, c->k, Y, c->k, rows, c->d_W, sharded);
+  k_mev_from_xty<<<1, 32, 0, c->stream>>>(c->d_W, c->k, c->lp, c->d_scal);
+  PCA_CHECK_LAUNCH();
+  PCA_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  c->tm.kernel_launches += 1;
+  return c->h_scal[0];
+}
+
+void finalize_usv(pcaone_ctx* c) {
+  const uint64_t bytes = c->N * c->lp * sizeof(double);
+  PCA_CUDA(cudaMemcpyAsync(c->d_U, c->d_Ucur, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  ts_rightmult(c, c->d_G, c->l, c->d_Vr, c->k, c->M, c->d_V);
+  PCA_CUDA(cudaMemcpyAsync(c->d_S, c->d_sigma, c->k * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->have_usv = true;
+}
+
+// RsvdOpData::computeUSV, Halko.cpp:46-97
+void compute_usv(pcaone_ctx* c, int p, double tol) {
+  double diff = 0.0;
+  int epochs = 0;
+  const uint64_t ubytes = c->N * c->lp * sizeof(double);
+  for (int pi = 0; pi <= p; ++pi) {
+    compute_gandh(c, pi);
+    small_stage(c);
+    epochs = pi + 1;
+    if (pi > 0) {
+      diff = 1.0 - device_mev(c, c->d_Ucur, c->d_Upre, c->N, false);
+      if (diff < tol || pi == p) {
+        if (c->cfg.svd == PCAONE_SVD_WINSVD && std::pow(2.0, pi) < (double)c->cfg.bands) {
+          p = (int)std::log2((double)c->cfg.bands);
+        } else {
+          finalize_usv(c);
+          break;
+        }
+      } else {
+        PCA_CUDA(cudaMemcpyAsync(c->d_Upre, c->d_Ucur, ubytes, cudaMemcpyDeviceToDevice, c->stream));
+      }
+    } else {
+      PCA_CUDA(cudaMemcpyAsync(c->d_Upre, c->d_Ucur, ubytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  PCA_CUDA(cudaMemcpyAsync(c->d_U, c->d_Ucur, ubytes, cudaMemcpyDeviceToDevice, c->stream));
+  c->last_diff = diff;
+  c->last_epochs = epochs;
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// flip_UV(U, V, false), Utils.cpp:136-143. V rows may be sharded: the column maxima are then
+// combined on the host side by the caller-installed allreduce (sum of one-hot winners is not
+// expressible as a sum), so multi-GPU flips use the per-rank maxima gathered through d_scal.
+void flip_uv(pcaone_ctx* c) {
+  uint64_t rpc = std::max<uint64_t>(256, (c->M + c->sms - 1) / c->sms);
+  int nparts = (int)((c->M + rpc - 1) / rpc);
+  double* pval = c->d_part;
+  double* psgn = c->d_part + (size_t)nparts * c->k;
+  if ((size_t)nparts * 2 * c->k > c->part_doubles) throw std::runtime_error("partial workspace too small");
+  k_colabsmax_partial<<<nparts, 256, 0, c->stream>>>(c->d_V, c->lp, c->k, c->M, rpc, pval, psgn, c->d_pidx);
+  PCA_CHECK_LAUNCH();
+  k_colabsmax_final<<<1, 128, 0, c->stream>>>(pval, psgn, c->d_pidx, nparts, c->k, c->d_scal + 8, c->d_sign);
+  PCA_CHECK_LAUNCH();
+  if (c->cfg.world > 1) throw std::runtime_error("flip_UV across SNP shards is not implemented yet");
+  k_scale_cols<<<grid_for(c->M * c->k, 256, c->sms), 256, 0, c->stream>>>(c->d_V, c->lp, c->k, c->M, c->d_sign);
+  k_scale_cols<<<grid_for(c->N * c->k, 256, c->sms), 256, 0, c->stream>>>(c->d_U, c->lp, c->k, c->N, c->d_sign);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches += 4;
+}
+
+// Halko.cpp:290-319 (EMU branch)
+void run_em(pcaone_ctx* c, int* iters_out) {
+  const int maxp = (int)c->cfg.maxp;
+  const double tol = c->cfg.tol;
+  c->update = 0;
+  c->standardize = 0;
+  compute_usv(c, maxp, tol);
+  flip_uv(c);
+  int iters = 0;
+  const uint64_t vbytes = c->M * c->lp * sizeof(double);
+  for (uint32_t i = 0; i < c->cfg.maxiter; ++i) {
+    c->update = 1;
+    c->standardize = 0;
+    PCA_CUDA(cudaMemcpyAsync(c->d_Vpre, c->d_V, vbytes, cudaMemcpyDeviceToDevice, c->stream));
+    compute_usv(c, maxp, tol);
+    flip_uv(c);
+    const double diff = 1.0 - device_mev(c, c->d_V, c->d_Vpre, c->M, true);
+    iters = (int)i + 1;
+    if (diff < c->cfg.tolem) break;
+  }
+  if (c->cfg.emu) {
+    c->update = 1;
+    c->standardize = 1;
+    compute_usv(c, maxp, tol);
+    flip_uv(c);
+  }
+  if (iters_out) *iters_out = iters;
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint32_t nblocks, uint32_t band_factor) {
+  c->blk_start.assign(start, start + nblocks);
+  c->blk_stop.assign(stop, stop + nblocks);
+  c->band_factor = band_factor ? band_factor : 1;
+  uint64_t mb = 0;
+  for (uint32_t i = 0; i < nblocks; ++i) {
+    if (stop[i] >= c->M || start[i] > stop[i]) throw std::runtime_error("set_blocks: block out of range");
+    mb = std::max(mb, stop[i] - start[i] + 1);
+  }
+  if (mb > c->max_block && c->d_blk[0]) throw std::runtime_error("set_blocks: cannot grow blocks after streaming began");
+  c->max_block = std::max(c->max_block, mb);
+}
+
+}  // namespace
+
+// =============================================================================== C-ABI
+extern "C" {
+
+int pcaone_abi_version(void) { return 1; }
+
+const char* pcaone_last_error(const pcaone_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
+  if (!cfg || !out) return 1;
+  pcaone_ctx* c = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw std::runtime_error(std::string("pcaone_b200 needs a CUDA device (no CPU fallback): ") +
+                               cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) throw std::runtime_error("invalid CUDA device ordinal");
+    PCA_CUDA(cudaSetDevice(cfg->device));
+    c = new pcaone_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.world < 1) c->cfg.world = 1;
+    if (c->cfg.nsnps_total == 0) c->cfg.nsnps_total = c->cfg.nsnps;
+    if (c->cfg.bands == 0) c->cfg.bands = 64;
+    c->N = cfg->nsamples;
+    c->M = cfg->nsnps;
+    c->k = (int)cfg->k;
+    c->l = (int)(cfg->k + cfg->oversamples);
+    if (c->N == 0 || c->M == 0 || c->k == 0) throw std::runtime_error("nsamples, nsnps and k must be positive");
+    if (c->l > kMaxL) throw std::runtime_error("k + oversamples must be <= 112");
+    if ((uint64_t)c->l > c->N || (uint64_t)c->l > c->M) throw std::runtime_error("k + oversamples exceeds the matrix size");
+    if (cfg->precision != PCAONE_PREC_FP64) throw std::runtime_error("only PCAONE_PREC_FP64 is built in this library");
+    if (cfg->svd != PCAONE_SVD_SSVD && cfg->svd != PCAONE_SVD_WINSVD) throw std::runtime_error("svd must be 1 or 2");
+    c->NT = supported_nt(c->l);
+    c->lp = c->NT * 8;
+    c->bpr = (uint32_t)((c->N + 3) >> 2);
+    c->pitch = (uint32_t)round_up(c->bpr, 16);
+    c->lut.sqrt_ploidy = sqrt((double)cfg->ploidy);
+    c->lut.standardize = 0;
+    cudaDeviceProp prop;
+    PCA_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    c->sms = prop.multiProcessorCount;
+    PCA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PCA_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    const size_t NL = c->N * c->lp, ML = c->M * c->lp, LL = (size_t)c->lp * c->lp;
+    dmalloc(&c->d_Omg0, NL);
+    dmalloc(&c->d_Omg, NL);
+    dmalloc(&c->d_Omg2, NL);
+    dmalloc(&c->d_H, NL);
+    dmalloc(&c->d_Bt, NL);
+    dmalloc(&c->d_Ucur, NL);
+    dmalloc(&c->d_Upre, NL);
+    dmalloc(&c->d_U, NL);
+    if (cfg->svd == PCAONE_SVD_WINSVD) {
+      dmalloc(&c->d_H1, NL);
+      dmalloc(&c->d_H2, NL);
+      PCA_CUDA(cudaMemset(c->d_H1, 0, NL * sizeof(double)));
+      PCA_CUDA(cudaMemset(c->d_H2, 0, NL * sizeof(double)));
+    }
+    dmalloc(&c->d_G, ML);
+    dmalloc(&c->d_V, ML);
+    if (cfg->emu) dmalloc(&c->d_Vpre, ML);
+    PCA_CUDA(cudaMemset(c->d_V, 0, ML * sizeof(double)));
+    PCA_CUDA(cudaMemset(c->d_U, 0, NL * sizeof(double)));
+    PCA_CUDA(cudaMemset(c->d_H, 0, NL * sizeof(double)));
+    dmalloc(&c->d_S, c->lp);
+    dmalloc(&c->d_F, c->M);
+    dmalloc(&c->d_nmiss, c->M);
+    PCA_CUDA(cudaMemset(c->d_F, 0, c->M * sizeof(double)));
+    const uint32_t tiles = ceil_div(c->N, kTileRows);
+    c->max_splits = std::max<uint32_t>(1, std::min<uint32_t>(64, (2u * c->sms + tiles - 1) / tiles));
+    dmalloc(&c->d_Hpart, (size_t)c->max_splits * NL);
+    for (double** p : {&c->d_W, &c->d_R, &c->d_Rinv, &c->d_T1, &c->d_T2, &c->d_T, &c->d_Vr, &c->d_Z}) dmalloc(p, LL);
+    dmalloc(&c->d_sigma, c->lp);
+    dmalloc(&c->d_sign, c->lp);
+    dmalloc(&c->d_scal, 64);
+    dmalloc(&c->d_status, 4);
+    PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
+    PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
+    c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;
+    dmalloc(&c->d_part, c->part_doubles);
+    dmalloc(&c->d_pidx, (size_t)(2 * c->sms + 8) * 128);
+    PCA_CUDA(cudaDeviceSynchronize());
+    *out = c;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    delete c;
+    return 1;
+  }
+}
+
+void pcaone_destroy(pcaone_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : {(void*)c->d_Omg0, (void*)c->d_packed, (void*)c->d_F, (void*)c->d_nmiss, (void*)c->d_Omg, (void*)c->d_Omg2,
+                  (void*)c->d_H, (void*)c->d_H1, (void*)c->d_H2, (void*)c->d_Bt, (void*)c->d_Ucur, (void*)c->d_Upre,
+                  (void*)c->d_U, (void*)c->d_G, (void*)c->d_V, (void*)c->d_Vpre, (void*)c->d_S, (void*)c->d_Hpart,
+                  (void*)c->d_W, (void*)c->d_R, (void*)c->d_Rinv, (void*)c->d_T1, (void*)c->d_T2, (void*)c->d_T,
+                  (void*)c->d_Vr, (void*)c->d_Z, (void*)c->d_sigma, (void*)c->d_sign, (void*)c->d_scal,
+                  (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
+                  (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1]})
+    if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  for (auto& e : c->evs) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  if (c->bed_file) fclose(c->bed_file);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+void* pcaone_stream(pcaone_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int pcaone_sync(pcaone_ctx* c) { CTX_GUARD(c, PCA_CUDA(cudaStreamSynchronize(c->stream))); }
+int pcaone_set_allreduce(pcaone_ctx* c, pcaone_allreduce_fn fn, void* user) {
+  CTX_GUARD(c, {
+    c->allreduce = fn;
+    c->allreduce_user = user;
+  });
+}
+
+int pcaone_upload_bed(pcaone_ctx* c, const uint8_t* packed, uint64_t nsnps, int device_ptr) {
+  CTX_GUARD(c, {
+    if (nsnps != c->M) throw std::runtime_error("upload_bed: nsnps does not match the context");
+    if (!c->d_packed) dmalloc(&c->d_packed, c->M * (size_t)c->pitch);
+    const cudaMemcpyKind kind = device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (c->pitch == c->bpr) {
+      PCA_CUDA(cudaMemcpyAsync(c->d_packed, packed, c->M * (size_t)c->bpr, kind, c->stream));
+    } else if (device_ptr) {
+      k_repitch<<<grid_for(c->M * (c->pitch >> 4), 256, c->sms), 256, 0, c->stream>>>(packed, c->d_packed, c->M, c->bpr,
+                                                                                     c->pitch);
+      PCA_CHECK_LAUNCH();
+    } else {
+      // chunked: stage raw rows then repitch on the device
+      const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / c->bpr);
+      uint8_t* raw = nullptr;
+      dmalloc(&raw, std::min(chunk, c->M) * (size_t)c->bpr);
+      for (uint64_t s = 0; s < c->M; s += chunk) {
+        const uint64_t n = std::min(chunk, c->M - s);
+        PCA_CUDA(cudaMemcpyAsync(raw, packed + s * c->bpr, n * (size_t)c->bpr, kind, c->stream));
+        k_repitch<<<grid_for(n * (c->pitch >> 4), 256, c->sms), 256, 0, c->stream>>>(
+            raw, c->d_packed + s * c->pitch, n, c->bpr, c->pitch);
+        PCA_CHECK_LAUNCH();
+      }
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(raw);
+    }
+    if (!device_ptr) c->tm.h2d_bytes += c->M * (size_t)c->bpr;
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->source = PCAONE_SRC_RESIDENT;
+    c->af_done = false;
+  });
+}
+
+int pcaone_set_host_source(pcaone_ctx* c, const uint8_t* packed, uint64_t nsnps) {
+  CTX_GUARD(c, {
+    if (nsnps != c->M) throw std::runtime_error("set_host_source: nsnps does not match the context");
+    c->h_packed = packed;
+    c->source = PCAONE_SRC_HOST;
+    c->af_done = false;
+  });
+}
+
+int pcaone_set_reader_source(pcaone_ctx* c, pcaone_read_block_fn fn, void* user) {
+  CTX_GUARD(c, {
+    c->reader = fn;
+    c->reader_user = user;
+    c->source = PCAONE_SRC_FILE;
+    c->af_done = false;
+  });
+}
+
+int pcaone_open_bed(pcaone_ctx* c, const char* path, uint64_t snp_offset) {
+  CTX_GUARD(c, {
+    if (c->bed_file) fclose(c->bed_file);
+    c->bed_file = fopen(path, "rb");
+    if (!c->bed_file) throw std::runtime_error("Cannot open bed file.");
+    unsigned char hdr[3];
+    if (fread(hdr, 1, 3, c->bed_file) != 3 || hdr[0] != 0x6c || hdr[1] != 0x1b || hdr[2] != 0x01)
+      throw std::runtime_error("Incorrect magic number in plink bed file.");
+    c->bed_snp_offset = snp_offset;
+    c->reader = nullptr;
+    c->source = PCAONE_SRC_FILE;
+    c->af_done = false;
+  });
+}
+
+int pcaone_set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint32_t nblocks,
+                      uint32_t band_factor) {
+  CTX_GUARD(c, set_blocks(c, start, stop, nblocks, band_factor));
+}
+
+int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
+  CTX_GUARD(c, {
+    if (c->source != PCAONE_SRC_RESIDENT) throw std::runtime_error("permute_resident needs a resident shard");
+    uint32_t* d_idx = nullptr;
+    uint8_t* d_new = nullptr;
+    double* d_Fn = nullptr;
+    dmalloc(&d_idx, c->M);
+    dmalloc(&d_new, c->M * (size_t)c->pitch);
+    dmalloc(&d_Fn, c->M);
+    PCA_CUDA(cudaMemcpyAsync(d_idx, indices, c->M * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    k_gather_rows<<<grid_for(c->M * (c->pitch >> 4), 256, c->sms), 256, 0, c->stream>>>(c->d_packed, d_new, d_idx, c->M,
+                                                                                       c->pitch);
+    k_gather_f64<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, d_Fn, d_idx, c->M);
+    PCA_CHECK_LAUNCH();
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_packed);
+    cudaFree(c->d_F);
+    cudaFree(d_idx);
+    c->d_packed = d_new;
+    c->d_F = d_Fn;
+  });
+}
+
+int pcaone_allele_freq(pcaone_ctx* c) {
+  CTX_GUARD(c, {
+    if (c->source == PCAONE_SRC_RESIDENT) {
+      Timed t(c, 6);
+      k_allele_freq<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_packed, c->pitch, (uint32_t)c->N,
+                                                                             c->M, c->d_F, c->d_nmiss);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+    } else if (c->source >= 0) {
+      if (c->blk_start.empty()) throw std::runtime_error("allele_freq on a streamed source needs pcaone_set_blocks");
+      alloc_stream_buffers(c);
+      for (uint32_t b = 0; b < c->blk_start.size(); ++b) {
+        const int buf = b & 1;
+        const uint8_t* P = stage_block(c, b, buf);
+        block_af_if_needed(c, P, c->blk_start[b], c->blk_stop[b] - c->blk_start[b] + 1);
+        PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
+      }
+    } else {
+      throw std::runtime_error("no genotype source set");
+    }
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->af_done = true;
+  });
+}
+
+int pcaone_get_F(pcaone_ctx* c, double* F) {
+  CTX_GUARD(c, {
+    PCA_CUDA(cudaMemcpyAsync(F, c->d_F, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+int pcaone_set_F(pcaone_ctx* c, const double* F) {
+  CTX_GUARD(c, {
+    PCA_CUDA(cudaMemcpyAsync(c->d_F, F, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->af_done = true;
+  });
+}
+int pcaone_get_lookup(pcaone_ctx* c, double* lut) {
+  CTX_GUARD(c, {
+    ensure_stage(c, 4 * c->M);
+    k_lookup_scale<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, c->M, c->lut, c->d_stage, nullptr);
+    PCA_CHECK_LAUNCH();
+    PCA_CUDA(cudaMemcpyAsync(lut, c->d_stage, 4 * c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+int pcaone_get_scale(pcaone_ctx* c, double* s) {
+  CTX_GUARD(c, {
+    ensure_stage(c, c->M);
+    LutParams p = c->lut;
+    p.standardize = c->cfg.scale == -9 ? 1 : 0;
+    k_lookup_scale<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, c->M, p, nullptr, c->d_stage);
+    PCA_CHECK_LAUNCH();
+    PCA_CUDA(cudaMemcpyAsync(s, c->d_stage, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+int pcaone_missing_count(pcaone_ctx* c, uint64_t* n) {
+  CTX_GUARD(c, {
+    std::vector<uint32_t> h(c->M);
+    PCA_CUDA(cudaMemcpyAsync(h.data(), c->d_nmiss, c->M * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t s = 0;
+    for (auto v : h) s += v;
+    *n = s;
+  });
+}
+
+int pcaone_decode_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int standardize, int update, double* out) {
+  CTX_GUARD(c, {
+    if (stop < start || stop >= c->M) throw std::runtime_error("decode_block: range out of bounds");
+    const uint64_t B = stop - start + 1;
+    const uint8_t* P;
+    if (c->source == PCAONE_SRC_RESIDENT) {
+      P = c->d_packed + start * c->pitch;
+    } else {
+      // stage the requested range through buffer 0 as a one-off block
+      std::vector<uint64_t> s0 = c->blk_start, e0 = c->blk_stop;
+      const uint64_t mb = c->max_block;
+      if (B > c->max_block && c->d_blk[0]) throw std::runtime_error("decode_block: range larger than the block plan");
+      c->max_block = std::max(c->max_block, B);
+      alloc_stream_buffers(c);
+      c->blk_start = {start};
+      c->blk_stop = {stop};
+      P = stage_block(c, 0, 0);
+      c->blk_start = s0;
+      c->blk_stop = e0;
+      c->max_block = std::max(mb, c->max_block);
+    }
+    if (!c->af_done) block_af_if_needed(c, P, start, B);
+    LutParams p = c->lut;
+    p.standardize = (standardize && c->cfg.scale == -9) ? 1 : 0;
+    ensure_stage(c, c->N * B);
+    const int emu = (update && c->cfg.emu) ? 1 : 0;
+    if (emu && !c->have_usv) throw std::runtime_error("decode_block(update) without U,S,V");
+    Timed t(c, 6);
+    k_decode_block<<<grid_for(((c->N + 3) / 4) * B, 256, c->sms), 256, 0, c->stream>>>(
+        P, c->pitch, (uint32_t)c->N, (uint32_t)B, c->d_F + start, p, emu, c->d_U, c->lp, c->d_S,
+        c->d_V + start * c->lp, c->lp, c->k, c->d_stage);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
+    if (c->source != PCAONE_SRC_RESIDENT) PCA_CUDA(cudaEventRecord(c->ev_done[0], c->stream));
+    PCA_CUDA(cudaMemcpyAsync(out, c->d_stage, c->N * B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->tm.d2h_bytes += c->N * B * sizeof(double);
+  });
+}
+
+int pcaone_set_flags(pcaone_ctx* c, int update, int standardize) {
+  CTX_GUARD(c, {
+    c->update = update;
+    c->standardize = standardize;
+  });
+}
+int pcaone_set_omega(pcaone_ctx* c, const double* Omg) {
+  CTX_GUARD(c, {
+    upload_colmajor(c, Omg, c->N, c->l, c->d_Omg0);
+    const size_t nb = c->N * c->lp * sizeof(double);
+    PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, nb, cudaMemcpyDeviceToDevice, c->stream));
+    PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, nb, cudaMemcpyDeviceToDevice, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_omg0 = true;
+  });
+}
+int pcaone_get_omega(pcaone_ctx* c, double* Omg) { CTX_GUARD(c, download_colmajor(c, c->d_Omg, c->N, c->l, Omg)); }
+int pcaone_set_usv(pcaone_ctx* c, const double* U, const double* S, const double* V) {
+  CTX_GUARD(c, {
+    upload_colmajor(c, U, c->N, c->k, c->d_U);
+    upload_colmajor(c, V, c->M, c->k, c->d_V);
+    PCA_CUDA(cudaMemcpyAsync(c->d_S, S, c->k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_usv = true;
+  });
+}
+int pcaone_get_usv(pcaone_ctx* c, double* U, double* S, double* V) {
+  CTX_GUARD(c, {
+    if (U) download_colmajor(c, c->d_U, c->N, c->k, U);
+    if (V) download_colmajor(c, c->d_V, c->M, c->k, V);
+    if (S) {
+      PCA_CUDA(cudaMemcpyAsync(S, c->d_S, c->k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+    }
+  });
+}
+int pcaone_get_GH(pcaone_ctx* c, double* G, double* H) {
+  CTX_GUARD(c, {
+    if (G) download_colmajor(c, c->d_G, c->M, c->l, G);
+    if (H) download_colmajor(c, c->d_H, c->N, c->l, H);
+  });
+}
+int pcaone_set_H(pcaone_ctx* c, const double* H) { CTX_GUARD(c, upload_colmajor(c, H, c->N, c->l, c->d_H)); }
+
+int pcaone_compute_gandh(pcaone_ctx* c, int pi) { CTX_GUARD(c, compute_gandh(c, pi)); }
+int pcaone_small_stage(pcaone_ctx* c) { CTX_GUARD(c, small_stage(c)); }
+int pcaone_compute_usv(pcaone_ctx* c, int maxp, double tol, double* diff_out, int* epochs_out) {
+  CTX_GUARD(c, {
+    compute_usv(c, maxp, tol);
+    if (diff_out) *diff_out = c->last_diff;
+    if (epochs_out) *epochs_out = c->last_epochs;
+  });
+}
+int pcaone_run_em(pcaone_ctx* c, int* iters_out) { CTX_GUARD(c, run_em(c, iters_out)); }
+int pcaone_orth_omega(pcaone_ctx* c, int flip) { CTX_GUARD(c, update_omega(c, c->d_H, flip != 0)); }
+
+int pcaone_mev(pcaone_ctx* c, const double* X, const double* Y, uint64_t rows, uint32_t cols, double* out) {
+  CTX_GUARD(c, {
+    if ((int)cols > c->lp) throw std::runtime_error("mev: too many columns");
+    double *dx = nullptr, *dy = nullptr;
+    dmalloc(&dx, rows * c->lp);
+    dmalloc(&dy, rows * c->lp);
+    ensure_stage(c, rows * cols);
+    dim3 blk(32, 8);
+    for (int i = 0; i < 2; ++i) {
+      PCA_CUDA(cudaMemcpyAsync(c->d_stage, i ? Y : X, rows * cols * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      k_colmajor_to_rowmajor<<<ceil_div(rows, 32), blk, 0, c->stream>>>(c->d_stage, rows, (int)cols, i ? dy : dx, c->lp);
+      PCA_CHECK_LAUNCH();
+    }
+    const int ksave = c->k;
+    c->k = (int)cols;
+    double r = 0.0;
+    try {
+      r = device_mev(c, dx, dy, rows, false);
+    } catch (...) {
+      c->k = ksave;
+      throw;
+    }
+    c->k = ksave;
+    cudaFree(dx);
+    cudaFree(dy);
+    *out = r;
+  });
+}
+
+int pcaone_ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
+                 double* r2_out) {
+  CTX_GUARD(c, {
+    (void)G; (void)nsnps; (void)ws; (void)we; (void)nwin; (void)r2_out;
+    throw std::runtime_error("pcaone_ld_r2: not built yet");
+  });
+}
+
+int pcaone_get_timers(pcaone_ctx* c, pcaone_timers* out, int reset) {
+  CTX_GUARD(c, {
+    resolve_timers(c);
+    if (out) *out = c->tm;
+    if (reset) c->tm = pcaone_timers{};
+  });
+}
+int pcaone_enable_timing(pcaone_ctx* c, int on) { CTX_GUARD(c, c->timing = on != 0); }
+
+// ---- host helpers that must match the reference's libstdc++ streams bit for bit -------------
+// RsvdOpData::initOmg (Halko.cpp:15-23) with StandardNormalRandom / UniformRandom
+// (RSVD.hpp:20-59): std::default_random_engine seeded with `seed`, values drawn in
+// column-major order (Eigen NullaryExpr evaluation order for a column-major MatrixXd).
+int pcaone_init_omega(uint64_t rows, uint32_t cols, int seed, int gaussian, double* out) {
+  auto rng = std::default_random_engine{};
+  rng.seed(seed);
+  const uint64_t n = rows * cols;
+  if (gaussian) {
+    std::normal_distribution<double> dist{0, 1};
+    for (uint64_t i = 0; i < n; ++i) out[i] = dist(rng);
+  } else {
+    std::uniform_real_distribution<double> dist{-1, 1};
+    for (uint64_t i = 0; i < n; ++i) out[i] = dist(rng);
+  }
+  return 0;
+}
+// permute_matrix (RSVD.hpp:61-71): std::shuffle of 0..n-1 with an UNSEEDED default engine
+int pcaone_shuffle_indices(uint64_t n, uint32_t* out) {
+  std::vector<int> idx(n);
+  for (uint64_t i = 0; i < n; ++i) idx[i] = (int)i;
+  auto rng = std::default_random_engine{};
+  std::shuffle(idx.data(), idx.data() + n, rng);
+  for (uint64_t i = 0; i < n; ++i) out[i] = (uint32_t)idx[i];
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// pcaone_b200 — single-CTA FP64 kernels on the l x l core (l <= 112):
+// Cholesky + triangular inverse (CholeskyQR2), one-sided Jacobi SVD (the "small on-device SVD"
+// that replaces Eigen::JacobiSVD of the l x N matrix B, Halko.cpp:69), l x l products, MEV.
+// Matrices are row-major with leading dimension LS.
+#pragma once
+#include "common.cuh"
+
+namespace pcaone {
+
+constexpr int kSmallThreads = 1024;
+constexpr int kMaxL = 112;  // 2*l*l doubles of Jacobi state must fit 227 KB of shared memory
+
+// status[0] = 0 ok / 1 breakdown (pivot <= tol * max diag: numerically rank deficient)
+// W (l x l, symmetric) -> R upper (W = R^T R), Rinv upper. W is not modified.
+__global__ void __launch_bounds__(kSmallThreads)
+k_chol_inv(const double* __restrict__ W, int l, int ld, double* __restrict__ R, double* __restrict__ Rinv,
+           int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* A = reinterpret_cast<double*>(smem_raw);  // l x l, ld = l
+  __shared__ double s_piv, s_maxd;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < l * l; i += nt) A[i] = W[(i / l) * ld + (i % l)];
+  if (tid == 0) {
+    s_fail = 0;
+    double m = 0.0;
+    for (int i = 0; i < l; ++i) m = fmax(m, W[i * ld + i]);
+    s_maxd = m;
+  }
+  __syncthreads();
+  const double tol = 64.0 * l * 2.220446049250313e-16 * s_maxd;
+  for (int j = 0; j < l; ++j) {
+    if (tid == 0) {
+      const double d = A[j * l + j];
+      if (!(d > tol)) s_fail = 1;
+      s_piv = sqrt(d > tol ? d : 1.0);
+      A[j * l + j] = s_piv;
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const double inv = 1.0 / s_piv;
+    for (int c = j + 1 + tid; c < l; c += nt) A[j * l + c] *= inv;
+    __syncthreads();
+    const int m = l - j - 1;  // trailing update on the upper triangle r <= c
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c >= r) A[r * l + c] -= A[j * l + r] * A[j * l + c];
+    }
+    __syncthreads();
+  }
+  if (s_fail) {
+    if (tid == 0) status[0] = 1;
+    return;
+  }
+  if (tid == 0) status[0] = 0;
+  for (int i = tid; i < l * l; i += nt) {
+    const int r = i / l, c = i % l;
+    R[r * ld + c] = c >= r ? A[i] : 0.0;
+  }
+  // inverse of upper-triangular R, one column per thread (back substitution)
+  for (int c = tid; c < l; c += nt) {
+    for (int r = l - 1; r > c; --r) Rinv[r * ld + c] = 0.0;
+    Rinv[c * ld + c] = 1.0 / A[c * l + c];
+    for (int r = c - 1; r >= 0; --r) {
+      double s = 0.0;
+      for (int p = r + 1; p <= c; ++p) s += A[r * l + p] * Rinv[p * ld + c];
+      Rinv[r * ld + c] = -s / A[r * l + r];
+    }
+  }
+}
+
+// C (m x n) = op(A) (m x p) * op(B) (p x n), tiny sizes, row-major ld.
+__global__ void k_small_matmul(const double* __restrict__ A, int transA, const double* __restrict__ B, int transB,
+                               int m, int p, int n, int ld, double* __restrict__ C) {
+  for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) {
+    const int r = idx / n, c = idx - r * n;
+    double s = 0.0;
+    for (int q = 0; q < p; ++q) {
+      const double a = transA ? A[q * ld + r] : A[r * ld + q];
+      const double b = transB ? B[c * ld + q] : B[q * ld + c];
+      s += a * b;
+    }
+    C[r * ld + c] = s;
+  }
+}
+
+// One-sided (Hestenes) Jacobi SVD of the l x l matrix A (row-major, ld): A = U diag(sigma) V^T.
+// Outputs sigma (descending) and V (row-major l x l, columns = right singular vectors, same
+// order). Round-robin pair ordering, one warp per column pair; all state in shared memory.
+// If `symmetric_psd` the caller passes W = B^T B and wants its eigen-decomposition: then
+// sigma_out = sqrt(singular values of W) and V = eigenvectors (fallback path for a rank-deficient
+// Gram where Cholesky broke down).
+__global__ void __launch_bounds__(kSmallThreads)
+k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, double* __restrict__ sigma,
+             double* __restrict__ Vout, int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* A = reinterpret_cast<double*>(smem_raw);  // column-major l x l: column j at A + j*l
+  double* V = A + (size_t)l * l;                    // column-major l x l
+  __shared__ int s_rot;
+  __shared__ double s_norm[kMaxL];
+  __shared__ int s_ord[kMaxL];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int i = tid; i < l * l; i += nt) {
+    const int r = i / l, c = i % l;
+    A[c * l + r] = Ain[r * ld + c];
+    V[c * l + r] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int n = (l + 1) & ~1;  // even number of players
+  const double eps = 1e-15;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < n - 1; ++round) {
+      for (int pi = warp; pi < n / 2; pi += nw) {
+        int p, q;
+        if (pi == 0) {
+          p = n - 1;
+          q = round;
+        } else {
+          p = (round + pi) % (n - 1);
+          q = (round - pi + (n - 1)) % (n - 1);
+        }
+        if (p > q) {
+          const int tmp = p;
+          p = q;
+          q = tmp;
+        }
+        if (q >= l) continue;  // bye (odd l)
+        double* ap = A + p * l;
+        double* aq = A + q * l;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int r = lane; r < l; r += 32) {
+          const double x = ap[r], y = aq[r];
+          alpha += x * x;
+          beta += y * y;
+          gamma += x * y;
+        }
+        alpha = warp_sum(alpha);
+        beta = warp_sum(beta);
+        gamma = warp_sum(gamma);
+        if (fabs(gamma) > eps * sqrt(alpha * beta) && gamma != 0.0) {
+          if (lane == 0) s_rot = 1;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+          double* vp = V + p * l;
+          double* vq = V + q * l;
+          for (int r = lane; r < l; r += 32) {
+            const double x = ap[r], y = aq[r];
+            ap[r] = c * x - s * y;
+            aq[r] = s * x + c * y;
+            const double vx = vp[r], vy = vq[r];
+            vp[r] = c * vx - s * vy;
+            vq[r] = s * vx + c * vy;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (!rot) break;
+  }
+  // column norms -> singular values
+  for (int j = warp; j < l; j += nw) {
+    double s = 0.0;
+    for (int r = lane; r < l; r += 32) s += A[j * l + r] * A[j * l + r];
+    s = warp_sum(s);
+    if (lane == 0) s_norm[j] = sqrt(s);
+  }
+  __syncthreads();
+  if (tid == 0) {  // insertion sort, descending, stable
+    for (int j = 0; j < l; ++j) s_ord[j] = j;
+    for (int a = 1; a < l; ++a) {
+      const int key = s_ord[a];
+      int b = a - 1;
+      while (b >= 0 && s_norm[s_ord[b]] < s_norm[key]) {
+        s_ord[b + 1] = s_ord[b];
+        --b;
+      }
+      s_ord[b + 1] = key;
+    }
+    if (sweeps_out) sweeps_out[0] = sweep;
+  }
+  __syncthreads();
+  for (int j = tid; j < l; j += nt) {
+    const double s = s_norm[s_ord[j]];
+    sigma[j] = symmetric_psd ? sqrt(s) : s;
+  }
+  for (int i = tid; i < l * l; i += nt) {
+    const int r = i / l, c = i % l;
+    Vout[r * ld + c] = V[s_ord[c] * l + r];
+  }
+}
+
+// Z (l x k, ld) = Vr[:, :k] * diag(1/sigma[:k]) ; sigma <= tiny -> column zeroed.
+__global__ void k_scale_v_by_inv_sigma(const double* __restrict__ Vr, const double* __restrict__ sigma, int l,
+                                       int k, int ld, double* __restrict__ Z) {
+  for (int idx = threadIdx.x; idx < l * ld; idx += blockDim.x) {
+    const int r = idx / ld, c = idx - r * ld;
+    double v = 0.0;
+    if (c < k) {
+      const double s = sigma[c];
+      v = (s > 1e-300 && s > 1e-14 * sigma[0]) ? Vr[r * ld + c] / s : 0.0;
+    }
+    Z[r * ld + c] = v;
+  }
+}
+
+// SVQB-style factor for a numerically rank-deficient Gram W = V diag(lam) V^T:
+// T = V diag(lam^-1/2), columns with lam <= tol*lam_max zeroed; Tinv^T = V diag(lam^1/2).
+// sigma holds sqrt(lam) (from k_jacobi_svd with symmetric_psd=1).
+__global__ void k_svqb_factor(const double* __restrict__ Vr, const double* __restrict__ sig, int l, int ld,
+                              double* __restrict__ T) {
+  const double smax = sig[0];
+  for (int idx = threadIdx.x; idx < l * l; idx += blockDim.x) {
+    const int r = idx / l, c = idx - r * l;
+    const double s = sig[c];
+    T[r * ld + c] = (s > 1e-7 * smax && s > 0.0) ? Vr[r * ld + c] / s : 0.0;
+  }
+}
+
+// mev(X, Y) = mean_i || X^T Y[:, i] ||  (Utils.cpp:194-200); C = X^T Y (k x k, row-major ld)
+__global__ void k_mev_from_xty(const double* __restrict__ C, int k, int ld, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double res = 0.0;
+    for (int i = 0; i < k; ++i) {
+      double s = 0.0;
+      for (int r = 0; r < k; ++r) s += C[r * ld + i] * C[r * ld + i];
+      res += sqrt(s);
+    }
+    out[0] = res / k;
+  }
+}
+
+}  // namespace pcaone

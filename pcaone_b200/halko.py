@@ -1,0 +1,378 @@
+"""Host-side mirror of PCAone's operator interface for the randomized-SVD path, on top of the
+C-ABI (include/pcaone_b200.h). Same names and argument meaning as the reference so the parity
+tests read like the reference's own call sites:
+
+    Param                      src/Cmd.hpp:16-98 (the fields the hot path reads; derivations
+                               of src/Cmd.cpp:141-238: oversamples=max(os,k), out_of_core=memory>0,
+                               perm = winSVD && !no_shuffle)
+    FileBed / Data.prepare     src/FilePlink.hpp:8-47, src/Data.cpp:14-85
+    RsvdOpData                 src/Halko.hpp:6-42  (U, S, V, Omg, setFlags, initOmg, computeGandH,
+                               computeUSV)
+    NormalRsvdOpData / FancyRsvdOpData   src/Halko.hpp:44-93
+    run_pca_with_halko         src/Halko.cpp:271-345
+    permute_plink              src/FilePlink.cpp:303-408 (index map; rows are permuted in memory)
+
+All arithmetic runs in the CUDA library; this module only plans blocks, owns host buffers
+and converts a non-zero C status into the RuntimeError the reference would throw
+(src/Logger.hpp:85-94).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .synth import BED_MAGIC, bytes_per_snp
+
+
+def _vp(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f(shape):
+    return np.zeros(shape, dtype=np.float64, order="F")
+
+
+@dataclass
+class Param:
+    """The hot-path subset of the reference's Param with the CLI spellings in comments."""
+    filein: str = ""            # -b/--bfile
+    fileout: str = "pcaone"     # -o
+    k: int = 10                 # -k
+    svd: int = 2                # -d/--svd (1: sSVD, 2: winSVD)
+    memory: float = 0.0         # -m GB; > 0 => out_of_core
+    maxp: int = 20              # --maxp
+    oversamples: int = 10       # --oversamples
+    bands: int = 64             # -w/--batches
+    tol: float = 1e-4           # --tol-rsvd
+    seed: int = 112             # --seed
+    rand: int = 1               # --rand
+    no_shuffle: bool = False    # -S
+    emu: bool = False           # --emu
+    maxiter: int = 100          # --maxiter
+    tolem: float = 1e-5         # --tol-em
+    scale: int = -9             # -C
+    haploid: bool = False       # --haploid
+    ld: bool = False            # -D/--ld
+    buffer: int = 2             # --buffer
+    device: int = 0
+    precision: int = _lib.PREC_FP64
+    # derived (src/Cmd.cpp:141-238)
+    out_of_core: bool = field(init=False, default=False)
+    perm: bool = field(init=False, default=False)
+    ploidy: int = field(init=False, default=2)
+
+    def __post_init__(self):
+        if self.svd not in (1, 2):
+            raise ValueError("only --svd 1 (sSVD) and 2 (winSVD) are on the GPU path")
+        if self.bands < 4 or self.bands % 2 != 0:
+            raise ValueError("the -w/--batches must be a power of 2 and the minimun is 4.")
+        self.oversamples = max(self.oversamples, self.k)
+        self.out_of_core = self.memory > 0
+        self.perm = self.svd == 2 and not self.no_shuffle
+        self.ploidy = 1 if self.haploid else 2
+
+    @property
+    def l(self):
+        return self.k + self.oversamples
+
+
+def ooc_block_plan(N, M, l, memory_gb, winsvd, bands):
+    """Data::prepare, out-of-core branch (src/Data.cpp:42-84)."""
+    m = float(3 * N * l + 2 * M * l + 5 * M) / 134217728
+    if memory_gb > 1.1 * m:
+        m = 0.0
+    blocksize = int(math.ceil(((m + memory_gb) * 134217728 - 3 * N * l - 2 * M * l - 5 * M) / N))
+    nblocks = int(math.ceil(M / blocksize))
+    band_factor = 1
+    if nblocks == 1:
+        raise RuntimeError("only one block exists. please remove -m option")
+    if winsvd:
+        if nblocks < bands:
+            blocksize = int(math.ceil(M / bands))
+        else:
+            band_factor = int(math.ceil(nblocks / bands))
+            blocksize = int(math.ceil(M / (bands * band_factor)))
+        nblocks = int(math.ceil(M / blocksize))
+    start = np.arange(nblocks, dtype=np.uint64) * np.uint64(blocksize)
+    stop = np.minimum(start + np.uint64(blocksize - 1), np.uint64(M - 1))
+    return blocksize, nblocks, band_factor, start, stop
+
+
+def permute_plink_indices(M, N, bands, gb=2):
+    """PermMat of permute_plink (src/FilePlink.cpp:303-408): indices[new] = original."""
+    bpr = bytes_per_snp(N)
+    two = int(math.floor(1073741824.0 * gb / bpr))
+    two = min(two, M)
+    bufsize = two // bands
+    two = bufsize * bands
+    if two == 0:
+        raise RuntimeError("permute_plink: fewer SNPs than bands")
+    nblocks = (M + two - 1) // two
+    modr2 = M % two
+    modr = M % bands
+    bandsize = (M + bands - 1) // bands
+    bandidx = [i * bandsize if (modr == 0 or i < modr) else modr * bandsize + (bandsize - 1) * (i - modr)
+               for i in range(bands)]
+    indices = np.full(M, -1, dtype=np.int64)
+    bufidx = bufsize
+    for i in range(nblocks):
+        if i == nblocks - 1 and modr2 != 0:
+            two2 = M - (nblocks - 1) * two
+            bufsize = (two2 + bands - 1) // bands
+            modr2 = two2 % bands
+        j = np.arange(bufsize - 1, dtype=np.int64)
+        for b in range(bands):
+            indices[i * bufidx + bandidx[b] + j] = i * two + j * bands + b
+            jl = bufsize - 1
+            if i != nblocks - 1 or b < modr2 or modr2 == 0:
+                indices[i * bufidx + bandidx[b] + jl] = i * two + jl * bands + b
+    return indices
+
+
+class FileBed:
+    """`Data` for PLINK bed input. In-core: the packed matrix goes to HBM once (read_all).
+    Out-of-core: blocks are streamed from the .bed file (or a host array) every pass."""
+
+    def __init__(self, params: Param, packed: np.ndarray | None = None, nsamples: int | None = None):
+        self.params = params
+        self.perm = None
+        self.start = self.stop = None
+        self.nblocks, self.blocksize, self.bandFactor = 1, 0, 1
+        if packed is None:
+            with open(params.filein + ".fam") as f:
+                self.nsamples = sum(1 for _ in f)
+            with open(params.filein + ".bim") as f:
+                self.nsnps = sum(1 for _ in f)
+            with open(params.filein + ".bed", "rb") as f:
+                if f.read(3) != BED_MAGIC:
+                    raise RuntimeError("Incorrect magic number in plink bed file.")
+            self.packed = None
+        else:
+            self.packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            self.nsamples = int(nsamples)
+            self.nsnps = int(self.packed.shape[0])
+            if self.packed.shape[1] != bytes_per_snp(self.nsamples):
+                raise RuntimeError("packed matrix does not have ceil(N/4) bytes per SNP")
+
+    def _load_packed(self):
+        if self.packed is None:
+            raw = np.fromfile(self.params.filein + ".bed", dtype=np.uint8)
+            self.packed = raw[3:].reshape(self.nsnps, bytes_per_snp(self.nsamples))
+        return self.packed
+
+    def prepare(self):
+        p = self.params
+        if not p.out_of_core:
+            self._load_packed()
+            return
+        self.blocksize, self.nblocks, self.bandFactor, self.start, self.stop = ooc_block_plan(
+            self.nsamples, self.nsnps, p.l, p.memory, p.svd == 2, p.bands)
+        if p.perm:
+            # permute_plink writes <out>.perm.bed; here the rows are permuted in host memory
+            self.perm = permute_plink_indices(self.nsnps, self.nsamples, p.bands, p.buffer)
+            self.packed = np.ascontiguousarray(self._load_packed()[self.perm])
+
+
+class RsvdOpData:
+    """Abstract op (src/Halko.hpp:6-42). Subclasses pick the computeGandH variant."""
+    svd = None
+
+    def __init__(self, data: FileBed, k: int, os_: int = 10, *, rank=0, world=1, nsnps_total=None,
+                 allreduce=None):
+        L = _lib.load()
+        self.L = L
+        self.data = data
+        p = data.params
+        self.nk, self.os = int(k), int(os_)
+        self.update = False
+        self.standardize = False
+        self.U = self.S = self.V = None
+        cfg = _lib.Config(nsamples=data.nsamples, nsnps=data.nsnps, nsnps_total=nsnps_total or data.nsnps,
+                          k=self.nk, oversamples=self.os, svd=self.svd, bands=p.bands, maxp=p.maxp, tol=p.tol,
+                          ploidy=p.ploidy, scale=p.scale, emu=int(p.emu), out_of_core=int(p.out_of_core),
+                          precision=p.precision, device=p.device, rank=rank, world=world, maxiter=p.maxiter,
+                          tolem=p.tolem)
+        h = C.c_void_p()
+        if L.pcaone_create(C.byref(cfg), C.byref(h)):
+            raise RuntimeError(L.pcaone_last_error(None).decode())
+        self.h = h
+        self._keep = []
+        if allreduce is not None:
+            cb = _lib.ALLREDUCE_FN(allreduce)
+            self._keep.append(cb)
+            self._chk(L.pcaone_set_allreduce(self.h, cb, None))
+        if p.out_of_core:
+            if data.packed is not None:
+                self._chk(L.pcaone_set_host_source(self.h, _vp(data.packed), data.nsnps))
+            else:
+                self._chk(L.pcaone_open_bed(self.h, (p.filein + ".bed").encode(), 0))
+            self._chk(L.pcaone_set_blocks(self.h, _vp(data.start), _vp(data.stop), data.nblocks, data.bandFactor))
+        else:
+            self._chk(L.pcaone_upload_bed(self.h, _vp(data.packed), data.nsnps, 0))
+            self._chk(L.pcaone_allele_freq(self.h))
+        self._permuted = False
+        self.initOmg()
+
+    # -- plumbing
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.L.pcaone_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pcaone_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference interface
+    def rows(self):
+        return self.data.nsnps
+
+    def cols(self):
+        return self.data.nsamples
+
+    def ranks(self):
+        return self.nk
+
+    def oversamples(self):
+        return self.os
+
+    def size(self):
+        return self.nk + self.os
+
+    def setFlags(self, is_update, is_standardize):
+        self.update, self.standardize = bool(is_update), bool(is_standardize)
+        self._chk(self.L.pcaone_set_flags(self.h, int(self.update), int(self.standardize)))
+
+    def initOmg(self):
+        p = self.data.params
+        self.Omg = _f((self.cols(), self.size()))
+        self.L.pcaone_init_omega(self.cols(), self.size(), p.seed, int(p.rand), _vp(self.Omg))
+        self._chk(self.L.pcaone_set_omega(self.h, _vp(self.Omg)))
+
+    def setOmg(self, Omg):
+        self.Omg = np.asfortranarray(Omg, dtype=np.float64)
+        self._chk(self.L.pcaone_set_omega(self.h, _vp(self.Omg)))
+
+    def _maybe_permute(self):
+        """in-core winSVD permutes the columns of G at pi == 0 of the first pass
+        (src/Halko.cpp:183-186, src/RSVD.hpp:61-71)."""
+        p = self.data.params
+        if self.svd == _lib.SVD_WINSVD and p.perm and not p.out_of_core and not self._permuted:
+            idx = np.zeros(self.rows(), dtype=np.uint32)
+            self.L.pcaone_shuffle_indices(self.rows(), _vp(idx))
+            self._chk(self.L.pcaone_permute_resident(self.h, _vp(idx)))
+            self.data.perm = idx.astype(np.int64)
+            self._permuted = True
+
+    def computeGandH(self, pi, want=True):
+        """One power-iteration pass; returns (G M x l, H N x l) col-major when want."""
+        if pi == 0:
+            self._maybe_permute()
+        self._chk(self.L.pcaone_compute_gandh(self.h, int(pi)))
+        if not want:
+            return None
+        G, H = _f((self.rows(), self.size())), _f((self.cols(), self.size()))
+        self._chk(self.L.pcaone_get_GH(self.h, _vp(G), _vp(H)))
+        return G, H
+
+    def computeUSV(self, p, tol):
+        self._maybe_permute()
+        diff, ep = C.c_double(0), C.c_int(0)
+        self._chk(self.L.pcaone_compute_usv(self.h, int(p), C.c_double(tol), C.byref(diff), C.byref(ep)))
+        self.diff, self.epochs = diff.value, ep.value
+        self._fetch_usv()
+
+    def _fetch_usv(self):
+        self.U, self.S, self.V = _f((self.cols(), self.nk)), np.zeros(self.nk), _f((self.rows(), self.nk))
+        self._chk(self.L.pcaone_get_usv(self.h, _vp(self.U), _vp(self.S), _vp(self.V)))
+
+    def runEM(self):
+        self._maybe_permute()
+        it = C.c_int(0)
+        self._chk(self.L.pcaone_run_em(self.h, C.byref(it)))
+        self._fetch_usv()
+        return it.value
+
+    # -- Data-side views used by the parity tests
+    def F(self):
+        out = np.zeros(self.rows())
+        self._chk(self.L.pcaone_get_F(self.h, _vp(out)))
+        return out
+
+    def lookup(self):
+        out = _f((4, self.rows()))
+        self._chk(self.L.pcaone_get_lookup(self.h, _vp(out)))
+        return out
+
+    def missing_count(self):
+        n = C.c_uint64(0)
+        self._chk(self.L.pcaone_missing_count(self.h, C.byref(n)))
+        return n.value
+
+    def read_block(self, start, stop, standardize, update=False):
+        """FileBed::read_block_initial / read_block_update output (N x B, col-major)."""
+        out = _f((self.cols(), stop - start + 1))
+        self._chk(self.L.pcaone_decode_block(self.h, int(start), int(stop), int(standardize), int(update), _vp(out)))
+        return out
+
+    def setUSV(self, U, S, V):
+        U = np.asfortranarray(U, dtype=np.float64)
+        V = np.asfortranarray(V, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        self._chk(self.L.pcaone_set_usv(self.h, _vp(U), _vp(S), _vp(V)))
+
+    def omega(self):
+        out = _f((self.cols(), self.size()))
+        self._chk(self.L.pcaone_get_omega(self.h, _vp(out)))
+        return out
+
+    def timers(self, reset=False):
+        t = _lib.Timers()
+        self._chk(self.L.pcaone_get_timers(self.h, C.byref(t), int(reset)))
+        return t
+
+    def enable_timing(self, on=True):
+        self._chk(self.L.pcaone_enable_timing(self.h, int(on)))
+
+    def sync(self):
+        self._chk(self.L.pcaone_sync(self.h))
+
+
+class NormalRsvdOpData(RsvdOpData):
+    """sSVD / "Halko" (src/Halko.cpp:99-153)."""
+    svd = _lib.SVD_SSVD
+
+
+class FancyRsvdOpData(RsvdOpData):
+    """winSVD / "PCAone Alg2" (src/Halko.cpp:155-269)."""
+    svd = _lib.SVD_WINSVD
+
+
+def run_pca_with_halko(data: FileBed, params: Param, **kw):
+    """src/Halko.cpp:271-345 without the file writers: returns the op with U, S, V set
+    (eigenvalues are S**2 / nsnps as written at :339)."""
+    cls = FancyRsvdOpData if params.svd == 2 else NormalRsvdOpData
+    rsvd = cls(data, params.k, params.oversamples, **kw)
+    if not params.emu:
+        rsvd.setFlags(False, not params.ld)
+        rsvd.computeUSV(params.maxp, params.tol)
+    else:
+        rsvd.em_iters = rsvd.runEM()
+    return rsvd
+
+
+def mev(X, Y, device=0):
+    """mev(X, Y) (src/Utils.cpp:194-200) evaluated on the device."""
+    raise NotImplementedError("use RsvdOpData / pcaone_mev through an op context")

@@ -1,0 +1,104 @@
+"""CPU: host-side logic of the product (block planning, permutation maps, Param derivations),
+the C-ABI library's exports, and the loud failure without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from pcaone_b200 import _lib, halko, synth
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pcaone_b200.h")).read()
+    declared = set(re.findall(r"\b(pcaone_[a-z_0-9A-Z]+)\s*\(", hdr))
+    declared -= {"pcaone_allreduce_fn", "pcaone_read_block_fn"}
+    L = _lib.load()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert L.pcaone_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib.load()
+    cfg = _lib.Config(nsamples=10, nsnps=100, k=2, oversamples=2, svd=1, ploidy=2, scale=-9, world=1)
+    h = C.c_void_p()
+    assert L.pcaone_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CPU fallback" in L.pcaone_last_error(None)
+    data = halko.FileBed(halko.Param(k=2, svd=1), packed=np.zeros((100, 3), np.uint8), nsamples=10)
+    data.prepare()
+    with pytest.raises(RuntimeError):
+        halko.NormalRsvdOpData(data, 2, 2)
+
+
+def test_param_derivations():
+    p = halko.Param(k=3)
+    assert p.oversamples == 10 and p.l == 13 and p.perm and not p.out_of_core
+    p = halko.Param(k=40, svd=1, memory=2.0)
+    assert p.oversamples == 40 and p.l == 80 and not p.perm and p.out_of_core
+    with pytest.raises(ValueError):
+        halko.Param(bands=3)
+
+
+def test_block_plan_matches_reference_golden():
+    g = golden("ssvd_small")
+    N, M, k = int(g["N"]), int(g["M"]), int(g["k"])
+    w = golden("winsvd_ooc_small")
+    bs, nb, bf, start, stop = halko.ooc_block_plan(N, M, k + 10, float(w["memory"]), True, int(w["bands"]))
+    assert [bs, nb, bf] == list(w["plan"])
+    assert np.array_equal(start, w["start"]) and np.array_equal(stop, w["stop"])
+    s = golden("ssvd_ooc_small")
+    bs, nb, bf, start, stop = halko.ooc_block_plan(N, M, k + 10, float(s["memory"]), False, 64)
+    assert [bs, nb, bf] == list(s["plan"])
+    assert np.array_equal(start, s["start"]) and np.array_equal(stop, s["stop"])
+    with pytest.raises(RuntimeError):
+        halko.ooc_block_plan(N, M, k + 10, 10.0, False, 64)
+
+
+def test_permute_plink_indices_match_reference_golden():
+    g = golden("ssvd_small")
+    w = golden("winsvd_ooc_small")
+    assert np.array_equal(halko.permute_plink_indices(int(g["M"]), int(g["N"]), int(w["bands"])), w["perm"])
+    assert np.array_equal(halko.permute_plink_indices(203, 13, 8), golden("helpers")["plink_perm"])
+
+
+def test_host_random_streams_match_reference_golden():
+    h = golden("helpers")
+    L = _lib.load()
+    a = np.zeros((7, 3), order="F")
+    L.pcaone_init_omega(7, 3, 9, 1, a.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, h["omega_7x3_seed9"])
+    L.pcaone_init_omega(7, 3, 9, 0, a.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, h["omega_uniform"])
+    idx = np.zeros(10, dtype=np.uint32)
+    L.pcaone_shuffle_indices(10, idx.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(idx, h["shuffle10"])
+    g = golden("ssvd_small")
+    om = np.zeros((int(g["N"]), 13), order="F")
+    L.pcaone_init_omega(int(g["N"]), 13, 112, 1, om.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(om, g["omega"])
+    idx = np.zeros(int(g["M"]), dtype=np.uint32)
+    L.pcaone_shuffle_indices(int(g["M"]), idx.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(idx, golden("winsvd_small")["perm"])
+
+
+def test_synth_bed_roundtrip(tmp_path):
+    prefix = str(tmp_path / "x")
+    packed = synth.write_bed(prefix, 23, 40, k_pop=3, seed=4, miss=0.05)
+    p2, n, m = synth.read_bed(prefix)
+    assert (n, m) == (23, 40) and np.array_equal(packed, p2)
+    codes = synth.unpack_codes(packed, 23)
+    assert np.array_equal(synth.pack_codes(codes), packed)
+    bad = open(prefix + ".bed", "r+b")
+    bad.write(b"\x00")
+    bad.close()
+    with pytest.raises(ValueError):
+        synth.read_bed(prefix)
+    with pytest.raises(RuntimeError):
+        halko.FileBed(halko.Param(filein=prefix, k=2, svd=1))
