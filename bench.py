@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric  : genotype GB/s per power-iteration pass (packed bed bytes / pass time)
+workload: configs[1] — PCAone window-based RSVD (winSVD, 64 windows), N=10,000 samples x
+          M=1,000,000 SNPs per GPU, k=20 (l=40), in-memory on B200. One "step" = one epoch of
+          RsvdOpData::computeUSV: computeGandH (decode + X^T Omega + X G for every window and all
+          Omega updates of that epoch) followed by the dense stage (QR(G) x2, B, SVD). Steps walk
+          epochs pi = 0,1,2,... of one winSVD run (7 epochs = a complete default run).
+value   : whole-job packed GB/s with the packed shard resident in HBM (device-timed, max over ranks)
+e2e     : same metric through the C-ABI with the packed matrix in pinned HOST memory: every
+          step streams all blocks host->device (double-buffered) and reads U,S back.
+N > 1   : SNP-sharded, weak scaling (every rank owns its own 1M SNPs of a world*1M-SNP job);
+          H (N x l) is all-reduced over NCCL at every Omega update, the l x l Gram of G once per epoch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "genotype GB/s per power-iteration pass"
+UNIT = "GB/s"
+N_SAMPLES, M_SNPS, K, BANDS = 10_000, 1_000_000, 20, 64
+CPU_SAMPLE_SNPS = 32_768
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_pass(packed_host, n_samples, k, steps, warmup, threads):
+    """Time the reference's own CPU computeGandH (oracle/_ref, unmodified PCAone) on a bounded
+    sample of the workload: the first CPU_SAMPLE_SNPS SNPs, all samples, winSVD in-core, -S."""
+    from oracle import ref
+    from pcaone_b200 import synth
+
+    if not ref.available():
+        return None
+    tmp = tempfile.mkdtemp(prefix="pcaone_cpu_")
+    prefix = os.path.join(tmp, "s")
+    synth.write_bed_from_packed(prefix, packed_host, n_samples)
+    ref.lib().ref_set_threads(threads)
+    t0 = time.perf_counter()
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 2 -S -o {tmp}/o -n {threads}", threads=threads)
+    r.new_op()
+    load_s = time.perf_counter() - t0
+    times = []
+    for i in range(warmup + steps):
+        t = r.time_gandh(i)  # epochs 0,1,2,... of one winSVD run, like the GPU arm
+        if i >= warmup:
+            times.append(t)
+    r.close()
+    nbytes = packed_host.shape[0] * packed_host.shape[1]
+    return {"times": times, "load_s": load_s, "bytes": nbytes}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: PCAone's CPU implementation of the pass on the box's host cores."""
+    if rank != 0:
+        return
+    import torch
+    from pcaone_b200 import synth
+
+    threads = os.cpu_count() or 1
+    m = CPU_SAMPLE_SNPS if not args.small else 4096
+    n = N_SAMPLES if not args.small else 1000
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    packed = synth.torch_packed(n, m, k_pop=K + 4, seed=1, device=dev, chunk=8192).cpu().numpy()
+    res = cpu_reference_pass(packed, n, K, args.steps, args.warmup, threads)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpcaone_ref.so was not built"}))
+        return
+    tot = sum(res["times"])
+    val = res["bytes"] * len(res["times"]) / tot / 1e9
+    sample = (f"first {m} of {M_SNPS} SNPs x {n} samples (1/{M_SNPS // m} of the workload), winSVD in-core -S, "
+              f"epochs {args.warmup}..{args.warmup + args.steps - 1}; Eigen built-in GEMM, no MKL")
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(res["times"]), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "configs[1]: winSVD N=10000 x M=1000000 k=20 (bounded CPU sample)",
+                       "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=7)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--small", action="store_true", help="debug-sized workload (not a bench number)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and not args.small:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pcaone_b200 import dist as pdist
+    from pcaone_b200 import halko, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pcaone_b200 has no CPU fallback")
+    rank, world, local = pdist.init_process_group_from_env("nccl")
+    torch.cuda.set_device(local)
+    n, m = (N_SAMPLES, M_SNPS) if not args.small else (1000, 65536)
+    peaks, peak_src = _peaks()
+
+    # ---- synthetic packed shard, generated in HBM (seeded per rank)
+    packed = synth.torch_packed(n, m, k_pop=K + 4, seed=1 + rank, device=f"cuda:{local}", chunk=16384)
+    bpr = packed.shape[1]
+    shard_bytes = m * bpr
+
+    hook = pdist.make_allreduce_hook() if world > 1 else None
+
+    def make_op(src, ooc):
+        p = halko.Param(k=K, svd=2, bands=BANDS, maxp=20, tol=1e-4, no_shuffle=True, device=local,
+                        memory=1.0 if ooc else 0.0)
+        d = halko.FileBed(p, packed=src, nsamples=n)
+        if ooc:  # 64 streamed blocks == the 64 windows (what -m gives when nblocks < bands)
+            bs = -(-m // BANDS)
+            d.start = np.arange(BANDS, dtype=np.uint64) * np.uint64(bs)
+            d.stop = np.minimum(d.start + np.uint64(bs - 1), np.uint64(m - 1))
+            d.nblocks, d.blocksize, d.bandFactor = BANDS, bs, 1
+        op = halko.FancyRsvdOpData(d, p.k, p.oversamples, rank=rank, world=world, nsnps_total=m * world,
+                                   allreduce=hook)
+        op.setFlags(False, True)
+        return op
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg
+    op = make_op(packed, ooc=False)
+    stream = torch.cuda.ExternalStream(op.L.pcaone_stream(op.h))
+
+    def step(o, i):
+        o._chk(o.L.pcaone_compute_gandh(o.h, i))
+        o._chk(o.L.pcaone_small_stage(o.h))
+
+    for i in range(args.warmup):
+        step(op, i)
+    op.sync()
+    op.enable_timing(True)
+    op.timers(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(op, i)
+    e1.record(stream)
+    op.sync()
+    torch.cuda.synchronize()
+    barrier()
+    dev_ms = maxr(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    tm = op.timers(reset=True)
+    op.enable_timing(False)
+    value = world * shard_bytes * args.steps / (dev_ms * 1e-3) / 1e9
+    l = op.size()
+    flops_per_gemm_total = 2.0 * n * m * l  # per pass, each of the two GEMMs
+    g_ms, h_ms = tm.gemm_g_ms / args.steps, tm.gemm_h_ms / args.steps
+    # dominant kernel: the fused decode->DMMA GEMM pair; report the slower of the two
+    dom, dom_ms, dom_launches = (("k_gemm_h", h_ms, tm.gemm_h_launches) if h_ms >= g_ms else
+                                 ("k_gemm_g", g_ms, tm.gemm_g_launches))
+    achieved_tf = flops_per_gemm_total / (dom_ms * 1e-3) / 1e12
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16 sustained",
+                "note": ("FP64 DMMA path: algorithmic flops 2*N*M*l per GEMM per pass; peak is the measured bf16 "
+                         "tensor figure because MEASURED_PEAKS has no FP64 entry (B200 FP64 tensor nominal ~37 TF)"),
+                "gemm_g_ms_per_pass": g_ms, "gemm_h_ms_per_pass": h_ms, "orth_ms_per_pass": tm.orth_ms / args.steps,
+                "small_stage_ms_per_pass": tm.small_ms / args.steps,
+                "launches_per_pass": dom_launches / args.steps,
+                "hbm_algorithmic_gbs": shard_bytes / (dom_ms * 1e-3) / 1e9}
+    gpu_launches = int(tm.kernel_launches)
+    op.close()
+
+    # ---- end-to-end leg: packed matrix in pinned host memory, streamed every pass
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((m, bpr), dtype=torch.uint8, pin_memory=True)
+        host.copy_(packed)
+        torch.cuda.synchronize()
+        del packed
+        torch.cuda.empty_cache()
+        op2 = make_op(host, ooc=True)
+        def step2(i):
+            step(op2, i)
+            # result of the step back on the host: sigma (l) and the current PCs are device state;
+            # read the N x l H (the pass output the reference hands to computeUSV)
+            op2.getH(Hh)
+
+        Hh = np.zeros((n, l), order="F")
+        for i in range(min(args.warmup, 3)):
+            step2(i)
+        op2.sync()
+        op2.timers(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step2(i)
+        op2.sync()
+        barrier()
+        e2e_s = maxr(time.perf_counter() - t0)
+        tm2 = op2.timers(reset=True)
+        e2e = {"value": world * shard_bytes * args.steps / e2e_s / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(tm2.h2d_bytes // args.steps), "d2h_bytes_per_step": int(tm2.d2h_bytes // args.steps),
+               "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "host wall clock between stream syncs, max over ranks"}
+        op2.close()
+        cpu_src = host.numpy()[: (CPU_SAMPLE_SNPS if not args.small else 4096)]
+    else:
+        cpu_src = packed[: (CPU_SAMPLE_SNPS if not args.small else 4096)].cpu().numpy()
+
+    # ---- CPU baseline (rank 0, N=1 only): the compiled reference on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        res = cpu_reference_pass(np.ascontiguousarray(cpu_src), n, K, 2, 1, threads)
+        if res is not None:
+            tot = sum(res["times"])
+            cpu = {"value": res["bytes"] * len(res["times"]) / tot / 1e9, "unit": UNIT, "cores": threads,
+                   "kind": "reference",
+                   "sample": (f"first {cpu_src.shape[0]} of {m} SNPs x {n} samples, winSVD in-core -S, epochs 1-2 "
+                              f"({tot:.1f} s of CPU passes + {res['load_s']:.1f} s read/decode); Eigen GEMM, no MKL")}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "oracle/_ref/libpcaone_ref.so missing"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[1]: winSVD in-memory, N={n} x M={m} SNPs per GPU, k={K}, l={l}, "
+                                       f"{BANDS} windows, no-shuffle; step = one computeUSV epoch (pi = step index)",
+                           "l2": "inputs (2.5 GB packed per GPU) are larger than L2; no flush needed",
+                           "parallelism": f"snp-shard x{world}"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

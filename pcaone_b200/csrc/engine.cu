@@ -78,7 +78,7 @@ struct pcaone_ctx {
 
   // small l x l (ld = lp)
   double *d_W = nullptr, *d_R = nullptr, *d_Rinv = nullptr, *d_T1 = nullptr, *d_T2 = nullptr, *d_T = nullptr,
-         *d_Vr = nullptr, *d_Z = nullptr, *d_sigma = nullptr, *d_sign = nullptr, *d_scal = nullptr;
+         *d_Vr = nullptr, *d_Z = nullptr, *d_sigma = nullptr, *d_sign = nullptr, *d_hsign = nullptr, *d_scal = nullptr;
   int* d_status = nullptr;
   int* h_status = nullptr;    // pinned
   double* h_scal = nullptr;   // pinned
@@ -400,13 +400,13 @@ void orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Tto
   if (Ttot) small_matmul(c, c->d_T1, 0, c->d_T2, 0, c->l, c->l, c->l, Ttot);
 }
 
-void flip_omg(pcaone_ctx* c) {
+void flip_omg(pcaone_ctx* c, const double* pre) {
   uint64_t rpc = std::max<uint64_t>(8, (c->N + c->sms - 1) / c->sms);
   int nparts = (int)((c->N + rpc - 1) / rpc);
   if ((size_t)nparts * 2 * c->l > c->part_doubles) throw std::runtime_error("partial workspace too small");
-  k_flip_partial<<<nparts, 256, 0, c->stream>>>(c->d_Omg2, c->d_Omg, c->lp, c->l, c->N, rpc, c->d_part);
+  k_flip_partial<<<nparts, 256, 0, c->stream>>>(c->d_Omg2, c->d_Omg, c->lp, c->l, c->N, rpc, pre, c->d_part);
   PCA_CHECK_LAUNCH();
-  k_flip_sign<<<1, 128, 0, c->stream>>>(c->d_part, nparts, c->l, c->d_sign);
+  k_flip_sign<<<1, 128, 0, c->stream>>>(c->d_part, nparts, c->l, pre, c->d_sign);
   PCA_CHECK_LAUNCH();
   k_flip_apply<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->d_Omg2, c->lp, c->l, c->N,
                                                                           c->d_sign);
@@ -426,7 +426,23 @@ void allreduce_H(pcaone_ctx* c, double* H) {
 void update_omega(pcaone_ctx* c, const double* H, bool flip) {
   Timed t(c, 2);
   orth2(c, H, c->N, c->d_Omg, nullptr, false);
-  if (flip) flip_omg(c);
+  // give the CholeskyQR basis the column signs of the reference's Householder thin Q
+  const size_t smem = (size_t)c->l * c->l * sizeof(double);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_householder_signs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k_householder_signs<<<1, kSmallThreads, smem, c->stream>>>(c->d_Omg, c->l, c->lp, c->d_hsign);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+  if (flip) {
+    flip_omg(c, c->d_hsign);
+  } else {
+    k_scale_cols<<<grid_for(c->N * c->l, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, c->N, c->d_hsign);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
+  }
   c->tm.omega_updates++;
 }
 
@@ -873,6 +889,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     for (double** p : {&c->d_W, &c->d_R, &c->d_Rinv, &c->d_T1, &c->d_T2, &c->d_T, &c->d_Vr, &c->d_Z}) dmalloc(p, LL);
     dmalloc(&c->d_sigma, c->lp);
     dmalloc(&c->d_sign, c->lp);
+    dmalloc(&c->d_hsign, c->lp);
     dmalloc(&c->d_scal, 64);
     dmalloc(&c->d_status, 4);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
@@ -898,7 +915,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_H, (void*)c->d_H1, (void*)c->d_H2, (void*)c->d_Bt, (void*)c->d_Ucur, (void*)c->d_Upre,
                   (void*)c->d_U, (void*)c->d_G, (void*)c->d_V, (void*)c->d_Vpre, (void*)c->d_S, (void*)c->d_Hpart,
                   (void*)c->d_W, (void*)c->d_R, (void*)c->d_Rinv, (void*)c->d_T1, (void*)c->d_T2, (void*)c->d_T,
-                  (void*)c->d_Vr, (void*)c->d_Z, (void*)c->d_sigma, (void*)c->d_sign, (void*)c->d_scal,
+                  (void*)c->d_Vr, (void*)c->d_Z, (void*)c->d_sigma, (void*)c->d_sign, (void*)c->d_hsign, (void*)c->d_scal,
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1]})
     if (p) cudaFree(p);

@@ -222,6 +222,40 @@ __global__ void k_svqb_factor(const double* __restrict__ Vr, const double* __res
   }
 }
 
+// Column signs that make a CholeskyQR basis Q (R diagonal > 0) equal the thin Q an unblocked
+// Householder QR would return (Eigen::HouseholderQR / LAPACK dgeqrf convention:
+// beta = -sign(c0)*norm, Householder.h makeHouseholder). The decisions only depend on the top
+// l x l block of Q: with orthonormal columns the i-th reflector turns the trailing block into
+// its Schur complement w.r.t. (Q_ii - beta_i), so a sign-modified LU of that block replays them
+// (Ballard et al., "Reconstructing Householder vectors from TSQR"). winSVD adds H1 and H2 that
+// were built with different Omegas, so the column signs of Omega are part of the algorithm
+// (that is what flipOmg is for) and must follow the reference's QR, not ours.
+__global__ void __launch_bounds__(kSmallThreads)
+k_householder_signs(const double* __restrict__ Qtop, int l, int ld, double* __restrict__ sign) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* W = reinterpret_cast<double*>(smem_raw);  // l x l row-major
+  __shared__ double s_piv;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < l * l; i += nt) W[i] = Qtop[(i / l) * ld + (i % l)];
+  __syncthreads();
+  for (int i = 0; i < l; ++i) {
+    if (tid == 0) {
+      const double c0 = W[i * l + i];
+      const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
+      sign[i] = beta;
+      s_piv = c0 - beta;  // |c0 - beta| >= 1
+    }
+    __syncthreads();
+    const double inv = 1.0 / s_piv;
+    const int m = l - i - 1;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int r = i + 1 + idx / m, c = i + 1 + idx % m;
+      W[r * l + c] -= W[r * l + i] * W[i * l + c] * inv;
+    }
+    __syncthreads();
+  }
+}
+
 // mev(X, Y) = mean_i || X^T Y[:, i] ||  (Utils.cpp:194-200); C = X^T Y (k x k, row-major ld)
 __global__ void k_mev_from_xty(const double* __restrict__ C, int k, int ld, double* __restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {

@@ -126,20 +126,24 @@ k_ts_rightmult(const double* __restrict__ A, int lda, int l1, const double* __re
 }
 
 // flipOmg (RSVD.hpp:80-89) stage 1: per-CTA partial column sums of |O2-O| and |O2+O|
+// `pre` (optional) is a per-column sign applied to O first (the Householder sign convention).
 __global__ void k_flip_partial(const double* __restrict__ O2, const double* __restrict__ O, int ld, int l,
-                               uint64_t rows, uint64_t rows_per_cta, double* __restrict__ part) {
+                               uint64_t rows, uint64_t rows_per_cta, const double* __restrict__ pre,
+                               double* __restrict__ part) {
   __shared__ double sm[2][8][128];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const uint64_t r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   for (int c0 = 0; c0 < l; c0 += 32) {
     const int c = c0 + tx;
     double d = 0.0, s = 0.0;
-    if (c < l)
+    if (c < l) {
+      const double ps = pre ? pre[c] : 1.0;
       for (uint64_t r = r0 + ty; r < r1; r += 8) {
-        const double a = O2[r * ld + c], b = O[r * ld + c];
+        const double a = O2[r * ld + c], b = ps * O[r * ld + c];
         d += fabs(a - b);
         s += fabs(a + b);
       }
+    }
     if (c < 128) {
       sm[0][ty][c] = d;
       sm[1][ty][c] = s;
@@ -156,14 +160,15 @@ __global__ void k_flip_partial(const double* __restrict__ O2, const double* __re
     part[(uint64_t)blockIdx.x * 2 * l + l + c] = s;
   }
 }
-__global__ void k_flip_sign(const double* __restrict__ part, int nparts, int l, double* __restrict__ sign) {
+__global__ void k_flip_sign(const double* __restrict__ part, int nparts, int l, const double* __restrict__ pre,
+                            double* __restrict__ sign) {
   for (int c = threadIdx.x; c < l; c += blockDim.x) {
     double d = 0.0, s = 0.0;
     for (int p = 0; p < nparts; ++p) {
       d += part[(uint64_t)p * 2 * l + c];
       s += part[(uint64_t)p * 2 * l + l + c];
     }
-    sign[c] = (d > 2 * s) ? -1.0 : 1.0;
+    sign[c] = ((d > 2 * s) ? -1.0 : 1.0) * (pre ? pre[c] : 1.0);
   }
 }
 // O[:,c] *= sign[c]; O2 = O

@@ -28,9 +28,16 @@ from . import _lib
 from .synth import BED_MAGIC, bytes_per_snp
 
 
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
 def _vp(a):
+    """void* of a numpy array or a torch tensor (host, pinned or device)."""
     if a is None:
         return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
     return a.ctypes.data_as(C.c_void_p)
 
 
@@ -154,7 +161,9 @@ class FileBed:
                     raise RuntimeError("Incorrect magic number in plink bed file.")
             self.packed = None
         else:
-            self.packed = np.ascontiguousarray(packed, dtype=np.uint8)
+            # numpy array, or a torch uint8 tensor (CUDA: uploaded device-to-device; pinned
+            # host: streamed by cudaMemcpyAsync in out-of-core mode)
+            self.packed = packed.contiguous() if _is_torch(packed) else np.ascontiguousarray(packed, dtype=np.uint8)
             self.nsamples = int(nsamples)
             self.nsnps = int(self.packed.shape[0])
             if self.packed.shape[1] != bytes_per_snp(self.nsamples):
@@ -176,7 +185,7 @@ class FileBed:
         if p.perm:
             # permute_plink writes <out>.perm.bed; here the rows are permuted in host memory
             self.perm = permute_plink_indices(self.nsnps, self.nsamples, p.bands, p.buffer)
-            self.packed = np.ascontiguousarray(self._load_packed()[self.perm])
+            self.packed = np.ascontiguousarray(np.asarray(self._load_packed())[self.perm])
 
 
 class RsvdOpData:
@@ -214,7 +223,11 @@ class RsvdOpData:
                 self._chk(L.pcaone_open_bed(self.h, (p.filein + ".bed").encode(), 0))
             self._chk(L.pcaone_set_blocks(self.h, _vp(data.start), _vp(data.stop), data.nblocks, data.bandFactor))
         else:
-            self._chk(L.pcaone_upload_bed(self.h, _vp(data.packed), data.nsnps, 0))
+            on_dev = _is_torch(data.packed) and data.packed.is_cuda
+            self._chk(L.pcaone_upload_bed(self.h, _vp(data.packed), data.nsnps, int(on_dev)))
+            if data.start is not None:  # explicit windows for a resident shard (SNP-sharded winSVD)
+                self._chk(L.pcaone_set_blocks(self.h, _vp(data.start), _vp(data.stop), len(data.start),
+                                              data.bandFactor))
             self._chk(L.pcaone_allele_freq(self.h))
         self._permuted = False
         self.initOmg()
@@ -275,6 +288,15 @@ class RsvdOpData:
             self._chk(self.L.pcaone_permute_resident(self.h, _vp(idx)))
             self.data.perm = idx.astype(np.int64)
             self._permuted = True
+
+    def getH(self, out=None):
+        H = out if out is not None else _f((self.cols(), self.size()))
+        self._chk(self.L.pcaone_get_GH(self.h, None, _vp(H)))
+        return H
+
+    def smallStage(self):
+        """dense stage of one computeUSV epoch (src/Halko.cpp:55-70)."""
+        self._chk(self.L.pcaone_small_stage(self.h))
 
     def computeGandH(self, pi, want=True):
         """One power-iteration pass; returns (G M x l, H N x l) col-major when want."""
