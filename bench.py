@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="debug-sized workload (not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default="int8x3", choices=["fp64", "int8x2", "int8x3", "int8x4"],
+                    help="GEMM arithmetic: FP64 DMMA, or the exact int8 tensor-core path with 2/3/4 slices")
     args = ap.parse_args()
     if args.warmup < 3 and not args.small:
         args.warmup = 3
@@ -181,6 +183,7 @@ def main():
     torch.cuda.set_device(local)
     n, m = (N_SAMPLES, M_SNPS) if not args.small else (1000, 65536)
     peaks, peak_src = _peaks()
+    prec = {"fp64": 0, "int8x2": 2, "int8x3": 3, "int8x4": 4}[args.precision]
 
     # ---- synthetic packed shard, generated in HBM (seeded per rank)
     packed = synth.torch_packed(n, m, k_pop=K + 4, seed=1 + rank, device=f"cuda:{local}", chunk=16384)
@@ -191,7 +194,7 @@ def main():
 
     def make_op(src, ooc):
         p = halko.Param(k=K, svd=2, bands=BANDS, maxp=20, tol=1e-4, no_shuffle=True, device=local,
-                        memory=1.0 if ooc else 0.0)
+                        memory=1.0 if ooc else 0.0, precision=prec)
         d = halko.FileBed(p, packed=src, nsamples=n)
         if ooc:  # 64 streamed blocks == the 64 windows (what -m gives when nblocks < bands)
             bs = -(-m // BANDS)
@@ -247,17 +250,30 @@ def main():
     l = op.size()
     flops_per_gemm_total = 2.0 * n * m * l  # per pass, each of the two GEMMs
     g_ms, h_ms = tm.gemm_g_ms / args.steps, tm.gemm_h_ms / args.steps
-    # dominant kernel: the fused decode->DMMA GEMM pair; report the slower of the two
-    dom, dom_ms, dom_launches = (("k_gemm_h", h_ms, tm.gemm_h_launches) if h_ms >= g_ms else
-                                 ("k_gemm_g", g_ms, tm.gemm_g_launches))
-    achieved_tf = flops_per_gemm_total / (dom_ms * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    if prec == 0:
+        # dominant kernel: the fused decode->DMMA GEMM pair; report the slower of the two
+        dom, dom_ms, dom_launches = (("k_gemm_h", h_ms, tm.gemm_h_launches) if h_ms >= g_ms else
+                                     ("k_gemm_g", g_ms, tm.gemm_g_launches))
+        note = ("FP64 DMMA path: algorithmic flops 2*N*M*l per GEMM per pass; peak is the measured bf16 "
+                "tensor figure because MEASURED_PEAKS has no FP64 entry (B200 FP64 tensor nominal ~37 TF)")
+    else:
+        # dominant kernel: k_tc_gemm (tcgen05 kind::i8, both passes use the same kernel); its
+        # own CUDA-event time (tc_g_ms / tc_h_ms), without the slice / finish kernels around it
+        tg, th = tm.tc_g_ms / args.steps, tm.tc_h_ms / args.steps
+        dom, dom_ms, dom_launches = (("k_tc_gemm (H pass)", th, tm.gemm_h_launches) if th >= tg else
+                                     ("k_tc_gemm (G pass)", tg, tm.gemm_g_launches))
+        note = (f"int8 Ozaki path, {prec} slices: algorithmic flops 2*N*M*l per GEMM per pass (the tensor cores "
+                f"execute {prec}x that as exact int8 MACs, so frac <= {1.0 / prec * 2:.2f} of the bf16 peak at the "
+                "int8 rate of 2x bf16); peak = measured bf16 sustained")
+    achieved_tf = flops_per_gemm_total / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peak_src} bf16 sustained",
-                "note": ("FP64 DMMA path: algorithmic flops 2*N*M*l per GEMM per pass; peak is the measured bf16 "
-                         "tensor figure because MEASURED_PEAKS has no FP64 entry (B200 FP64 tensor nominal ~37 TF)"),
+                "note": note,
                 "gemm_g_ms_per_pass": g_ms, "gemm_h_ms_per_pass": h_ms, "orth_ms_per_pass": tm.orth_ms / args.steps,
                 "small_stage_ms_per_pass": tm.small_ms / args.steps,
+                "tc_g_ms_per_pass": tm.tc_g_ms / args.steps, "tc_h_ms_per_pass": tm.tc_h_ms / args.steps,
+                "tc_ranges": int(tm.tc_ranges), "fp64_ranges": int(tm.fp64_ranges),
                 "launches_per_pass": dom_launches / args.steps,
                 "hbm_algorithmic_gbs": shard_bytes / (dom_ms * 1e-3) / 1e9}
     gpu_launches = int(tm.kernel_launches)
@@ -317,7 +333,8 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec == 0 else f"int8x{prec} (exact, FP64 epilogue)",
+                "data": "synthetic",
                 "config": {"workload": f"configs[1]: winSVD in-memory, N={n} x M={m} SNPs per GPU, k={K}, l={l}, "
                                        f"{BANDS} windows, no-shuffle; step = one computeUSV epoch (pi = step index)",
                            "l2": "inputs (2.5 GB packed per GPU) are larger than L2; no flush needed",

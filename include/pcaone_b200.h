@@ -31,7 +31,11 @@ extern "C" {
 typedef struct pcaone_ctx pcaone_ctx;
 
 enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cmd.cpp:41-45) */
-enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_BF16X3 = 1 };        /* GEMM arithmetic */
+/* GEMM arithmetic. FP64: DMMA tensor cores. INT8Xs: error-free Ozaki scheme on
+ * the tcgen05 int8 tensor cores — Omega / G are rounded once to s signed 8-bit slices per entry
+ * (8s-1 bits against the column maximum) and the products are then exact integers; ranges with
+ * missing genotypes and EMU update passes still run on the FP64 kernels. */
+enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_INT8X2 = 2, PCAONE_PREC_INT8X3 = 3, PCAONE_PREC_INT8X4 = 4 };
 enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2 };
 
 /* Mirrors the fields of `Param` (Cmd.hpp:16-98) that the hot path reads. */
@@ -155,6 +159,8 @@ typedef struct pcaone_timers {
   double gemm_g_ms, gemm_h_ms, orth_ms, small_ms, h2d_ms, allreduce_ms, decode_ms;
   uint64_t gemm_g_launches, gemm_h_launches, kernel_launches, h2d_bytes, d2h_bytes;
   uint64_t omega_updates;
+  uint64_t tc_ranges, fp64_ranges; /* SNP ranges whose GEMMs ran on the int8 / FP64 tensor-core kernels */
+  double tc_g_ms, tc_h_ms;         /* k_tc_gemm alone (inside gemm_g_ms / gemm_h_ms), G pass / H pass */
 } pcaone_timers;
 int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
 int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */

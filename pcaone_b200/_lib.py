@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpcaone_b200.so")
 
 SVD_SSVD, SVD_WINSVD = 1, 2
-PREC_FP64, PREC_BF16X3 = 0, 1
+PREC_FP64, PREC_INT8X2, PREC_INT8X3, PREC_INT8X4 = 0, 2, 3, 4
 
 
 class Config(C.Structure):
@@ -29,6 +29,7 @@ class Timers(C.Structure):
         ("h2d_ms", C.c_double), ("allreduce_ms", C.c_double), ("decode_ms", C.c_double),
         ("gemm_g_launches", C.c_uint64), ("gemm_h_launches", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("omega_updates", C.c_uint64),
+        ("tc_ranges", C.c_uint64), ("fp64_ranges", C.c_uint64), ("tc_g_ms", C.c_double), ("tc_h_ms", C.c_double),
     ]
 
 

@@ -40,6 +40,11 @@ __global__ void k_gather_rows(const uint8_t* __restrict__ src, uint8_t* __restri
         reinterpret_cast<const uint4*>(src + (uint64_t)idx[r] * pitch)[c];
   }
 }
+__global__ void k_gather_u32(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                             const uint32_t* __restrict__ idx, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = src[idx[i]];
+}
 __global__ void k_gather_f64(const double* __restrict__ src, double* __restrict__ dst,
                              const uint32_t* __restrict__ idx, uint64_t n) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)

@@ -22,6 +22,7 @@
 #include "gemm_fp64.cuh"
 #include "small_dense.cuh"
 #include "tall_skinny.cuh"
+#include "tc_gemm.cuh"
 
 using namespace pcaone;
 
@@ -90,6 +91,22 @@ struct pcaone_ctx {
 
   // winSVD state (FancyRsvdOpData members, Halko.hpp:66-68)
   uint64_t bandsize = 1;
+
+  // tensor-core (int8 Ozaki) path, tc_gemm.cuh. slices == 0 -> FP64 DMMA only.
+  int slices = 0, NP = 0, RT = 1;
+  uint8_t *d_PG = nullptr, *d_PH = nullptr;            // resident tiled operands (rows = SNPs / rows = samples)
+  uint8_t *d_PGb[2] = {nullptr, nullptr}, *d_PHb[2] = {nullptr, nullptr};  // per streamed block
+  bool tiles_valid = false;
+  int8_t *d_BimgO = nullptr, *d_BimgW = nullptr;       // B operand images: Omega, W = s o G of the current range
+  size_t bimgW_kb = 0;
+  long long* d_Racc = nullptr;                         // int64 accumulators
+  size_t R_rows = 0;
+  unsigned long long* d_tcs = nullptr;                 // [4][lp]: Omega colmax, Omega Csum, W colmax, W Csum
+  double* d_Fpart = nullptr;
+  bool omega_img_valid = false;
+  std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
+  std::vector<uint64_t> nmiss_prefix;
+  uint64_t tc_ranges = 0, fp64_ranges = 0;
 
   pcaone_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
@@ -168,6 +185,8 @@ void resolve_timers(pcaone_ctx* c) {
       case 4: c->tm.h2d_ms += ms; break;
       case 5: c->tm.allreduce_ms += ms; break;
       case 6: c->tm.decode_ms += ms; break;
+      case 7: c->tm.tc_g_ms += ms; break;
+      case 8: c->tm.tc_h_ms += ms; break;
     }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
@@ -242,8 +261,8 @@ void gemm_h_nt(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, const double* F,
     default: throw std::runtime_error("unsupported NT");       \
   }
 
-// G rows [0,nrows) of the range = X^T Omega ; Hacc (+)= X G
-void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate) {
+// G rows [0,nrows) of the range = X^T Omega ; Hacc (+)= X G      (FP64 DMMA kernels)
+void range_gemms_fp64(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate) {
   if (nrows == 0) return;
   const double* F = c->d_F + snp0;
   double* G = c->d_G + snp0 * c->lp;
@@ -269,6 +288,267 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
     PCA_CHECK_LAUNCH();
     c->tm.gemm_h_launches++;
     c->tm.kernel_launches += 2;
+  }
+}
+
+// ---------------------------------------------------------------- tensor-core (int8 Ozaki) path
+uint64_t tc_nkb_samples(const pcaone_ctx* c) { return (c->N + tc::kKB - 1) / tc::kKB; }
+uint64_t tc_nrt_samples(const pcaone_ctx* c) { return (c->N + tc::kRowTile - 1) / tc::kRowTile; }
+size_t tc_pg_bytes(const pcaone_ctx* c, uint64_t rows) {
+  return (size_t)((rows + tc::kRowTile - 1) / tc::kRowTile) * tc_nkb_samples(c) * tc::kChunkBytes;
+}
+size_t tc_ph_bytes(const pcaone_ctx* c, uint64_t rows) {
+  return (size_t)((rows + tc::kKB - 1) / tc::kKB) * tc_nrt_samples(c) * tc::kChunkBytes;
+}
+
+// tiled copies of `rows` packed SNP rows at P: PG (rows = SNPs) and PH (rows = samples)
+void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st) {
+  const uint32_t nkb = (uint32_t)tc_nkb_samples(c), nrt = (uint32_t)tc_nrt_samples(c);
+  const uint64_t work = (uint64_t)((rows + tc::kRowTile - 1) / tc::kRowTile) * nkb * tc::kRowTile;
+  tc::k_tile_rows<<<grid_for(work, 256, c->sms), 256, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nkb, PG);
+  PCA_CHECK_LAUNCH();
+  const uint64_t nkbh = (rows + tc::kKB - 1) / tc::kKB;
+  tc::k_tile_transpose<<<(unsigned)(nkbh * nrt), 128, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nrt, PH);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches += 2;
+}
+
+void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
+  if (!c->d_tcs) {
+    dmalloc(&c->d_tcs, (size_t)4 * c->lp);
+    PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)4 * c->lp * sizeof(unsigned long long), c->stream));
+    dmalloc(&c->d_BimgO, (size_t)tc_nkb_samples(c) * tc::kKB * c->NP);
+  }
+  const size_t need_rows = std::max<uint64_t>(tc_nrt_samples(c) * tc::kRowTile, max_range_rows + 2 * tc::kRowTile);
+  if (need_rows > c->R_rows) {
+    if (c->d_Racc) cudaFree(c->d_Racc);
+    dmalloc(&c->d_Racc, need_rows * c->lp);
+    PCA_CUDA(cudaMemsetAsync(c->d_Racc, 0, need_rows * c->lp * sizeof(long long), c->stream));
+    c->R_rows = need_rows;
+  }
+  const size_t need_kb = max_range_rows / tc::kKB + 2;
+  if (need_kb > c->bimgW_kb) {
+    if (c->d_BimgW) cudaFree(c->d_BimgW);
+    if (c->d_Fpart) cudaFree(c->d_Fpart);
+    dmalloc(&c->d_BimgW, need_kb * tc::kKB * c->NP);
+    dmalloc(&c->d_Fpart, need_kb * c->lp);
+    c->bimgW_kb = need_kb;
+  }
+}
+
+// missing genotypes among local SNPs [s, s+n): UINT64_MAX if not known on the host yet
+uint64_t tc_missing_in(pcaone_ctx* c, uint64_t s, uint64_t n) {
+  if (c->h_nmiss.size() != c->M) return UINT64_MAX;
+  if (c->nmiss_prefix.size() == c->M + 1) return c->nmiss_prefix[s + n] - c->nmiss_prefix[s];
+  uint64_t tot = 0;
+  for (uint64_t j = s; j < s + n; ++j) {
+    if (c->h_nmiss[j] == UINT32_MAX) return UINT64_MAX;
+    tot += c->h_nmiss[j];
+  }
+  return tot;
+}
+void tc_fetch_nmiss(pcaone_ctx* c, uint64_t s, uint64_t n) {
+  if (c->h_nmiss.size() != c->M) c->h_nmiss.assign(c->M, UINT32_MAX);
+  PCA_CUDA(cudaMemcpyAsync(c->h_nmiss.data() + s, c->d_nmiss + s, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  c->nmiss_prefix.clear();
+  bool all = true;
+  for (uint64_t j = 0; j < c->M && all; ++j) all = c->h_nmiss[j] != UINT32_MAX;
+  if (all) {
+    c->nmiss_prefix.resize(c->M + 1);
+    c->nmiss_prefix[0] = 0;
+    for (uint64_t j = 0; j < c->M; ++j) c->nmiss_prefix[j + 1] = c->nmiss_prefix[j] + c->h_nmiss[j];
+  }
+}
+
+template <int S, int RT>
+void tc_launch_st(pcaone_ctx* c, const tc::TcGemmArgs& a, int grid) {
+  const size_t smem = tc::tc_smem_bytes(RT, c->NP);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<S, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  tc::k_tc_gemm<S, RT><<<grid, tc::tc_threads(RT), smem, c->stream>>>(a);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a) {
+  // split-K so that (row-tile groups x splits) fills the SMs in whole waves
+  const uint32_t n_rtp = (a.nrt + c->RT - 1) / c->RT;
+  const uint32_t epi_cost = 24;  // epilogue + pipeline fill, in k-block units
+  uint32_t best_ns = 1;
+  uint64_t best = UINT64_MAX;
+  const uint32_t max_ns = std::max<uint32_t>(1, a.nkb / 8);
+  for (uint32_t ns = 1; ns <= std::min<uint32_t>(max_ns, 4u * c->sms); ++ns) {
+    const uint64_t per = (a.nkb + ns - 1) / ns;
+    const uint64_t waves = ((uint64_t)n_rtp * ns + c->sms - 1) / c->sms;
+    const uint64_t cost = waves * (per + epi_cost);
+    if (cost < best) {
+      best = cost;
+      best_ns = ns;
+    }
+  }
+  a.kb_per_split = (a.nkb + best_ns - 1) / best_ns;
+  a.nsplit = (a.nkb + a.kb_per_split - 1) / a.kb_per_split;
+  if ((uint64_t)a.kb_per_split * tc::kKB >= (1ull << 22)) throw std::runtime_error("tc_gemm: contraction too long for exact s32 sums");
+  const int grid = (int)std::min<uint64_t>((uint64_t)n_rtp * a.nsplit, (uint64_t)c->sms);
+  a.NP = c->NP;
+  a.l = c->l;
+  a.lp = c->lp;
+  a.R = c->d_Racc;
+#define TC_CASE(S_, RT_) \
+  if (c->slices == S_ && c->RT == RT_) { tc_launch_st<S_, RT_>(c, a, grid); return; }
+  TC_CASE(2, 1) TC_CASE(2, 2) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(4, 1) TC_CASE(4, 2)
+#undef TC_CASE
+  throw std::runtime_error("tc_gemm: unsupported slice count");
+}
+
+void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned long long* colmax, const double* F,
+              int writeback, int8_t* Bimg, long long* Csum, double* Fpart, uint32_t* nkb_out) {
+  tc::TcSliceArgs a{};
+  a.X = X;
+  a.lp = c->lp;
+  a.l = c->l;
+  a.S = c->slices;
+  a.NP = c->NP;
+  a.r0 = r0;
+  a.r1 = r1;
+  a.kb0 = (uint32_t)(r0 / tc::kKB);
+  a.colmax = colmax;
+  a.F = F;
+  a.lut = c->lut;
+  a.writeback = writeback;
+  a.Bimg = Bimg;
+  a.Csum = Csum;
+  a.Fpart = Fpart;
+  const uint32_t nkb = (uint32_t)((r1 - 1) / tc::kKB) - a.kb0 + 1;
+  const size_t smem = (size_t)tc::kKB * c->NP + (size_t)tc::kKB * c->l * 8 * (Fpart ? 2 : 1);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(tc::k_tc_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  tc::k_tc_slice<<<nkb, 256, smem, c->stream>>>(a);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+  if (nkb_out) *nkb_out = nkb;
+}
+
+// tensor-core version of range_gemms. PG/PH: tiled operands in which the range starts at local
+// row / contraction index `loc0`; snp0 = first SNP of the range in d_G / d_F.
+void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0,
+                    double* Hacc, bool accumulate) {
+  unsigned long long* o_colmax = c->d_tcs;
+  long long* o_csum = reinterpret_cast<long long*>(c->d_tcs + c->lp);
+  unsigned long long* w_colmax = c->d_tcs + 2 * c->lp;
+  long long* w_csum = reinterpret_cast<long long*>(c->d_tcs + 3 * c->lp);
+  const uint32_t nkb_s = (uint32_t)tc_nkb_samples(c), nrt_s = (uint32_t)tc_nrt_samples(c);
+  {
+    Timed t(c, 0);
+    if (!c->omega_img_valid) {
+      PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
+      tc::k_tc_colmax<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, 0, c->N, o_colmax);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+      tc_slice(c, c->d_Omg, 0, c->N, o_colmax, nullptr, 0, c->d_BimgO, o_csum, nullptr, nullptr);
+      c->omega_img_valid = true;
+    }
+    PCA_CUDA(cudaMemsetAsync(w_colmax, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
+    tc::TcGemmArgs a{};
+    a.PA = PG;
+    a.stride_rt = (uint64_t)nkb_s * tc::kChunkBytes;
+    a.stride_kb = tc::kChunkBytes;
+    a.Bimg = c->d_BimgO;
+    a.rt0 = (uint32_t)(loc0 / tc::kRowTile);
+    a.nrt = (uint32_t)((loc0 + nrows - 1) / tc::kRowTile) - a.rt0 + 1;
+    a.kb0 = 0;
+    a.nkb = nkb_s;
+    a.row_begin = (long long)loc0;
+    a.row_end = (long long)(loc0 + nrows);
+    a.row_r0 = (long long)a.rt0 * tc::kRowTile;
+    {
+      Timed tk(c, 7);
+      tc_launch(c, a);
+    }
+    long long* Rrow = c->d_Racc + (loc0 - (uint64_t)a.row_r0) * c->lp;
+    tc::k_tc_finish_g<<<grid_for((uint64_t)nrows * c->lp, 256, c->sms), 256, 0, c->stream>>>(
+        Rrow, nrows, c->l, c->lp, c->slices, c->d_F + snp0, c->lut, o_csum, o_colmax, c->d_G + snp0 * c->lp, w_colmax);
+    PCA_CHECK_LAUNCH();
+    c->tm.gemm_g_launches++;
+    c->tm.kernel_launches++;
+  }
+  {
+    Timed t(c, 1);
+    uint32_t nkb_w = 0;
+    // contraction index = loc0 + (row of d_G - snp0): hand the slice kernel pointers to index 0
+    double* X0 = c->d_G + snp0 * c->lp - loc0 * c->lp;
+    const double* F0 = c->d_F + snp0 - loc0;
+    tc_slice(c, X0, loc0, loc0 + nrows, w_colmax, F0, 1, c->d_BimgW, w_csum, c->d_Fpart, &nkb_w);
+    tc::TcGemmArgs a{};
+    a.PA = PH;
+    a.stride_rt = tc::kChunkBytes;
+    a.stride_kb = (uint64_t)nrt_s * tc::kChunkBytes;
+    a.Bimg = c->d_BimgW;
+    a.rt0 = 0;
+    a.nrt = nrt_s;
+    a.kb0 = (uint32_t)(loc0 / tc::kKB);
+    a.nkb = nkb_w;
+    a.row_begin = 0;
+    a.row_end = (long long)c->N;
+    a.row_r0 = 0;
+    {
+      Timed tk(c, 8);
+      tc_launch(c, a);
+    }
+    tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
+        c->d_Racc, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, c->d_Fpart, nkb_w, Hacc, accumulate ? 1 : 0);
+    PCA_CHECK_LAUNCH();
+    c->tm.gemm_h_launches++;
+    c->tm.kernel_launches++;
+  }
+  c->tc_ranges++;
+}
+
+// G rows of the range = X^T Omega ; Hacc (+)= X G. `buf` = streamed block buffer holding P, or -1
+// when P points into the resident shard. Ranges without missing genotypes (and no EMU fill) run
+// on the int8 tensor-core kernels when the context was created with a PCAONE_PREC_INT8* mode.
+void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate,
+                 int buf) {
+  if (nrows == 0) return;
+  bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu);
+  if (use_tc) {
+    uint64_t miss = tc_missing_in(c, snp0, nrows);
+    if (miss == UINT64_MAX) {
+      tc_fetch_nmiss(c, snp0, nrows);
+      miss = tc_missing_in(c, snp0, nrows);
+    }
+    use_tc = miss == 0;
+  }
+  if (!use_tc) {
+    range_gemms_fp64(c, P, nrows, snp0, Hacc, accumulate);
+    c->fp64_ranges++;
+    return;
+  }
+  tc_alloc(c, std::max<uint64_t>(nrows, c->max_block));
+  if (buf < 0) {
+    if (!c->tiles_valid) {
+      if (!c->d_PG) {
+        PCA_CUDA(cudaMalloc((void**)&c->d_PG, tc_pg_bytes(c, c->M)));
+        PCA_CUDA(cudaMalloc((void**)&c->d_PH, tc_ph_bytes(c, c->M)));
+      }
+      tc_build_tiles(c, c->d_packed, c->M, c->d_PG, c->d_PH, c->stream);
+      c->tiles_valid = true;
+    }
+    range_gemms_tc(c, c->d_PG, c->d_PH, snp0, nrows, snp0, Hacc, accumulate);
+  } else {
+    if (!c->d_PGb[buf]) {
+      PCA_CUDA(cudaMalloc((void**)&c->d_PGb[buf], tc_pg_bytes(c, c->max_block)));
+      PCA_CUDA(cudaMalloc((void**)&c->d_PHb[buf], tc_ph_bytes(c, c->max_block)));
+    }
+    tc_build_tiles(c, P, nrows, c->d_PGb[buf], c->d_PHb[buf], c->stream);
+    range_gemms_tc(c, c->d_PGb[buf], c->d_PHb[buf], 0, nrows, snp0, Hacc, accumulate);
   }
 }
 
@@ -444,6 +724,7 @@ void update_omega(pcaone_ctx* c, const double* H, bool flip) {
     c->tm.kernel_launches++;
   }
   c->tm.omega_updates++;
+  c->omega_img_valid = false;
 }
 
 // ---------------------------------------------------------------- host <-> device matrices
@@ -591,6 +872,7 @@ void compute_gandh(pcaone_ctx* c, int pi) {
     if (!c->have_omg0) throw std::runtime_error("call pcaone_set_omega before the first pass");
     PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->omega_img_valid = false;
   }
   if (ooc) {
     if (c->blk_start.empty()) throw std::runtime_error("out-of-core source needs pcaone_set_blocks");
@@ -608,12 +890,12 @@ void compute_gandh(pcaone_ctx* c, int pi) {
     }
     if (!ooc) {
       if (c->blk_start.empty()) {
-        range_gemms(c, c->d_packed, (uint32_t)c->M, 0, c->d_H, false);
+        range_gemms(c, c->d_packed, (uint32_t)c->M, 0, c->d_H, false, -1);
       } else {
         zero_async(c, c->d_H, HN);
         for (size_t b = 0; b < c->blk_start.size(); ++b)
           range_gemms(c, c->d_packed + c->blk_start[b] * c->pitch, (uint32_t)(c->blk_stop[b] - c->blk_start[b] + 1),
-                      c->blk_start[b], c->d_H, true);
+                      c->blk_start[b], c->d_H, true, -1);
       }
     } else {
       zero_async(c, c->d_H, HN);
@@ -622,7 +904,7 @@ void compute_gandh(pcaone_ctx* c, int pi) {
         const uint8_t* P = stage_block(c, b, buf);
         const uint64_t nrows = c->blk_stop[b] - c->blk_start[b] + 1;
         block_af_if_needed(c, P, c->blk_start[b], nrows);
-        range_gemms(c, P, (uint32_t)nrows, c->blk_start[b], c->d_H, true);
+        range_gemms(c, P, (uint32_t)nrows, c->blk_start[b], c->d_H, true, buf);
         PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
       }
       c->af_done = true;
@@ -659,12 +941,12 @@ void compute_gandh(pcaone_ctx* c, int pi) {
     if (steps[b].stop >= steps[b].start) {
       const uint64_t s0 = steps[b].start, nrows = steps[e].stop - s0 + 1;
       if (!ooc) {
-        range_gemms(c, c->d_packed + s0 * c->pitch, (uint32_t)nrows, s0, Hacc, true);
+        range_gemms(c, c->d_packed + s0 * c->pitch, (uint32_t)nrows, s0, Hacc, true, -1);
       } else {
         const int buf = (int)(b & 1);
         const uint8_t* P = stage_block(c, (uint32_t)b, buf);
         block_af_if_needed(c, P, s0, nrows);
-        range_gemms(c, P, (uint32_t)nrows, s0, Hacc, true);
+        range_gemms(c, P, (uint32_t)nrows, s0, Hacc, true, buf);
         PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
       }
     }
@@ -845,10 +1127,19 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     if (c->N == 0 || c->M == 0 || c->k == 0) throw std::runtime_error("nsamples, nsnps and k must be positive");
     if (c->l > kMaxL) throw std::runtime_error("k + oversamples must be <= 112");
     if ((uint64_t)c->l > c->N || (uint64_t)c->l > c->M) throw std::runtime_error("k + oversamples exceeds the matrix size");
-    if (cfg->precision != PCAONE_PREC_FP64) throw std::runtime_error("only PCAONE_PREC_FP64 is built in this library");
+    if (cfg->precision != PCAONE_PREC_FP64 && cfg->precision != PCAONE_PREC_INT8X2 &&
+        cfg->precision != PCAONE_PREC_INT8X3 && cfg->precision != PCAONE_PREC_INT8X4)
+      throw std::runtime_error("precision must be PCAONE_PREC_FP64 or PCAONE_PREC_INT8X2/3/4");
     if (cfg->svd != PCAONE_SVD_SSVD && cfg->svd != PCAONE_SVD_WINSVD) throw std::runtime_error("svd must be 1 or 2");
     c->NT = supported_nt(c->l);
     c->lp = c->NT * 8;
+    if (cfg->precision != PCAONE_PREC_FP64) {
+      c->slices = cfg->precision;
+      c->NP = (int)round_up((size_t)c->slices * c->l, 16);
+      if (c->NP > tc::kMaxNP)
+        throw std::runtime_error("slices * (k + oversamples) must be <= 256 for the tensor-core path");
+      c->RT = c->NP <= 128 ? 2 : 1;
+    }
     c->bpr = (uint32_t)((c->N + 3) >> 2);
     c->pitch = (uint32_t)round_up(c->bpr, 16);
     c->lut.sqrt_ploidy = sqrt((double)cfg->ploidy);
@@ -883,6 +1174,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     dmalloc(&c->d_F, c->M);
     dmalloc(&c->d_nmiss, c->M);
     PCA_CUDA(cudaMemset(c->d_F, 0, c->M * sizeof(double)));
+    PCA_CUDA(cudaMemset(c->d_nmiss, 0xff, c->M * sizeof(uint32_t)));  // unknown -> treated as "has missing"
     const uint32_t tiles = ceil_div(c->N, kTileRows);
     c->max_splits = std::max<uint32_t>(1, std::min<uint32_t>(64, (2u * c->sms + tiles - 1) / tiles));
     dmalloc(&c->d_Hpart, (size_t)c->max_splits * NL);
@@ -917,7 +1209,9 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_W, (void*)c->d_R, (void*)c->d_Rinv, (void*)c->d_T1, (void*)c->d_T2, (void*)c->d_T,
                   (void*)c->d_Vr, (void*)c->d_Z, (void*)c->d_sigma, (void*)c->d_sign, (void*)c->d_hsign, (void*)c->d_scal,
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
-                  (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1]})
+                  (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
+                  (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
+                  (void*)c->d_Racc, (void*)c->d_tcs, (void*)c->d_Fpart})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -975,6 +1269,9 @@ int pcaone_upload_bed(pcaone_ctx* c, const uint8_t* packed, uint64_t nsnps, int 
     PCA_CUDA(cudaStreamSynchronize(c->stream));
     c->source = PCAONE_SRC_RESIDENT;
     c->af_done = false;
+    c->tiles_valid = false;
+    c->h_nmiss.clear();
+    c->nmiss_prefix.clear();
   });
 }
 
@@ -1031,11 +1328,21 @@ int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
     k_gather_f64<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, d_Fn, d_idx, c->M);
     PCA_CHECK_LAUNCH();
     PCA_CUDA(cudaStreamSynchronize(c->stream));
+    uint32_t* d_nm = nullptr;
+    dmalloc(&d_nm, c->M);
+    k_gather_u32<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_nmiss, d_nm, d_idx, c->M);
+    PCA_CHECK_LAUNCH();
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(c->d_packed);
     cudaFree(c->d_F);
+    cudaFree(c->d_nmiss);
     cudaFree(d_idx);
     c->d_packed = d_new;
     c->d_F = d_Fn;
+    c->d_nmiss = d_nm;
+    c->tiles_valid = false;
+    c->h_nmiss.clear();
+    c->nmiss_prefix.clear();
   });
 }
 
@@ -1244,8 +1551,13 @@ int pcaone_ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* 
 int pcaone_get_timers(pcaone_ctx* c, pcaone_timers* out, int reset) {
   CTX_GUARD(c, {
     resolve_timers(c);
+    c->tm.tc_ranges = c->tc_ranges;
+    c->tm.fp64_ranges = c->fp64_ranges;
     if (out) *out = c->tm;
-    if (reset) c->tm = pcaone_timers{};
+    if (reset) {
+      c->tm = pcaone_timers{};
+      c->tc_ranges = c->fp64_ranges = 0;
+    }
   });
 }
 int pcaone_enable_timing(pcaone_ctx* c, int on) { CTX_GUARD(c, c->timing = on != 0); }

@@ -1,0 +1,502 @@
+// pcaone_b200 — error-free tensor-core GEMMs for the power-iteration products (sm_100a).
+//
+//   G_b = X_b^T * Omega   (reference Halko.cpp:125,150,195-196,243)
+//   H  += X_b   * G_b     (reference Halko.cpp:126,151,200-202,246-248)
+//
+// Both are the same contraction  T[row][c] = sum_k u(row,k) * I[k][c]  of a packed 2-bit operand
+// (rows x K, two bits per entry, u = popcount(code) in {0,1,2} = 2 - dosage) with a tall dense
+// matrix, run on the 5th-generation tensor cores as EXACT integer arithmetic (Ozaki scheme):
+//
+//  * the dense operand (Omega, or W = s o G) is rounded ONCE to S signed 8-bit slices per entry
+//    against a per-column power-of-two scale (k_tc_slice): X~ = I * 2^(e_c - p), p = 8S - 1,
+//    I = sum_s d_s 256^(S-1-s), d_s in [-128,127]. The rounded matrix X~ is what the algorithm
+//    then uses everywhere (G~ is written back), so H = X G~ holds to FP64 accuracy and the
+//    rounding only perturbs the iterate the way a slightly different Omega would;
+//  * the packed codes are expanded in registers to int8 (one shift + one mask per four
+//    genotypes) and written straight into TENSOR MEMORY as the A operand (tcgen05.st), never
+//    through shared memory; the slices are the B operand, bulk-copied (UBLKCP) into a shared
+//    memory ring in the UMMA no-swizzle K-major core-matrix layout;
+//  * tcgen05.mma kind::i8 accumulates s32 in TMEM — exact for K < 2^23 — and the epilogue folds
+//    the S slice sums into one int64 per (row, column) and adds it to global memory with integer
+//    atomics, so split-K partials combine in any order to the same bits;
+//  * centring, scaling by sqrt(ploidy)/sqrt(F(1-F)) and the column-sum (rank-1) terms are applied
+//    in FP64 by the finish kernels below.
+//
+// Missing genotypes (code 01) and the EMU fill are not expressible as u in {0,1,2}: ranges that
+// contain them run on the FP64 DMMA kernels (gemm_fp64.cuh) instead — still on the GPU.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pcaone {
+namespace tc {
+
+constexpr int kRowTile = 128;  // rows per UMMA (M)
+constexpr int kKB = 64;        // contraction entries per k-block = one 16-byte packed load
+constexpr int kNAS = 4;        // A stages per row tile (TMEM ring)
+constexpr int kNBS = 8;        // B stages (shared-memory ring)
+constexpr int kAcol0 = 256;    // first TMEM column of the A ring (accumulators use [0,256))
+constexpr int kPF = 4;         // packed loads in flight per decode thread
+constexpr int kMaxNP = 256;
+constexpr uint32_t kChunkBytes = kRowTile * 16;  // one (row tile, k-block) chunk of the tiled operand
+
+__host__ __device__ constexpr int tc_threads(int RT) { return 128 + 128 * RT; }
+__host__ __device__ constexpr size_t tc_scratch_bytes(int RT) { return (size_t)4 * RT * 32 * 17 * 8; }
+__host__ __device__ inline size_t tc_smem_bytes(int RT, int NP) { return (size_t)kNBS * kKB * NP + tc_scratch_bytes(RT); }
+
+// position inside a k-block at which the decode puts source entry g (see decode64)
+__host__ __device__ __forceinline__ int kpos_of(int g) {
+  const int x = g >> 4, rem = g & 15;
+  return (x << 4) | ((rem & 3) << 2) | (rem >> 2);
+}
+// byte offset of element (n, kp) inside one k-block image of the B operand
+__host__ __device__ __forceinline__ uint32_t bimg_offset(int n, int kp, int NP) {
+  return (uint32_t)(((kp >> 4) * (NP >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (kp & 15));
+}
+
+// 64 two-bit codes (one uint4) -> 64 int8 values u = popcount(code), 4 per word.
+// Word 4x+w, byte b holds source entry 16x + w + 4b  (=> kpos_of).
+__device__ __forceinline__ void decode64(const uint4& q, uint32_t (&o)[16]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const uint32_t t = (w[x] & 0x55555555u) + ((w[x] >> 1) & 0x55555555u);
+    o[4 * x + 0] = t & 0x03030303u;
+    o[4 * x + 1] = (t >> 2) & 0x03030303u;
+    o[4 * x + 2] = (t >> 4) & 0x03030303u;
+    o[4 * x + 3] = (t >> 6) & 0x03030303u;
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+struct TcGemmArgs {
+  const uint8_t* PA;              // tiled packed operand: chunk(rt, kb) = PA + rt*stride_rt + kb*stride_kb
+  uint64_t stride_rt, stride_kb;  // bytes
+  const int8_t* Bimg;             // k-block images of this launch, image of kb0 first, 64*NP bytes each
+  uint32_t rt0, nrt;              // row tiles of the launch: [rt0, rt0 + nrt)
+  uint32_t kb0, nkb;              // k-blocks of the launch: [kb0, kb0 + nkb)
+  uint32_t kb_per_split, nsplit;  // split-K decomposition
+  uint32_t NP, l, lp;             // padded UMMA N (= round_up(S*l,16)), columns, leading dim of R
+  long long row_begin, row_end;   // absolute rows that receive output
+  long long row_r0;               // absolute row stored at R[0]
+  long long* R;                   // [rows][lp] int64 accumulators (zero on entry, added to)
+};
+
+template <int S, int RT>
+__global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t b_full[kNBS], b_empty[kNBS], a_full[RT][kNAS], a_empty[RT][kNAS], acc_full, acc_empty;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = kKB * a.NP;
+  uint8_t* Bs = smem;
+  long long* scratch = reinterpret_cast<long long*>(smem + (size_t)kNBS * stage_bytes);
+
+  if (warp == 2) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNBS; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int t = 0; t < RT; ++t)
+      for (int i = 0; i < kNAS; ++i) {
+        mbar_init(&a_full[t][i], 4);
+        mbar_init(&a_empty[t][i], 1);
+      }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 4 * RT);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+
+  const uint32_t n_rtp = (a.nrt + RT - 1) / RT;
+  const uint32_t n_items = n_rtp * a.nsplit;
+
+  if (warp == 0) {
+    // ------------------------------------------------ B producer: bulk copies into the smem ring
+    if (lane == 0) {
+      uint32_t kit = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t sp = item / n_rtp;
+        const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
+        const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
+        for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++kit) {
+          const uint32_t bs = kit % kNBS, ph = (kit / kNBS) & 1;
+          mbar_wait(&b_empty[bs], ph ^ 1);
+          mbar_expect_tx(&b_full[bs], stage_bytes);
+          bulk_g2s(Bs + (size_t)bs * stage_bytes, a.Bimg + (size_t)(kb - a.kb0) * stage_bytes, stage_bytes,
+                   &b_full[bs]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_i8(kRowTile, (int)a.NP);
+      const uint32_t lbo = (a.NP >> 3) * 128, sbo = 128;
+      uint32_t kit = 0, ait[RT], n = 0;
+#pragma unroll
+      for (int t = 0; t < RT; ++t) ait[t] = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
+        const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
+        const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
+        const uint32_t ntile = min((uint32_t)RT, a.nrt - rtp * RT);
+        mbar_wait(&acc_empty, (n & 1) ^ 1);
+        tc_fence_after();
+        for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++kit) {
+          const uint32_t bs = kit % kNBS, bph = (kit / kNBS) & 1;
+          mbar_wait(&b_full[bs], bph);
+          const uint32_t bsaddr = smem_u32(Bs + (size_t)bs * stage_bytes);
+#pragma unroll
+          for (int t = 0; t < RT; ++t) {
+            if ((uint32_t)t < ntile) {
+              const uint32_t as = ait[t] % kNAS, aph = (ait[t] / kNAS) & 1;
+              mbar_wait(&a_full[t][as], aph);
+              tc_fence_after();
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t bd = smem_desc_kmajor_noswizzle(bsaddr + ks * 2 * lbo, lbo, sbo);
+                umma_i8_ts(tbase + t * a.NP, tbase + kAcol0 + (t * kNAS + as) * 16 + ks * 8, bd, idesc,
+                           (kb > kb_begin || ks > 0) ? 1u : 0u);
+              }
+              umma_commit(&a_empty[t][as]);
+              ++ait[t];
+            }
+          }
+          umma_commit(&b_empty[bs]);
+        }
+        umma_commit(&acc_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ decode warps (A producer) + epilogue
+    const int t = (warp - 4) >> 2, q = warp & 3;
+    const uint32_t rloc = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    long long* my_scratch = scratch + (size_t)(warp - 4) * 32 * 17;
+    uint32_t ait = 0, n = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
+      const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
+      const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
+      const uint32_t ntile = min((uint32_t)RT, a.nrt - rtp * RT);
+      const bool active = (uint32_t)t < ntile;
+      const uint32_t rt = a.rt0 + rtp * RT + t;
+      if (active) {
+        const uint8_t* p = a.PA + (uint64_t)rt * a.stride_rt + (uint64_t)rloc * 16;
+        uint4 buf[kPF];
+#pragma unroll
+        for (int j = 0; j < kPF; ++j)
+          if (kb_begin + j < kb_end) buf[j] = ldg_stream16(p + (uint64_t)(kb_begin + j) * a.stride_kb);
+        for (uint32_t kb = kb_begin; kb < kb_end; kb += kPF) {
+#pragma unroll
+          for (int j = 0; j < kPF; ++j) {
+            if (kb + j < kb_end) {
+              uint32_t o[16];
+              decode64(buf[j], o);
+              if (kb + j + kPF < kb_end) buf[j] = ldg_stream16(p + (uint64_t)(kb + j + kPF) * a.stride_kb);
+              const uint32_t as = ait % kNAS, aph = (ait / kNAS) & 1;
+              mbar_wait(&a_empty[t][as], aph ^ 1);
+              tc_fence_after();
+              tmem_st16(tbase + lane_addr + kAcol0 + (t * kNAS + as) * 16, o);
+              tmem_wait_st();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_full[t][as]);
+              ++ait;
+            }
+          }
+        }
+      }
+      // ---- epilogue: s32 slice sums -> one int64 per (row, column) -> integer atomics
+      mbar_wait(&acc_full, n & 1);
+      tc_fence_after();
+      const long long row0 = (long long)rt * kRowTile + q * 32;  // first row of this warp
+      for (uint32_t c0 = 0; c0 < a.l; c0 += 16) {
+        if (active) {
+          uint32_t v[S][16];
+#pragma unroll
+          for (int s = 0; s < S; ++s) tmem_ld16(tbase + lane_addr + t * a.NP + c0 * S + 16 * s, v[s]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int ci = 0; ci < 16; ++ci) {
+            long long acc = 0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const int f = ci * S + s;
+              acc += (long long)(int32_t)v[f >> 4][f & 15] << (8 * (S - 1 - s));
+            }
+            my_scratch[lane * 17 + ci] = acc;
+          }
+          __syncwarp();
+          // two rows per step: lanes 0-15 row rr, lanes 16-31 row rr+1; 16 consecutive columns each
+          const int ci = lane & 15;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr += 2) {
+            const int r = rr + (lane >> 4);
+            const long long row = row0 + r;
+            const long long val = my_scratch[r * 17 + ci];
+            if (row >= a.row_begin && row < a.row_end && c0 + ci < a.l && val != 0)
+              atomicAdd(reinterpret_cast<unsigned long long*>(a.R + (row - a.row_r0) * a.lp + c0 + ci),
+                        (unsigned long long)val);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tbase);
+}
+
+// ------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------
+
+// Row-tiled copy of the SNP-major packed rows ([rows][pitch]): chunk (rt, kb) holds, for each of
+// 128 rows, the 16 bytes of k-block kb. dst chunk = dst + (rt * nkb + kb) * 2 KB.
+// Entries beyond `ncols` (sample padding of the last byte; the reference ignores those bits,
+// FilePlink.cpp:42) and rows beyond `rows` are code 00 (u = 0).
+__global__ void k_tile_rows(const uint8_t* __restrict__ P, uint32_t pitch, uint64_t rows, uint32_t ncols,
+                            uint32_t nkb, uint8_t* __restrict__ dst) {
+  const uint64_t total = (uint64_t)((rows + kRowTile - 1) / kRowTile) * nkb * kRowTile;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(idx % kRowTile);
+    const uint64_t chunk = idx / kRowTile;
+    const uint32_t kb = (uint32_t)(chunk % nkb);
+    const uint64_t rt = chunk / nkb;
+    const uint64_t row = rt * kRowTile + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < rows && kb * 16 < pitch) {
+      v = *reinterpret_cast<const uint4*>(P + row * pitch + kb * 16);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const long long first = (long long)kb * 64 + x * 16;
+        const long long nvalid = (long long)ncols - first;
+        if (nvalid <= 0)
+          w[x] = 0;
+        else if (nvalid < 16)
+          w[x] &= (1u << (2 * nvalid)) - 1u;
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + chunk * kChunkBytes + r * 16) = v;
+  }
+}
+
+// Transposed tiled copy: rows = samples, contraction = SNPs. chunk (kb, rt) = dst + (kb * nrt + rt)
+// * 2 KB; row r = sample rt*128 + r, byte q = SNPs kb*64 + 4q .. +3 (two bits each, same bit
+// order as the bed file along its own axis). SNPs >= nsnps and samples >= N are code 00.
+__global__ void __launch_bounds__(128) k_tile_transpose(const uint8_t* __restrict__ P, uint32_t pitch, uint64_t nsnps,
+                                                        uint32_t N, uint32_t nrt, uint8_t* __restrict__ dst) {
+  __shared__ uint32_t tile[kKB][9];  // 64 SNP rows x 32 bytes (128 samples), padded
+  const uint32_t rt = blockIdx.x % nrt;
+  const uint64_t kb = blockIdx.x / nrt;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kKB * 8; i += 128) {
+    const int g = i >> 3, wq = i & 7;
+    const uint64_t snp = kb * kKB + g;
+    const uint32_t byte0 = rt * 32 + wq * 4;
+    uint32_t w = 0;
+    if (snp < nsnps && byte0 < pitch) w = *reinterpret_cast<const uint32_t*>(P + snp * pitch + byte0);
+    tile[g][wq] = w;
+  }
+  __syncthreads();
+  const uint32_t sample = rt * kRowTile + tid;
+  uint32_t out[4] = {0, 0, 0, 0};
+  if (sample < N) {
+    const int wq = tid >> 4, sh = (tid & 15) * 2;
+#pragma unroll 16
+    for (int g = 0; g < kKB; ++g) {
+      const uint32_t code = (tile[g][wq] >> sh) & 3u;
+      out[g >> 4] |= code << (2 * (g & 15));
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + ((uint64_t)kb * nrt + rt) * kChunkBytes + tid * 16) =
+      make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// column abs-max of X[r0..r1)[0..l) (times an optional per-row factor) -> colmax bits (atomicMax on
+// the IEEE pattern, order-preserving for non-negative doubles)
+__global__ void k_tc_colmax(const double* __restrict__ X, int lp, int l, uint64_t r0, uint64_t r1,
+                            unsigned long long* __restrict__ colmax) {
+  __shared__ unsigned long long smax[kMaxNP];
+  for (int c = threadIdx.x; c < l; c += blockDim.x) smax[c] = 0ull;
+  __syncthreads();
+  const uint64_t total = (r1 - r0) * (uint64_t)lp;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % lp);
+    if (c < l) atomicMax(&smax[c], (unsigned long long)__double_as_longlong(fabs(X[r0 * lp + idx])));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < l; c += blockDim.x)
+    if (smax[c]) atomicMax(&colmax[c], smax[c]);
+}
+
+// power-of-two column scale: X~ = I * 2^(e - p) with |I| < 127.5 * 256^(S-1)
+__device__ __forceinline__ int tc_exponent(unsigned long long maxbits) {
+  const double m = __longlong_as_double((long long)maxbits);
+  if (!(m > 0.0)) return 0;
+  return ilogb(m * (128.0 / 126.0)) + 1;
+}
+
+struct TcSliceArgs {
+  double* X;                          // [rows][lp], rows indexed by the contraction index
+  int lp, l, S, NP;
+  uint64_t r0, r1;                    // contraction entries [r0, r1) are live, the rest of the k-blocks is zero
+  uint32_t kb0;                       // first k-block of the image (= r0 / 64)
+  const unsigned long long* colmax;   // per-column abs max bits
+  const double* F;                    // per-row allele frequency (indexed like X rows) or nullptr
+  LutParams lut;
+  int writeback;                      // X[row][c] <- X~[row][c] / s_row  (G~ for the QR stage)
+  int8_t* Bimg;                       // out: [nkb][64*NP]
+  long long* Csum;                    // out (atomic): sum_rows I[row][c]
+  double* Fpart;                      // out: [gridDim.x][lp] partial sums of f_row * X~[row][c], or nullptr
+};
+
+// One block per k-block. In: X rows are W = s o G (H pass; F != nullptr, the kernel multiplies by
+// s_row itself) or Omega (G pass).
+__global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  int8_t* img = reinterpret_cast<int8_t*>(sm);                                   // 64*NP
+  double* fw = reinterpret_cast<double*>(sm + (size_t)kKB * a.NP);               // [64][l] (only if Fpart)
+  long long* ci = reinterpret_cast<long long*>(sm + (size_t)kKB * a.NP + (a.Fpart ? (size_t)kKB * a.l * 8 : 0));  // [64][l]
+  const uint32_t kb = a.kb0 + blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kKB * a.NP / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int g = tid & 63, cg = tid >> 6;
+  const uint64_t row = (uint64_t)kb * kKB + g;
+  const bool live = row >= a.r0 && row < a.r1;
+  const int kp = kpos_of(g);
+  const int p = 8 * a.S - 1;
+  double s_row = 1.0, f_row = 0.0;
+  if (live && a.F) {
+    f_row = a.F[row];
+    s_row = snp_scale(f_row, a.lut);
+  }
+  for (int c = cg; c < a.l; c += 4) {
+    long long I = 0;
+    double xt = 0.0;
+    if (live) {
+      const int e = tc_exponent(a.colmax[c]);
+      const double x = a.X[row * a.lp + c] * s_row;
+      I = llrint(scalbn(x, p - e));
+      xt = scalbn((double)I, e - p);
+      if (a.writeback) a.X[row * a.lp + c] = xt / s_row;
+      long long rem = I;
+#pragma unroll 1
+      for (int s = a.S - 1; s >= 0; --s) {
+        long long d;
+        if (s > 0) {
+          d = ((rem + 128) & 255) - 128;
+          rem = (rem - d) >> 8;
+        } else {
+          d = rem;
+        }
+        img[bimg_offset(c * a.S + s, kp, a.NP)] = (int8_t)d;
+      }
+    }
+    ci[g * a.l + c] = I;
+    if (a.Fpart) fw[g * a.l + c] = f_row * xt;
+  }
+  __syncthreads();
+  for (int i = tid; i < kKB * a.NP / 16; i += 256)
+    reinterpret_cast<uint4*>(a.Bimg + (size_t)blockIdx.x * kKB * a.NP)[i] = reinterpret_cast<const uint4*>(img)[i];
+  for (int c = tid; c < a.l; c += 256) {
+    long long sc = 0;
+    double sf = 0.0;
+    for (int r = 0; r < kKB; ++r) {
+      sc += ci[r * a.l + c];
+      if (a.Fpart) sf += fw[r * a.l + c];
+    }
+    if (sc) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + c), (unsigned long long)sc);
+    if (a.Fpart) a.Fpart[(size_t)blockIdx.x * a.lp + c] = sf;
+  }
+}
+
+// G pass finish: W[j][c] = s_j * G[j][c],  G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * C_c - T[j][c] / 2)
+// written to Gout rows (the slice kernel turns W into G~ afterwards); also the column abs-max of
+// W for that slicing. R is re-zeroed.
+__global__ void k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S,
+                              const double* __restrict__ F, LutParams lut, const long long* __restrict__ Csum,
+                              const unsigned long long* __restrict__ colmax_in, double* __restrict__ Gout,
+                              unsigned long long* __restrict__ colmax_out) {
+  __shared__ unsigned long long smax[kMaxNP];
+  for (int c = threadIdx.x; c < l; c += blockDim.x) smax[c] = 0ull;
+  __syncthreads();
+  const int p = 8 * S - 1;
+  const uint64_t total = nrows * (uint64_t)lp;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = idx / lp;
+    const int c = (int)(idx - j * lp);
+    double w = 0.0;
+    if (c < l) {
+      const long long T = R[idx];
+      R[idx] = 0;
+      const double f = F[j];
+      const double s = snp_scale(f, lut);
+      const double g = scalbn((1.0 - f) * (double)Csum[c] - 0.5 * (double)T, tc_exponent(colmax_in[c]) - p) * s;
+      w = g;  // G itself; the slice kernel applies s again to form W
+      atomicMax(&smax[c], (unsigned long long)__double_as_longlong(fabs(g * s)));
+    }
+    Gout[idx] = w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < l; c += blockDim.x)
+    if (smax[c]) atomicMax(&colmax_out[c], smax[c]);
+}
+
+// H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c ,  Fw_c = sum of the slice
+// kernel's per-block partials in block order. R is re-zeroed.
+__global__ void k_tc_finish_h(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S,
+                              const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax,
+                              const double* __restrict__ Fpart, uint32_t nparts, double* __restrict__ Hacc,
+                              int accumulate) {
+  __shared__ double sFw[kMaxNP], sScale[kMaxNP], sC[kMaxNP];
+  const int p = 8 * S - 1;
+  for (int c = threadIdx.x; c < l; c += blockDim.x) {
+    double f = 0.0;
+    for (uint32_t b = 0; b < nparts; ++b) f += Fpart[(size_t)b * lp + c];
+    sFw[c] = f;
+    sScale[c] = scalbn(1.0, tc_exponent(colmax[c]) - p);
+    sC[c] = (double)Csum[c];
+  }
+  __syncthreads();
+  const uint64_t total = nrows * (uint64_t)lp;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % lp);
+    if (c < l) {
+      const long long T = R[idx];
+      R[idx] = 0;
+      const double h = sScale[c] * (sC[c] - 0.5 * (double)T) - sFw[c];
+      Hacc[idx] = accumulate ? Hacc[idx] + h : h;
+    } else if (!accumulate) {
+      Hacc[idx] = 0.0;
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace pcaone
