@@ -45,53 +45,76 @@ def _peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML
+    (nvidia_ml_py) every 100 ms; falls back to one `nvidia-smi` query when NVML is unavailable.
+    (A polling `nvidia-smi -lms` child process contends for the driver lock and slows down a
+    launch-bound timed region several-fold, so it is not used.)"""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.t = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs: map the CUDA ordinal through CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.idx < len(ids) and ids[self.idx].isdigit():
+                    phys = int(ids[self.idx])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nv is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted({n for _, _, rs in self.samples for n, bit in names.items() if rs & bit})
+        sm = [x[0] for x in self.samples]
+        mx = [x[1] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml in-process, 100 ms"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=5)
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                    "reasons": [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")],
+                    "samples": 1, "source": "nvidia-smi, one query after the timed region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
 def cpu_reference_pass(packed_host, n_samples, k, steps, warmup, threads):

@@ -317,7 +317,7 @@ void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
   if (!c->d_tcs) {
     dmalloc(&c->d_tcs, (size_t)4 * c->lp);
     PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)4 * c->lp * sizeof(unsigned long long), c->stream));
-    dmalloc(&c->d_BimgO, (size_t)tc_nkb_samples(c) * tc::kKB * c->NP);
+    dmalloc(&c->d_BimgO, (size_t)(tc_nkb_samples(c) + 1) * tc::kKB * c->NP);
   }
   const size_t need_rows = std::max<uint64_t>(tc_nrt_samples(c) * tc::kRowTile, max_range_rows + 2 * tc::kRowTile);
   if (need_rows > c->R_rows) {
@@ -326,7 +326,7 @@ void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
     PCA_CUDA(cudaMemsetAsync(c->d_Racc, 0, need_rows * c->lp * sizeof(long long), c->stream));
     c->R_rows = need_rows;
   }
-  const size_t need_kb = max_range_rows / tc::kKB + 2;
+  const size_t need_kb = max_range_rows / tc::kKB + 4;
   if (need_kb > c->bimgW_kb) {
     if (c->d_BimgW) cudaFree(c->d_BimgW);
     if (c->d_Fpart) cudaFree(c->d_Fpart);
@@ -382,7 +382,7 @@ void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a) {
   uint64_t best = UINT64_MAX;
   const uint32_t max_ns = std::max<uint32_t>(1, a.nkb / 8);
   for (uint32_t ns = 1; ns <= std::min<uint32_t>(max_ns, 4u * c->sms); ++ns) {
-    const uint64_t per = (a.nkb + ns - 1) / ns;
+    const uint64_t per = ((a.nkb + ns - 1) / ns + 1) & ~1ull;
     const uint64_t waves = ((uint64_t)n_rtp * ns + c->sms - 1) / c->sms;
     const uint64_t cost = waves * (per + epi_cost);
     if (cost < best) {
@@ -390,7 +390,7 @@ void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a) {
       best_ns = ns;
     }
   }
-  a.kb_per_split = (a.nkb + best_ns - 1) / best_ns;
+  a.kb_per_split = ((a.nkb + best_ns - 1) / best_ns + 1) & ~1u;
   a.nsplit = (a.nkb + a.kb_per_split - 1) / a.kb_per_split;
   if ((uint64_t)a.kb_per_split * tc::kKB >= (1ull << 22)) throw std::runtime_error("tc_gemm: contraction too long for exact s32 sums");
   const int grid = (int)std::min<uint64_t>((uint64_t)n_rtp * a.nsplit, (uint64_t)c->sms);
@@ -423,7 +423,8 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
   a.Bimg = Bimg;
   a.Csum = Csum;
   a.Fpart = Fpart;
-  const uint32_t nkb = (uint32_t)((r1 - 1) / tc::kKB) - a.kb0 + 1;
+  // an even number of k-block images: a pipeline stage of k_tc_gemm is two k-blocks (the pad image is zero)
+  const uint32_t nkb = ((uint32_t)((r1 - 1) / tc::kKB) - a.kb0 + 2) & ~1u;
   const size_t smem = (size_t)tc::kKB * c->NP + (size_t)tc::kKB * c->l * 8 * (Fpart ? 2 : 1);
   static size_t attr = 0;
   if (smem > attr) {
@@ -464,7 +465,8 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     a.rt0 = (uint32_t)(loc0 / tc::kRowTile);
     a.nrt = (uint32_t)((loc0 + nrows - 1) / tc::kRowTile) - a.rt0 + 1;
     a.kb0 = 0;
-    a.nkb = nkb_s;
+    a.nkb = (nkb_s + 1) & ~1u;
+    a.kb_valid_last = nkb_s - 1;
     a.row_begin = (long long)loc0;
     a.row_end = (long long)(loc0 + nrows);
     a.row_r0 = (long long)a.rt0 * tc::kRowTile;
@@ -495,6 +497,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     a.nrt = nrt_s;
     a.kb0 = (uint32_t)(loc0 / tc::kKB);
     a.nkb = nkb_w;
+    a.kb_valid_last = (uint32_t)((loc0 + nrows - 1) / tc::kKB);
     a.row_begin = 0;
     a.row_end = (long long)c->N;
     a.row_r0 = 0;

@@ -32,17 +32,19 @@ namespace pcaone {
 namespace tc {
 
 constexpr int kRowTile = 128;  // rows per UMMA (M)
-constexpr int kKB = 64;        // contraction entries per k-block = one 16-byte packed load
-constexpr int kNAS = 4;        // A stages per row tile (TMEM ring)
-constexpr int kNBS = 8;        // B stages (shared-memory ring)
+constexpr int kKB = 64;        // contraction entries per k-block = one 16-byte packed load per row
+constexpr int kStageKB = 2;    // k-blocks per pipeline stage (128 contraction entries = 4 UMMAs per row tile)
+constexpr int kNS = 4;         // pipeline stages: A ring in TMEM + B ring in shared memory
 constexpr int kAcol0 = 256;    // first TMEM column of the A ring (accumulators use [0,256))
-constexpr int kPF = 4;         // packed loads in flight per decode thread
+constexpr int kPF = 4;         // stages of packed loads in flight per decode thread (2 x 16 B each)
 constexpr int kMaxNP = 256;
 constexpr uint32_t kChunkBytes = kRowTile * 16;  // one (row tile, k-block) chunk of the tiled operand
 
 __host__ __device__ constexpr int tc_threads(int RT) { return 128 + 128 * RT; }
 __host__ __device__ constexpr size_t tc_scratch_bytes(int RT) { return (size_t)4 * RT * 32 * 17 * 8; }
-__host__ __device__ inline size_t tc_smem_bytes(int RT, int NP) { return (size_t)kNBS * kKB * NP + tc_scratch_bytes(RT); }
+__host__ __device__ inline size_t tc_smem_bytes(int RT, int NP) {
+  return (size_t)kNS * kStageKB * kKB * NP + tc_scratch_bytes(RT);
+}
 
 // position inside a k-block at which the decode puts source entry g (see decode64)
 __host__ __device__ __forceinline__ int kpos_of(int g) {
@@ -56,7 +58,7 @@ __host__ __device__ __forceinline__ uint32_t bimg_offset(int n, int kp, int NP) 
 
 // 64 two-bit codes (one uint4) -> 64 int8 values u = popcount(code), 4 per word.
 // Word 4x+w, byte b holds source entry 16x + w + 4b  (=> kpos_of).
-__device__ __forceinline__ void decode64(const uint4& q, uint32_t (&o)[16]) {
+__device__ __forceinline__ void decode64(const uint4& q, uint32_t* o) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
@@ -70,9 +72,9 @@ __device__ __forceinline__ void decode64(const uint4& q, uint32_t (&o)[16]) {
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(p));
   return r;
 }
 
@@ -81,36 +83,67 @@ struct TcGemmArgs {
   uint64_t stride_rt, stride_kb;  // bytes
   const int8_t* Bimg;             // k-block images of this launch, image of kb0 first, 64*NP bytes each
   uint32_t rt0, nrt;              // row tiles of the launch: [rt0, rt0 + nrt)
-  uint32_t kb0, nkb;              // k-blocks of the launch: [kb0, kb0 + nkb)
-  uint32_t kb_per_split, nsplit;  // split-K decomposition
+  uint32_t kb0, nkb;              // k-blocks of the launch: [kb0, kb0 + nkb), nkb EVEN (zero image padding)
+  uint32_t kb_valid_last;         // last k-block that exists in PA (loads are clamped to it)
+  uint32_t kb_per_split, nsplit;  // split-K decomposition, kb_per_split EVEN
   uint32_t NP, l, lp;             // padded UMMA N (= round_up(S*l,16)), columns, leading dim of R
   long long row_begin, row_end;   // absolute rows that receive output
   long long row_r0;               // absolute row stored at R[0]
   long long* R;                   // [rows][lp] int64 accumulators (zero on entry, added to)
 };
 
+// Four UMMAs (K = 4 x 32) of one row tile for one stage: D[d_tmem] (+)= A[a_tmem .. +32 cols] * B.
+// `dk` = descriptor increment per K step (two 16-byte K chunks = 2*LBO bytes >> 4).
+__device__ __forceinline__ void umma_i8_ts_x4(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, uint64_t dk) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 d1, d2, d3;\n\t"
+      ".reg .b32 a1, a2, a3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 d1, %2, %5;\n\t"
+      "add.u64 d2, d1, %5;\n\t"
+      "add.u64 d3, d2, %5;\n\t"
+      "add.u32 a1, %1, 8;\n\t"
+      "add.u32 a2, %1, 16;\n\t"
+      "add.u32 a3, %1, 24;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [a1], d1, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [a2], d2, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [a3], d3, %3, pt;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "l"(dk)
+      : "memory");
+}
+
+// Pipeline (one CTA per SM, persistent over work items = (row-tile group, K split)):
+//   warp 0      B producer   : bulk-copies one stage (128 x NP int8) of the slice image into smem
+//   warp 1      UMMA issuer  : per stage 4 UMMAs per row tile, then ONE tcgen05.commit frees the stage
+//   warps 4..   decode warps : 4 per row tile (one per TMEM lane quadrant); each thread owns one
+//                              output row: 2 x 16-byte packed loads -> 128 int8 -> tcgen05.st
+//   full[s]  : 4*RT decode-warp arrivals + the B producer's expect_tx arrival + the copied bytes
+//   empty[s] : the issuer's tcgen05.commit
+// After the last stage of an item the decode warps drain the s32 accumulators (epilogue).
 template <int S, int RT>
 __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t b_full[kNBS], b_empty[kNBS], a_full[RT][kNAS], a_empty[RT][kNAS], acc_full, acc_empty;
+  __shared__ __align__(8) uint64_t full[kNS], empty[kNS], acc_full, acc_empty;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = kKB * a.NP;
+  const uint32_t kb_bytes = kKB * a.NP;
+  const uint32_t stage_bytes = kStageKB * kb_bytes;
   uint8_t* Bs = smem;
-  long long* scratch = reinterpret_cast<long long*>(smem + (size_t)kNBS * stage_bytes);
+  long long* scratch = reinterpret_cast<long long*>(smem + (size_t)kNS * stage_bytes);
 
   if (warp == 2) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNBS; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+    for (int i = 0; i < kNS; ++i) {
+      mbar_init(&full[i], 4 * RT + 1);
+      mbar_init(&empty[i], 1);
     }
-    for (int t = 0; t < RT; ++t)
-      for (int i = 0; i < kNAS; ++i) {
-        mbar_init(&a_full[t][i], 4);
-        mbar_init(&a_empty[t][i], 1);
-      }
     mbar_init(&acc_full, 1);
     mbar_init(&acc_empty, 4 * RT);
     mbar_fence_init();
@@ -124,19 +157,19 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
   const uint32_t n_items = n_rtp * a.nsplit;
 
   if (warp == 0) {
-    // ------------------------------------------------ B producer: bulk copies into the smem ring
+    // ------------------------------------------------ B producer
     if (lane == 0) {
-      uint32_t kit = 0;
+      uint32_t sit = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t sp = item / n_rtp;
         const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
         const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
-        for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++kit) {
-          const uint32_t bs = kit % kNBS, ph = (kit / kNBS) & 1;
-          mbar_wait(&b_empty[bs], ph ^ 1);
-          mbar_expect_tx(&b_full[bs], stage_bytes);
-          bulk_g2s(Bs + (size_t)bs * stage_bytes, a.Bimg + (size_t)(kb - a.kb0) * stage_bytes, stage_bytes,
-                   &b_full[bs]);
+        const int8_t* src = a.Bimg + (size_t)(kb_begin - a.kb0) * kb_bytes;
+        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB, ++sit, src += stage_bytes) {
+          const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], stage_bytes);
+          bulk_g2s(Bs + (size_t)s * stage_bytes, src, stage_bytes, &full[s]);
         }
       }
     }
@@ -145,9 +178,10 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
     if (lane == 0) {
       const uint32_t idesc = idesc_i8(kRowTile, (int)a.NP);
       const uint32_t lbo = (a.NP >> 3) * 128, sbo = 128;
-      uint32_t kit = 0, ait[RT], n = 0;
-#pragma unroll
-      for (int t = 0; t < RT; ++t) ait[t] = 0;
+      const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(Bs), lbo, sbo);
+      const uint64_t dk = (uint64_t)((2 * lbo) >> 4);         // one K step (32 entries)
+      const uint64_t dstage = (uint64_t)(stage_bytes >> 4);   // one stage
+      uint32_t sit = 0, n = 0;
       for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
         const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
         const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
@@ -155,27 +189,17 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
         const uint32_t ntile = min((uint32_t)RT, a.nrt - rtp * RT);
         mbar_wait(&acc_empty, (n & 1) ^ 1);
         tc_fence_after();
-        for (uint32_t kb = kb_begin; kb < kb_end; ++kb, ++kit) {
-          const uint32_t bs = kit % kNBS, bph = (kit / kNBS) & 1;
-          mbar_wait(&b_full[bs], bph);
-          const uint32_t bsaddr = smem_u32(Bs + (size_t)bs * stage_bytes);
-#pragma unroll
-          for (int t = 0; t < RT; ++t) {
-            if ((uint32_t)t < ntile) {
-              const uint32_t as = ait[t] % kNAS, aph = (ait[t] / kNAS) & 1;
-              mbar_wait(&a_full[t][as], aph);
-              tc_fence_after();
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t bd = smem_desc_kmajor_noswizzle(bsaddr + ks * 2 * lbo, lbo, sbo);
-                umma_i8_ts(tbase + t * a.NP, tbase + kAcol0 + (t * kNAS + as) * 16 + ks * 8, bd, idesc,
-                           (kb > kb_begin || ks > 0) ? 1u : 0u);
-              }
-              umma_commit(&a_empty[t][as]);
-              ++ait[t];
-            }
-          }
-          umma_commit(&b_empty[bs]);
+        uint32_t accflag = 0;
+        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB, ++sit) {
+          const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t bd = desc0 + s * dstage;
+          const uint32_t at = tbase + kAcol0 + s * (RT * 32);
+          umma_i8_ts_x4(tbase, at, bd, idesc, accflag, dk);
+          if (RT > 1 && ntile > 1) umma_i8_ts_x4(tbase + a.NP, at + 32, bd, idesc, accflag, dk);
+          umma_commit(&empty[s]);
+          accflag = 1;
         }
         umma_commit(&acc_full);
       }
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
     const uint32_t rloc = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long long* my_scratch = scratch + (size_t)(warp - 4) * 32 * 17;
-    uint32_t ait = 0, n = 0;
+    uint32_t sit = 0, n = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
       const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
@@ -196,28 +220,44 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
       const uint32_t rt = a.rt0 + rtp * RT + t;
       if (active) {
         const uint8_t* p = a.PA + (uint64_t)rt * a.stride_rt + (uint64_t)rloc * 16;
-        uint4 buf[kPF];
+        // register ring: kPF stages (2 packed loads each) in flight per thread. Loads are
+        // unconditional (clamped) so that every ring slot keeps its own registers.
+        uint4 buf[kPF][kStageKB];
 #pragma unroll
         for (int j = 0; j < kPF; ++j)
-          if (kb_begin + j < kb_end) buf[j] = ldg_stream16(p + (uint64_t)(kb_begin + j) * a.stride_kb);
-        for (uint32_t kb = kb_begin; kb < kb_end; kb += kPF) {
+#pragma unroll
+          for (int h = 0; h < kStageKB; ++h)
+            buf[j][h] = ldg_stream16(p + (uint64_t)min(kb_begin + kStageKB * j + h, a.kb_valid_last) * a.stride_kb);
+        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB * kPF) {
 #pragma unroll
           for (int j = 0; j < kPF; ++j) {
-            if (kb + j < kb_end) {
-              uint32_t o[16];
-              decode64(buf[j], o);
-              if (kb + j + kPF < kb_end) buf[j] = ldg_stream16(p + (uint64_t)(kb + j + kPF) * a.stride_kb);
-              const uint32_t as = ait % kNAS, aph = (ait / kNAS) & 1;
-              mbar_wait(&a_empty[t][as], aph ^ 1);
+            const uint32_t kbj = kb + kStageKB * j;
+            uint32_t o[32];
+            decode64(buf[j][0], o);
+            decode64(buf[j][1], o + 16);
+#pragma unroll
+            for (int h = 0; h < kStageKB; ++h)
+              buf[j][h] = ldg_stream16(p + (uint64_t)min(kbj + kStageKB * kPF + h, a.kb_valid_last) * a.stride_kb);
+            if (kbj < kb_end) {
+              const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+              mbar_wait(&empty[s], ph ^ 1);
               tc_fence_after();
-              tmem_st16(tbase + lane_addr + kAcol0 + (t * kNAS + as) * 16, o);
+              tmem_st32(tbase + lane_addr + kAcol0 + s * (RT * 32) + t * 32, o);
               tmem_wait_st();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&a_full[t][as]);
-              ++ait;
+              if (lane == 0) mbar_arrive(&full[s]);
+              ++sit;
             }
           }
+        }
+      } else {
+        // idle tile of a ragged last group: keep the stage barriers in step
+        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB, ++sit) {
+          const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
         }
       }
       // ---- epilogue: s32 slice sums -> one int64 per (row, column) -> integer atomics
