@@ -8,6 +8,7 @@
 //   FileBed::read_all / read_block_*       reference src/FilePlink.cpp:26-298
 // Nothing here falls back to the CPU: every arithmetic step is a kernel launch.
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,6 +23,7 @@
 #include "gemm_fp64.cuh"
 #include "small_dense.cuh"
 #include "tall_skinny.cuh"
+#include "orth_fused.cuh"
 #include "tc_gemm.cuh"
 
 using namespace pcaone;
@@ -107,6 +109,8 @@ struct pcaone_ctx {
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
   std::vector<uint64_t> nmiss_prefix;
   uint64_t tc_ranges = 0, fp64_ranges = 0;
+  double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
+  int fused_orth = 1;                                  // PCAONE_FUSED_ORTH=0 selects the multi-kernel path
 
   pcaone_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
@@ -672,8 +676,74 @@ void gram_factor(pcaone_ctx* c, const double* W, double* Tout) {
   }
 }
 
+template <int R>
+void orth_fused_r(pcaone_ctx* c, OrthArgs& a) {
+  const size_t smem = orth_smem_bytes(c->l, R);
+  static size_t attr = 0;
+  if (smem > attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_orth_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  void* args[] = {(void*)&a};
+  PCA_CUDA(cudaLaunchCooperativeKernel((void*)k_orth_fused<R>, dim3(c->sms), dim3(kOrthThreads), args, smem, c->stream));
+  c->tm.kernel_launches++;
+}
+
+bool orth_fused_ok(const pcaone_ctx* c) { return c->fused_orth && c->l <= kOrthMaxL; }
+
+// One cooperative launch: Q = orth(A) (CholeskyQR2) [+ Householder signs] [+ flipOmg against Q2].
+void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Q2, double* Ttot, bool signs,
+                bool flip) {
+  OrthArgs a{};
+  a.A = A;
+  a.Q = Q;
+  a.Q2 = Q2;
+  a.rows = rows;
+  a.l = c->l;
+  a.lp = c->lp;
+  a.want_signs = signs ? 1 : 0;
+  a.want_flip = flip ? 1 : 0;
+  a.part = c->d_part;
+  a.Wg = c->d_W;
+  a.T1g = c->d_T1;
+  a.T2g = c->d_T2;
+  a.Ttot = Ttot;
+  a.hsign = c->d_hsign;
+  a.fsign = c->d_sign;
+  a.jscratch = c->d_jscratch;
+  a.status = c->d_status + 1;
+  static unsigned long long* d_prof = nullptr;
+  static int prof_left = getenv("PCAONE_ORTH_PROF") ? atoi(getenv("PCAONE_ORTH_PROF")) : 0;
+  if (prof_left > 0) {
+    if (!d_prof) PCA_CUDA(cudaMalloc((void**)&d_prof, 64 * sizeof(unsigned long long)));
+    a.prof = d_prof;
+  }
+  if ((size_t)c->sms * c->l * c->lp > c->part_doubles) throw std::runtime_error("partial workspace too small");
+  switch ((c->l + 15) / 16) {
+    case 1: orth_fused_r<1>(c, a); break;
+    case 2: orth_fused_r<2>(c, a); break;
+    case 3: orth_fused_r<3>(c, a); break;
+    case 4: orth_fused_r<4>(c, a); break;
+    case 5: orth_fused_r<5>(c, a); break;
+    default: throw std::runtime_error("orth_fused: l too large");
+  }
+  if (prof_left > 0) {
+    --prof_left;
+    unsigned long long h[32];
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    PCA_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "orth_fused rows=%llu phases(us):", (unsigned long long)rows);
+    for (int i = 1; i < 18; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[i - 1]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+}
+
 // Q = orth(A) in two passes (CholeskyQR2); Q may alias A. Ttot (optional) = T1*T2, Q = A*Ttot.
 void orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Ttot, bool sharded_rows) {
+  if (orth_fused_ok(c) && !(sharded_rows && c->cfg.world > 1)) {
+    orth_fused(c, A, rows, Q, nullptr, Ttot, false, false);
+    return;
+  }
   ts_gemm_tn(c, A, c->l, A, c->l, rows, c->d_W, sharded_rows);
   gram_factor(c, c->d_W, c->d_T1);
   ts_rightmult(c, A, c->l, c->d_T1, c->l, rows, Q);
@@ -708,6 +778,12 @@ void allreduce_H(pcaone_ctx* c, double* H) {
 // Omega = thinQ(H) (+ flipOmg)   Halko.cpp:120-124 / 208-213
 void update_omega(pcaone_ctx* c, const double* H, bool flip) {
   Timed t(c, 2);
+  if (orth_fused_ok(c)) {
+    orth_fused(c, H, c->N, c->d_Omg, flip ? c->d_Omg2 : nullptr, nullptr, true, flip);
+    c->tm.omega_updates++;
+    c->omega_img_valid = false;
+    return;
+  }
   orth2(c, H, c->N, c->d_Omg, nullptr, false);
   // give the CholeskyQR basis the column signs of the reference's Householder thin Q
   const size_t smem = (size_t)c->l * c->l * sizeof(double);
@@ -1187,6 +1263,9 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     dmalloc(&c->d_hsign, c->lp);
     dmalloc(&c->d_scal, 64);
     dmalloc(&c->d_status, 4);
+    PCA_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
+    dmalloc(&c->d_jscratch, (size_t)2 * c->l * c->l + 2 * c->l + 8);
+    if (const char* e = getenv("PCAONE_FUSED_ORTH")) c->fused_orth = atoi(e);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
     c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;
@@ -1214,7 +1293,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
-                  (void*)c->d_Racc, (void*)c->d_tcs, (void*)c->d_Fpart})
+                  (void*)c->d_Racc, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);

@@ -1,0 +1,559 @@
+// pcaone_b200 — the whole tall-skinny orthonormalisation in ONE cooperative kernel.
+//
+//   Omega = thinQ(H); flipOmg                (reference Halko.cpp:120-124, 208-213; RSVD.hpp:80-89)
+//   G = Q R twice, R = R2 R1                 (reference Halko.cpp:55-65)
+//
+// CholeskyQR2 with the Householder sign convention of the reference's thin Q (see
+// k_householder_signs) and flipOmg, as phases of a persistent grid separated by grid.sync():
+//   P1  partial Gram A^T A per CTA                        P2  distributed reduction -> W
+//   P3  CTA 0: T1 = chol(W)^-1 (SVQB eigen route if W is numerically rank deficient)
+//   P4  partial Gram of Q1 = A T1 (rows recomputed, never stored)     P5  reduction
+//   P6  CTA 0: T2, Ttot = T1 T2, Householder signs from the top l x l block of Q
+//   P7  Q = (A T1) T2 o signs written out; partial flipOmg column sums
+//   P8  flip decision, Omega *= flip sign, Omega2 = Omega
+// winSVD calls this up to 63 times per epoch on an N x l matrix that is a few MB: the multi-kernel
+// version (2 Gram + 2 reduce + 2 Cholesky + 2 host status reads + 2 right-multiplies + signs + 3
+// flip kernels) is launch/latency bound at ~0.3 ms per update; this kernel is one launch and no
+// host round trip. Every reduction has a fixed summation order (deterministic).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "small_dense.cuh"
+
+namespace pcaone {
+namespace cg = cooperative_groups;
+
+constexpr int kOrthThreads = 256;
+constexpr int kOrthMaxL = 80;  // two l x 16R factor matrices must fit shared memory
+__host__ __device__ constexpr int orth_tile_rows(int R) { return R <= 4 ? 64 : 32; }  // rows per staged tile
+
+struct OrthArgs {
+  const double* A;   // [rows][lp] input (H or G); may alias Q
+  double* Q;         // [rows][lp] output
+  double* Q2;        // Omega2 for flipOmg (read, then overwritten with the new Omega) or nullptr
+  uint64_t rows;
+  int l, lp;
+  int want_signs;    // Householder column signs (Omega updates)
+  int want_flip;     // flipOmg (needs Q2)
+  double* part;      // [gridDim.x][l*lp] partial Gram / flip sums
+  double* Wg;        // [l*lp] reduced Gram
+  double* T1g;       // [l*lp]
+  double* T2g;       // [l*lp]
+  double* Ttot;      // [l*lp] out: T1 T2 (Q = A Ttot), or nullptr
+  double* hsign;     // [l] out: Householder signs (1.0 when !want_signs)
+  double* fsign;     // [l] out: total applied column sign
+  double* jscratch;  // [2*l*l + 2*l] global scratch of the eigen fallback
+  int* status;       // out: number of factorizations that took the eigen (rank-deficient) route
+  unsigned long long* prof;  // optional: globaltimer (ns) at the phase boundaries, CTA 0 (debug aid)
+};
+
+__host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
+  const int LC = 16 * R;
+  return ((size_t)2 * l * LC + (size_t)2 * orth_tile_rows(R) * (LC + 1) + (size_t)l * l) * sizeof(double);
+}
+
+// W (l x l, row-major ld, global) -> T (l x l row-major ld, global) with (A T) orthonormal:
+// T = R^-1 from the Cholesky factor, or V diag(lam^-1/2) when the pivot test fails.
+// Executed by ONE CTA; `Ws` is l*l doubles of shared memory.
+// The result is left in shared memory Ts ([l][lc], zero padded) AND written to global T.
+__device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, double* __restrict__ T,
+                                   double* __restrict__ Ws, double* __restrict__ Ts, int lc,
+                                   double* __restrict__ jscratch, int* status) {
+  __shared__ double s_piv, s_maxd;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < l * l; i += nt) Ws[i] = W[(i / l) * ld + (i % l)];
+  if (tid == 0) {
+    s_fail = 0;
+    double m = 0.0;
+    for (int i = 0; i < l; ++i) m = fmax(m, W[i * ld + i]);
+    s_maxd = m;
+  }
+  __syncthreads();
+  const double tol = 64.0 * l * 2.220446049250313e-16 * s_maxd;
+  for (int j = 0; j < l; ++j) {
+    if (tid == 0) {
+      const double d = Ws[j * l + j];
+      if (!(d > tol)) s_fail = 1;
+      s_piv = sqrt(d > tol ? d : 1.0);
+      Ws[j * l + j] = s_piv;
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const double inv = 1.0 / s_piv;
+    for (int c = j + 1 + tid; c < l; c += nt) Ws[j * l + c] *= inv;
+    __syncthreads();
+    const int m = l - j - 1;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c >= r) Ws[r * l + c] -= Ws[j * l + r] * Ws[j * l + c];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
+  __syncthreads();
+  if (!s_fail) {
+    // T = R^-1 (upper triangular), one column per thread, all in shared memory
+    for (int c = tid; c < l; c += nt) {
+      Ts[c * lc + c] = 1.0 / Ws[c * l + c];
+      for (int r = c - 1; r >= 0; --r) {
+        double s = 0.0;
+        for (int p = r + 1; p <= c; ++p) s += Ws[r * l + p] * Ts[p * lc + c];
+        Ts[r * lc + c] = -s / Ws[r * l + r];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < l * ld; i += nt) {
+      const int r = i / ld, c = i - r * ld;
+      T[i] = c < l ? Ts[r * lc + c] : 0.0;
+    }
+    __syncthreads();
+    return;
+  }
+  // ---- eigen route (SVQB): one-sided Jacobi on W in global scratch (rare, slow path)
+  double* Aj = jscratch;            // column-major l x l
+  double* Vj = Aj + (size_t)l * l;  // column-major l x l
+  double* nrm = Vj + (size_t)l * l; // l
+  __shared__ int s_rot;
+  __shared__ int s_ord[kMaxL];
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int i = tid; i < l * l; i += nt) {
+    const int r = i / l, c = i % l;
+    Aj[c * l + r] = W[r * ld + c];
+    Vj[c * l + r] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int n = (l + 1) & ~1;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < n - 1; ++round) {
+      for (int pi = warp; pi < n / 2; pi += nw) {
+        int p, q;
+        if (pi == 0) {
+          p = n - 1;
+          q = round;
+        } else {
+          p = (round + pi) % (n - 1);
+          q = (round - pi + (n - 1)) % (n - 1);
+        }
+        if (p > q) {
+          const int tmp = p;
+          p = q;
+          q = tmp;
+        }
+        if (q >= l) continue;
+        double* ap = Aj + p * l;
+        double* aq = Aj + q * l;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int r = lane; r < l; r += 32) {
+          const double x = ap[r], y = aq[r];
+          alpha += x * x;
+          beta += y * y;
+          gamma += x * y;
+        }
+        alpha = warp_sum(alpha);
+        beta = warp_sum(beta);
+        gamma = warp_sum(gamma);
+        if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && gamma != 0.0) {
+          if (lane == 0) s_rot = 1;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cc = 1.0 / sqrt(1.0 + tt * tt), ss = cc * tt;
+          double* vp = Vj + p * l;
+          double* vq = Vj + q * l;
+          for (int r = lane; r < l; r += 32) {
+            const double x = ap[r], y = aq[r];
+            ap[r] = cc * x - ss * y;
+            aq[r] = ss * x + cc * y;
+            const double vx = vp[r], vy = vq[r];
+            vp[r] = cc * vx - ss * vy;
+            vq[r] = ss * vx + cc * vy;
+          }
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (!rot) break;
+  }
+  for (int j = warp; j < l; j += nw) {
+    double s = 0.0;
+    for (int r = lane; r < l; r += 32) s += Aj[j * l + r] * Aj[j * l + r];
+    s = warp_sum(s);
+    if (lane == 0) nrm[j] = sqrt(s);  // eigenvalue lam_j of W
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int j = 0; j < l; ++j) s_ord[j] = j;
+    for (int a = 1; a < l; ++a) {
+      const int key = s_ord[a];
+      int b = a - 1;
+      while (b >= 0 && nrm[s_ord[b]] < nrm[key]) {
+        s_ord[b + 1] = s_ord[b];
+        --b;
+      }
+      s_ord[b + 1] = key;
+    }
+    atomicAdd(status, 1);
+  }
+  __syncthreads();
+  const double smax = sqrt(nrm[s_ord[0]]);
+  for (int i = tid; i < l * l; i += nt) {
+    const int r = i / l, c = i % l;
+    const double s = sqrt(nrm[s_ord[c]]);
+    Ts[r * lc + c] = (s > 1e-7 * smax && s > 0.0) ? Vj[s_ord[c] * l + r] / s : 0.0;
+  }
+  __syncthreads();
+  for (int i = tid; i < l * ld; i += nt) {
+    const int r = i / ld, c = i - r * ld;
+    T[i] = c < l ? Ts[r * lc + c] : 0.0;
+  }
+  __syncthreads();
+}
+
+// out[e] = sum_p part[p*stride + e], one warp per element, lanes stride over parts, fixed order
+__device__ __forceinline__ void orth_reduce_parts(const double* __restrict__ part, int nparts, size_t stride,
+                                                  int nelem, double* __restrict__ out, int gwarp, int nwarps, int lane) {
+  for (int e = gwarp; e < nelem; e += nwarps) {
+    double v = 0.0;
+    for (int p = lane; p < nparts; p += 32) v += part[(size_t)p * stride + e];
+    v = warp_sum(v);
+    if (lane == 0) out[e] = v;
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  constexpr int LC = 16 * R;
+  constexpr int TR = orth_tile_rows(R);  // rows per tile
+  constexpr int RI = TR / 16;            // rows per thread
+  constexpr int NLD = TR * R / 16;       // register-prefetched doubles per thread (>= TR*lp/256)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* T1s = reinterpret_cast<double*>(smem_raw);  // [l][LC]
+  double* T2s = T1s + (size_t)a.l * LC;               // [l][LC]
+  double* As = T2s + (size_t)a.l * LC;                // [TR][LC+1]
+  double* Qs = As + TR * (LC + 1);                    // [TR][LC+1]
+  double* Ws = Qs + TR * (LC + 1);                    // [l][l]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+  const int l = a.l, lp = a.lp;
+  const int gwarp = (blockIdx.x * kOrthThreads + tid) >> 5, nwarps = (gridDim.x * kOrthThreads) >> 5;
+  const uint64_t rpc = ((a.rows + gridDim.x - 1) / gridDim.x + TR - 1) / TR * TR;
+  const uint64_t r0 = min(a.rows, (uint64_t)blockIdx.x * rpc), r1 = min(a.rows, r0 + rpc);
+  const size_t pstride = (size_t)l * lp;
+  double* mypart = a.part + (size_t)blockIdx.x * pstride;
+  const int tile_elems = TR * lp;  // a tile is TR contiguous rows of lp doubles
+
+  // register prefetch of the tile starting at row r (flat, coalesced), zero beyond r1
+  double pre[NLD];
+  auto prefetch = [&](uint64_t r) {
+    const double* src = a.A + r * lp;
+    const uint64_t lim = r < r1 ? (r1 - r) * (uint64_t)lp : 0;
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int e = tid + kOrthThreads * i;
+      pre[i] = (e < tile_elems && (uint64_t)e < lim) ? src[e] : 0.0;
+    }
+  };
+  auto commit_tile = [&]() {  // registers -> As[rr][c]
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int e = tid + kOrthThreads * i;
+      if (e < tile_elems) {
+        const int rr = e / lp, c = e - rr * lp;
+        if (c < LC) As[rr * (LC + 1) + c] = c < l ? pre[i] : 0.0;
+      }
+    }
+  };
+  auto zero_pad_cols = [&]() {  // columns lp..LC-1 of As are never written by commit_tile
+    if (lp < LC)
+      for (int idx = tid; idx < TR * (LC - lp); idx += kOrthThreads) {
+        const int rr = idx / (LC - lp), c = lp + idx - rr * (LC - lp);
+        As[rr * (LC + 1) + c] = 0.0;
+      }
+  };
+  auto load_T = [&](const double* Tg, double* Ts) {
+    for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
+      const int r = idx / LC, c = idx - r * LC;
+      Ts[idx] = c < l ? Tg[r * lp + c] : 0.0;
+    }
+  };
+  // acc[i][j] = sum_k src[ty+16i][k] * Ts[k][tx+16j]
+  auto tile_times_T = [&](const double* src, const double* Ts, double (&acc)[RI][R]) {
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < l; ++k) {
+      double av[RI], tv[R];
+#pragma unroll
+      for (int i = 0; i < RI; ++i) av[i] = src[(ty + 16 * i) * (LC + 1) + k];
+#pragma unroll
+      for (int j = 0; j < R; ++j) tv[j] = Ts[k * LC + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] += av[i] * tv[j];
+    }
+  };
+  auto store_tile = [&](double* dst, const double (&acc)[RI][R]) {
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) dst[(ty + 16 * i) * (LC + 1) + tx + 16 * j] = acc[i][j];
+  };
+  auto gram_accumulate = [&](const double* src, double (&acc)[R][R]) {
+#pragma unroll 4
+    for (int rr = 0; rr < TR; ++rr) {
+      double av[R], bv[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) av[i] = src[rr * (LC + 1) + ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < R; ++j) bv[j] = src[rr * (LC + 1) + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] += av[i] * bv[j];
+    }
+  };
+  auto store_part = [&](double (&acc)[R][R]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (r < l && c < lp) mypart[r * lp + c] = c < l ? acc[i][j] : 0.0;
+      }
+  };
+
+  int prof_i = 0;
+  auto stamp = [&]() {
+    if (a.prof && blockIdx.x == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      a.prof[prof_i] = t;
+    }
+    ++prof_i;
+  };
+  stamp();
+  zero_pad_cols();
+  // ---------------- P1: partial Gram of A
+  {
+    double acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    prefetch(r0);
+    for (uint64_t r = r0; r < r1; r += TR) {
+      __syncthreads();
+      commit_tile();
+      prefetch(r + TR);
+      __syncthreads();
+      gram_accumulate(As, acc);
+    }
+    store_part(acc);
+  }
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P2: W = sum of partials
+  orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P3: T1
+  if (blockIdx.x == 0) orth_factor(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
+  __threadfence();
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P4: partial Gram of Q1 = A T1
+  if (blockIdx.x != 0) load_T(a.T1g, T1s);
+  {
+    double acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    prefetch(r0);
+    for (uint64_t r = r0; r < r1; r += TR) {
+      __syncthreads();
+      commit_tile();
+      prefetch(r + TR);
+      __syncthreads();
+      double q1[RI][R];
+      tile_times_T(As, T1s, q1);
+      store_tile(Qs, q1);
+      __syncthreads();
+      gram_accumulate(Qs, acc);
+    }
+    store_part(acc);
+  }
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P5
+  orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+  grid.sync();
+  stamp();
+  // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
+  if (blockIdx.x == 0) {
+    orth_factor(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
+    if (a.Ttot) {
+      for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
+        const int r = idx / lp, c = idx - r * lp;
+        double s = 0.0;
+        if (c < l)
+          for (int k = 0; k < l; ++k) s += T1s[r * LC + k] * T2s[k * LC + c];
+        a.Ttot[idx] = s;
+      }
+    }
+    if (a.want_signs) {
+      // top l x l block of Q = (A T1) T2 -> Ws (row-major l x l)
+      const uint64_t r1_save = r1;
+      for (int rb = 0; rb < l; rb += TR) {
+        __syncthreads();
+        for (int idx = tid; idx < TR * LC; idx += kOrthThreads) {
+          const int rr = idx / LC, c = idx - rr * LC;
+          As[rr * (LC + 1) + c] =
+              ((uint64_t)(rb + rr) < a.rows && rb + rr < l && c < l) ? a.A[(uint64_t)(rb + rr) * lp + c] : 0.0;
+        }
+        __syncthreads();
+        double q[RI][R];
+        tile_times_T(As, T1s, q);
+        store_tile(Qs, q);
+        __syncthreads();
+        tile_times_T(Qs, T2s, q);
+#pragma unroll
+        for (int i = 0; i < RI; ++i)
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int rr = rb + ty + 16 * i, c = tx + 16 * j;
+            if (rr < l && c < l) Ws[rr * l + c] = q[i][j];
+          }
+      }
+      (void)r1_save;
+      __syncthreads();
+      // sign-modified LU replay of the Householder sign decisions (see k_householder_signs)
+      __shared__ double s_piv2;
+      for (int i = 0; i < l; ++i) {
+        if (tid == 0) {
+          const double c0 = Ws[i * l + i];
+          const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
+          a.hsign[i] = beta;
+          s_piv2 = c0 - beta;
+        }
+        __syncthreads();
+        const double inv = 1.0 / s_piv2;
+        const int m = l - i - 1;
+        for (int idx = tid; idx < m * m; idx += kOrthThreads) {
+          const int r = i + 1 + idx / m, c = i + 1 + idx % m;
+          Ws[r * l + c] -= Ws[r * l + i] * Ws[i * l + c] * inv;
+        }
+        __syncthreads();
+      }
+    } else {
+      for (int c = tid; c < l; c += kOrthThreads) a.hsign[c] = 1.0;
+    }
+  }
+  __threadfence();
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P7: Q = (A T1) T2 o hsign ; partial flip sums
+  if (blockIdx.x != 0) load_T(a.T2g, T2s);
+  double hs[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? a.hsign[tx + 16 * j] : 0.0;
+  double dsum[R], ssum[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = 0.0;
+  zero_pad_cols();
+  prefetch(r0);
+  for (uint64_t r = r0; r < r1; r += TR) {
+    __syncthreads();
+    commit_tile();
+    prefetch(r + TR);
+    __syncthreads();
+    double q[RI][R];
+    tile_times_T(As, T1s, q);
+    store_tile(Qs, q);
+    __syncthreads();
+    tile_times_T(Qs, T2s, q);
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      const uint64_t row = r + ty + 16 * i;
+      if (row < r1) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int c = tx + 16 * j;
+          if (c < lp) {
+            const double qv = c < l ? q[i][j] * hs[j] : 0.0;
+            if (a.want_flip && c < l) {
+              const double o2 = a.Q2[row * lp + c];
+              dsum[j] += fabs(o2 - qv);
+              ssum[j] += fabs(o2 + qv);
+            }
+            a.Q[row * lp + c] = qv;
+          }
+        }
+      }
+    }
+  }
+  if (!a.want_flip) {
+    if (blockIdx.x == 0)
+      for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
+    return;  // uniform across the grid: no further grid.sync
+  }
+  __syncthreads();
+  // reduce the 16 row-lanes (ty) per column in fixed order: reuse As/Qs as [16][LC+1]
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    As[ty * (LC + 1) + tx + 16 * j] = dsum[j];
+    Qs[ty * (LC + 1) + tx + 16 * j] = ssum[j];
+  }
+  __syncthreads();
+  for (int c = tid; c < l; c += kOrthThreads) {
+    double d = 0.0, s = 0.0;
+    for (int y = 0; y < 16; ++y) {
+      d += As[y * (LC + 1) + c];
+      s += Qs[y * (LC + 1) + c];
+    }
+    mypart[c] = d;
+    mypart[l + c] = s;
+  }
+  stamp();
+  grid.sync();
+  stamp();
+  // ---------------- P8: flip decision (every CTA, same fixed order), apply to own rows
+  __syncthreads();
+  for (int c = tid; c < 2 * l; c += kOrthThreads) {
+    double v = 0.0;
+    for (unsigned p = 0; p < gridDim.x; ++p) v += a.part[(size_t)p * pstride + c];
+    Qs[c] = v;
+  }
+  __syncthreads();
+  for (int c = tid; c < l; c += kOrthThreads) {
+    const double f = (Qs[c] > 2 * Qs[l + c]) ? -1.0 : 1.0;
+    As[c] = f;
+    if (blockIdx.x == 0) a.fsign[c] = f * a.hsign[c];
+  }
+  __syncthreads();
+  const uint64_t total = (r1 - r0) * (uint64_t)lp;
+  for (uint64_t i = tid; i < total; i += kOrthThreads) {
+    const int c = (int)(i % lp);
+    double v = a.Q[r0 * lp + i];
+    if (c < l) v *= As[c];
+    a.Q[r0 * lp + i] = v;
+    a.Q2[r0 * lp + i] = v;
+  }
+  stamp();
+}
+
+}  // namespace pcaone
