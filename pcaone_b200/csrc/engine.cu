@@ -103,7 +103,7 @@ struct pcaone_ctx {
   size_t bimgW_kb = 0;
   long long* d_Racc = nullptr;                         // int64 accumulators
   size_t R_rows = 0;
-  unsigned long long* d_tcs = nullptr;                 // [4][lp]: Omega colmax, Omega Csum, W colmax, W Csum
+  unsigned long long* d_tcs = nullptr;                 // [5][lp]: Omega colmax, Omega Csum, W colmax, W Csum, Fw
   double* d_Fpart = nullptr;
   bool omega_img_valid = false;
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
@@ -319,8 +319,8 @@ void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG,
 
 void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
   if (!c->d_tcs) {
-    dmalloc(&c->d_tcs, (size_t)4 * c->lp);
-    PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)4 * c->lp * sizeof(unsigned long long), c->stream));
+    dmalloc(&c->d_tcs, (size_t)5 * c->lp);
+    PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)5 * c->lp * sizeof(unsigned long long), c->stream));
     dmalloc(&c->d_BimgO, (size_t)(tc_nkb_samples(c) + 1) * tc::kKB * c->NP);
   }
   const size_t need_rows = std::max<uint64_t>(tc_nrt_samples(c) * tc::kRowTile, max_range_rows + 2 * tc::kRowTile);
@@ -454,7 +454,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     Timed t(c, 0);
     if (!c->omega_img_valid) {
       PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
-      tc::k_tc_colmax<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, 0, c->N, o_colmax);
+      tc::k_tc_colmax<<<grid_for(c->N * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, 0, c->N, o_colmax);
       PCA_CHECK_LAUNCH();
       c->tm.kernel_launches++;
       tc_slice(c, c->d_Omg, 0, c->N, o_colmax, nullptr, 0, c->d_BimgO, o_csum, nullptr, nullptr);
@@ -479,7 +479,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       tc_launch(c, a);
     }
     long long* Rrow = c->d_Racc + (loc0 - (uint64_t)a.row_r0) * c->lp;
-    tc::k_tc_finish_g<<<grid_for((uint64_t)nrows * c->lp, 256, c->sms), 256, 0, c->stream>>>(
+    tc::k_tc_finish_g<<<(unsigned)std::min<uint64_t>((nrows + tc::kKB - 1) / tc::kKB, (uint64_t)c->sms * 8), 256, 0, c->stream>>>(
         Rrow, nrows, c->l, c->lp, c->slices, c->d_F + snp0, c->lut, o_csum, o_colmax, c->d_G + snp0 * c->lp, w_colmax);
     PCA_CHECK_LAUNCH();
     c->tm.gemm_g_launches++;
@@ -509,9 +509,13 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       Timed tk(c, 8);
       tc_launch(c, a);
     }
-    tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
-        c->d_Racc, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, c->d_Fpart, nkb_w, Hacc, accumulate ? 1 : 0);
+    double* Fw = reinterpret_cast<double*>(c->d_tcs + 4 * c->lp);
+    tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
     PCA_CHECK_LAUNCH();
+    tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
+        c->d_Racc, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw, Hacc, accumulate ? 1 : 0);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
     c->tm.gemm_h_launches++;
     c->tm.kernel_launches++;
   }

@@ -374,18 +374,28 @@ __global__ void __launch_bounds__(128) k_tile_transpose(const uint8_t* __restric
       make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// column abs-max of X[r0..r1)[0..l) (times an optional per-row factor) -> colmax bits (atomicMax on
-// the IEEE pattern, order-preserving for non-negative doubles)
-__global__ void k_tc_colmax(const double* __restrict__ X, int lp, int l, uint64_t r0, uint64_t r1,
-                            unsigned long long* __restrict__ colmax) {
+// column abs-max of X[r0..r1)[0..l) -> colmax bits (atomicMax on the IEEE pattern, which is
+// order-preserving for non-negative doubles). One warp per row, lanes across columns.
+__global__ void __launch_bounds__(256) k_tc_colmax(const double* __restrict__ X, int lp, int l, uint64_t r0, uint64_t r1,
+                                                    unsigned long long* __restrict__ colmax) {
   __shared__ unsigned long long smax[kMaxNP];
   for (int c = threadIdx.x; c < l; c += blockDim.x) smax[c] = 0ull;
   __syncthreads();
-  const uint64_t total = (r1 - r0) * (uint64_t)lp;
-  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (uint64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % lp);
-    if (c < l) atomicMax(&smax[c], (unsigned long long)__double_as_longlong(fabs(X[r0 * lp + idx])));
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t gw = (uint64_t)blockIdx.x * 8 + wib, nw = (uint64_t)gridDim.x * 8;
+  double m[4] = {0.0, 0.0, 0.0, 0.0};
+  for (uint64_t r = r0 + gw; r < r1; r += nw) {
+    const double* row = X + r * lp;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      if (c < l) m[q] = fmax(m[q], fabs(row[c]));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = lane + 32 * q;
+    if (c < l && m[q] > 0.0) atomicMax(&smax[c], (unsigned long long)__double_as_longlong(m[q]));
   }
   __syncthreads();
   for (int c = threadIdx.x; c < l; c += blockDim.x)
@@ -413,112 +423,188 @@ struct TcSliceArgs {
   double* Fpart;                      // out: [gridDim.x][lp] partial sums of f_row * X~[row][c], or nullptr
 };
 
-// One block per k-block. In: X rows are W = s o G (H pass; F != nullptr, the kernel multiplies by
-// s_row itself) or Omega (G pass).
+// One block per k-block (64 rows x l columns). X rows are G (H pass: F != nullptr, the kernel
+// forms W = s_row * G itself) or Omega (G pass). The 64 rows are one contiguous run of 64*lp
+// doubles: loads and the write-back are flat and coalesced.
 __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   int8_t* img = reinterpret_cast<int8_t*>(sm);                                   // 64*NP
-  double* fw = reinterpret_cast<double*>(sm + (size_t)kKB * a.NP);               // [64][l] (only if Fpart)
-  long long* ci = reinterpret_cast<long long*>(sm + (size_t)kKB * a.NP + (a.Fpart ? (size_t)kKB * a.l * 8 : 0));  // [64][l]
+  long long* ci = reinterpret_cast<long long*>(sm + (size_t)kKB * a.NP);         // [64][l]
+  double* fw = reinterpret_cast<double*>(ci + (size_t)kKB * a.l);                // [64][l] (only if Fpart)
+  __shared__ double s_scale[kKB], s_f[kKB], s_up[kMaxNP], s_dn[kMaxNP];
   const uint32_t kb = a.kb0 + blockIdx.x;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kKB * a.NP / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  const int g = tid & 63, cg = tid >> 6;
-  const uint64_t row = (uint64_t)kb * kKB + g;
-  const bool live = row >= a.r0 && row < a.r1;
-  const int kp = kpos_of(g);
   const int p = 8 * a.S - 1;
-  double s_row = 1.0, f_row = 0.0;
-  if (live && a.F) {
-    f_row = a.F[row];
-    s_row = snp_scale(f_row, a.lut);
-  }
-  for (int c = cg; c < a.l; c += 4) {
-    long long I = 0;
-    double xt = 0.0;
-    if (live) {
-      const int e = tc_exponent(a.colmax[c]);
-      const double x = a.X[row * a.lp + c] * s_row;
-      I = llrint(scalbn(x, p - e));
-      xt = scalbn((double)I, e - p);
-      if (a.writeback) a.X[row * a.lp + c] = xt / s_row;
-      long long rem = I;
-#pragma unroll 1
-      for (int s = a.S - 1; s >= 0; --s) {
-        long long d;
-        if (s > 0) {
-          d = ((rem + 128) & 255) - 128;
-          rem = (rem - d) >> 8;
-        } else {
-          d = rem;
-        }
-        img[bimg_offset(c * a.S + s, kp, a.NP)] = (int8_t)d;
-      }
+  const uint64_t row0 = (uint64_t)kb * kKB;
+  for (int i = tid; i < kKB * a.NP / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < kKB) {
+    const uint64_t row = row0 + tid;
+    double s = 1.0, f = 0.0;
+    if (row >= a.r0 && row < a.r1 && a.F) {
+      f = a.F[row];
+      s = snp_scale(f, a.lut);
     }
-    ci[g * a.l + c] = I;
-    if (a.Fpart) fw[g * a.l + c] = f_row * xt;
+    s_scale[tid] = s;
+    s_f[tid] = f;
+  }
+  for (int c = tid; c < a.l; c += 256) {
+    const int e = tc_exponent(a.colmax[c]);
+    s_up[c] = scalbn(1.0, p - e);
+    s_dn[c] = scalbn(1.0, e - p);
+  }
+  __syncthreads();
+  const int total = kKB * a.lp;
+  double* Xb = a.X + row0 * a.lp;
+  // column / row of flat element e = tid + 256 i, advanced incrementally (no divisions in the loop)
+  int g = tid / a.lp, c = tid - g * a.lp;
+  const int dg = 256 / a.lp, dc = 256 - dg * a.lp;
+  for (int e = tid; e < total; e += 256) {
+    const uint64_t row = row0 + g;
+    if (c < a.l) {
+      long long I = 0;
+      double xt = 0.0;
+      if (row >= a.r0 && row < a.r1) {
+        const double x = Xb[e] * s_scale[g];
+        I = llrint(x * s_up[c]);
+        xt = (double)I * s_dn[c];
+        if (a.writeback) Xb[e] = xt / s_scale[g];
+        if (I != 0) {
+          const int kp = kpos_of(g);
+          long long rem = I;
+          for (int s = a.S - 1; s > 0; --s) {
+            const long long d = ((rem + 128) & 255) - 128;
+            rem = (rem - d) >> 8;
+            img[bimg_offset(c * a.S + s, kp, a.NP)] = (int8_t)d;
+          }
+          img[bimg_offset(c * a.S, kp, a.NP)] = (int8_t)rem;
+        }
+      }
+      ci[g * a.l + c] = I;
+      if (a.Fpart) fw[g * a.l + c] = s_f[g] * xt;
+    }
+    g += dg;
+    c += dc;
+    if (c >= a.lp) {
+      c -= a.lp;
+      ++g;
+    }
   }
   __syncthreads();
   for (int i = tid; i < kKB * a.NP / 16; i += 256)
     reinterpret_cast<uint4*>(a.Bimg + (size_t)blockIdx.x * kKB * a.NP)[i] = reinterpret_cast<const uint4*>(img)[i];
-  for (int c = tid; c < a.l; c += 256) {
-    long long sc = 0;
-    double sf = 0.0;
-    for (int r = 0; r < kKB; ++r) {
-      sc += ci[r * a.l + c];
-      if (a.Fpart) sf += fw[r * a.l + c];
+  // column sums in a fixed order: 4 quarter sums of 16 rows per column, then combined
+  {
+    const int q = tid >> 6, cc = tid & 63;  // quarter, column lane
+    for (int c0 = 0; c0 < a.l; c0 += 64) {
+      const int col = c0 + cc;
+      long long sc = 0;
+      double sf = 0.0;
+      if (col < a.l) {
+        for (int r = 16 * q; r < 16 * q + 16; ++r) {
+          sc += ci[r * a.l + col];
+          if (a.Fpart) sf += fw[r * a.l + col];
+        }
+      }
+      __syncthreads();
+      // reuse s_up/s_dn as [4][64] staging (the per-column scales are no longer needed)
+      double* stage_f = s_up;
+      long long* stage_c = reinterpret_cast<long long*>(s_dn);
+      stage_f[q * 64 + cc] = sf;
+      stage_c[q * 64 + cc] = sc;
+      __syncthreads();
+      if (q == 0 && col < a.l) {
+        const long long tc_ = stage_c[cc] + stage_c[64 + cc] + stage_c[128 + cc] + stage_c[192 + cc];
+        if (tc_) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + col), (unsigned long long)tc_);
+        if (a.Fpart)
+          a.Fpart[(size_t)blockIdx.x * a.lp + col] =
+              ((stage_f[cc] + stage_f[64 + cc]) + stage_f[128 + cc]) + stage_f[192 + cc];
+      }
+      __syncthreads();
     }
-    if (sc) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + c), (unsigned long long)sc);
-    if (a.Fpart) a.Fpart[(size_t)blockIdx.x * a.lp + c] = sf;
   }
 }
 
-// G pass finish: W[j][c] = s_j * G[j][c],  G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * C_c - T[j][c] / 2)
-// written to Gout rows (the slice kernel turns W into G~ afterwards); also the column abs-max of
-// W for that slicing. R is re-zeroed.
-__global__ void k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S,
-                              const double* __restrict__ F, LutParams lut, const long long* __restrict__ Csum,
-                              const unsigned long long* __restrict__ colmax_in, double* __restrict__ Gout,
-                              unsigned long long* __restrict__ colmax_out) {
+// G pass finish: G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * C_c - T[j][c] / 2) written to Gout rows
+// (the slice kernel turns s o G into the rounded G~ afterwards); also the column abs-max of
+// W = s o G for that slicing. R is re-zeroed. One block per 64 rows: the rows are one contiguous
+// run of 64*lp values, so every access is flat and coalesced with many loads in flight.
+__global__ void __launch_bounds__(256)
+k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, const double* __restrict__ F,
+              LutParams lut, const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax_in,
+              double* __restrict__ Gout, unsigned long long* __restrict__ colmax_out) {
+  __shared__ double s_s[kKB], s_omf[kKB], s_cs[kMaxNP], s_sc[kMaxNP];
   __shared__ unsigned long long smax[kMaxNP];
-  for (int c = threadIdx.x; c < l; c += blockDim.x) smax[c] = 0ull;
-  __syncthreads();
+  const int tid = threadIdx.x;
   const int p = 8 * S - 1;
-  const uint64_t total = nrows * (uint64_t)lp;
-  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t j = idx / lp;
-    const int c = (int)(idx - j * lp);
-    double w = 0.0;
-    if (c < l) {
-      const long long T = R[idx];
-      R[idx] = 0;
-      const double f = F[j];
-      const double s = snp_scale(f, lut);
-      const double g = scalbn((1.0 - f) * (double)Csum[c] - 0.5 * (double)T, tc_exponent(colmax_in[c]) - p) * s;
-      w = g;  // G itself; the slice kernel applies s again to form W
-      atomicMax(&smax[c], (unsigned long long)__double_as_longlong(fabs(g * s)));
+  for (int c = tid; c < l; c += 256) {
+    s_cs[c] = (double)Csum[c];
+    s_sc[c] = scalbn(1.0, tc_exponent(colmax_in[c]) - p);
+    smax[c] = 0ull;
+  }
+  const int dg = 256 / lp, dc = 256 - dg * lp;
+  for (uint64_t row0 = (uint64_t)blockIdx.x * kKB; row0 < nrows; row0 += (uint64_t)gridDim.x * kKB) {
+    __syncthreads();
+    if (tid < kKB) {
+      double f = 0.0, sj = 1.0;
+      if (row0 + tid < nrows) {
+        f = F[row0 + tid];
+        sj = snp_scale(f, lut);
+      }
+      s_s[tid] = sj;
+      s_omf[tid] = 1.0 - f;
     }
-    Gout[idx] = w;
+    __syncthreads();
+    const uint64_t left = nrows - row0;
+    const int total = (int)(left < (uint64_t)kKB ? left : (uint64_t)kKB) * lp;
+    long long* Rb = R + row0 * lp;
+    double* Gb = Gout + row0 * lp;
+    int g = tid / lp, c = tid - g * lp;
+    for (int e = tid; e < total; e += 256) {
+      double gv = 0.0;
+      if (c < l) {
+        const long long T = Rb[e];
+        Rb[e] = 0;
+        const double sj = s_s[g];
+        gv = ((s_omf[g] * s_cs[c] - 0.5 * (double)T) * s_sc[c]) * sj;
+        const double w = fabs(gv * sj);
+        // most entries are far below the running maximum: test before the atomic
+        if ((unsigned long long)__double_as_longlong(w) > smax[c]) atomicMax(&smax[c], (unsigned long long)__double_as_longlong(w));
+      }
+      Gb[e] = gv;
+      g += dg;
+      c += dc;
+      if (c >= lp) {
+        c -= lp;
+        ++g;
+      }
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < l; c += blockDim.x)
+  for (int c = tid; c < l; c += 256)
     if (smax[c]) atomicMax(&colmax_out[c], smax[c]);
 }
 
-// H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c ,  Fw_c = sum of the slice
-// kernel's per-block partials in block order. R is re-zeroed.
+// Fw[c] = sum over the slice kernel's per-block partials, in block order with a fixed tree:
+// one warp per column, lane q sums parts q, q+32, ... then the 32 lane sums are folded.
+__global__ void __launch_bounds__(256) k_tc_reduce_fpart(const double* __restrict__ Fpart, uint32_t nparts, int l, int lp,
+                                                          double* __restrict__ Fw) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= l) return;
+  double v = 0.0;
+  for (uint32_t b = lane; b < nparts; b += 32) v += Fpart[(size_t)b * lp + c];
+  v = warp_sum(v);
+  if (lane == 0) Fw[c] = v;
+}
+
+// H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c. R is re-zeroed.
 __global__ void k_tc_finish_h(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S,
                               const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax,
-                              const double* __restrict__ Fpart, uint32_t nparts, double* __restrict__ Hacc,
-                              int accumulate) {
+                              const double* __restrict__ Fw, double* __restrict__ Hacc, int accumulate) {
   __shared__ double sFw[kMaxNP], sScale[kMaxNP], sC[kMaxNP];
   const int p = 8 * S - 1;
   for (int c = threadIdx.x; c < l; c += blockDim.x) {
-    double f = 0.0;
-    for (uint32_t b = 0; b < nparts; ++b) f += Fpart[(size_t)b * lp + c];
-    sFw[c] = f;
+    sFw[c] = Fw[c];
     sScale[c] = scalbn(1.0, tc_exponent(colmax[c]) - p);
     sC[c] = (double)Csum[c];
   }
