@@ -429,13 +429,8 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
   a.Fpart = Fpart;
   // an even number of k-block images: a pipeline stage of k_tc_gemm is two k-blocks (the pad image is zero)
   const uint32_t nkb = ((uint32_t)((r1 - 1) / tc::kKB) - a.kb0 + 2) & ~1u;
-  const size_t smem = (size_t)tc::kKB * c->NP + (size_t)tc::kKB * c->l * 8 * (Fpart ? 2 : 1);
-  static size_t attr = 0;
-  if (smem > attr) {
-    PCA_CUDA(cudaFuncSetAttribute(tc::k_tc_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  tc::k_tc_slice<<<nkb, 256, smem, c->stream>>>(a);
+  const size_t smem = (size_t)tc::kKB * c->NP;
+  tc::k_tc_slice<<<nkb, tc::tc_flat_threads(c->lp), smem, c->stream>>>(a);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
   if (nkb_out) *nkb_out = nkb;
@@ -479,7 +474,8 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       tc_launch(c, a);
     }
     long long* Rrow = c->d_Racc + (loc0 - (uint64_t)a.row_r0) * c->lp;
-    tc::k_tc_finish_g<<<(unsigned)std::min<uint64_t>((nrows + tc::kKB - 1) / tc::kKB, (uint64_t)c->sms * 8), 256, 0, c->stream>>>(
+    tc::k_tc_finish_g<<<(unsigned)std::min<uint64_t>((nrows + tc::kKB - 1) / tc::kKB, (uint64_t)c->sms * 8),
+                        tc::tc_pair_threads(c->lp), 0, c->stream>>>(
         Rrow, nrows, c->l, c->lp, c->slices, c->d_F + snp0, c->lut, o_csum, o_colmax, c->d_G + snp0 * c->lp, w_colmax);
     PCA_CHECK_LAUNCH();
     c->tm.gemm_g_launches++;

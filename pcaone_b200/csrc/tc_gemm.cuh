@@ -423,20 +423,24 @@ struct TcSliceArgs {
   double* Fpart;                      // out: [gridDim.x][lp] partial sums of f_row * X~[row][c], or nullptr
 };
 
+// Threads per block of the slice / finish kernels: a multiple of lp, so that with the flat index
+// e = tid + B*i every thread stays on ONE column (c = tid % lp) and walks rows g0, g0 + B/lp, ...
+__host__ __device__ inline int tc_flat_threads(int lp) { return lp * (256 / lp); }
+
 // One block per k-block (64 rows x l columns). X rows are G (H pass: F != nullptr, the kernel
 // forms W = s_row * G itself) or Omega (G pass). The 64 rows are one contiguous run of 64*lp
-// doubles: loads and the write-back are flat and coalesced.
+// doubles: loads and the write-back are flat and coalesced; column sums live in registers.
 __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
-  int8_t* img = reinterpret_cast<int8_t*>(sm);                                   // 64*NP
-  long long* ci = reinterpret_cast<long long*>(sm + (size_t)kKB * a.NP);         // [64][l]
-  double* fw = reinterpret_cast<double*>(ci + (size_t)kKB * a.l);                // [64][l] (only if Fpart)
-  __shared__ double s_scale[kKB], s_f[kKB], s_up[kMaxNP], s_dn[kMaxNP];
+  int8_t* img = reinterpret_cast<int8_t*>(sm);  // 64*NP
+  __shared__ double s_scale[kKB], s_f[kKB];
+  __shared__ double s_pf[256];      // [rows-per-pass][lp] partial sums (rpp * lp <= 256)
+  __shared__ long long s_pc[256];
   const uint32_t kb = a.kb0 + blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, B = blockDim.x;
   const int p = 8 * a.S - 1;
   const uint64_t row0 = (uint64_t)kb * kKB;
-  for (int i = tid; i < kKB * a.NP / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kKB * a.NP / 16; i += B) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
   if (tid < kKB) {
     const uint64_t row = row0 + tid;
     double s = 1.0, f = 0.0;
@@ -447,27 +451,30 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     s_scale[tid] = s;
     s_f[tid] = f;
   }
-  for (int c = tid; c < a.l; c += 256) {
+  const int rpp = B / a.lp;  // rows per pass
+  const int g0 = tid / a.lp, c = tid - g0 * a.lp;
+  double up = 0.0, dn = 0.0;
+  if (c < a.l) {
     const int e = tc_exponent(a.colmax[c]);
-    s_up[c] = scalbn(1.0, p - e);
-    s_dn[c] = scalbn(1.0, e - p);
+    up = scalbn(1.0, p - e);
+    dn = scalbn(1.0, e - p);
   }
   __syncthreads();
-  const int total = kKB * a.lp;
   double* Xb = a.X + row0 * a.lp;
-  // column / row of flat element e = tid + 256 i, advanced incrementally (no divisions in the loop)
-  int g = tid / a.lp, c = tid - g * a.lp;
-  const int dg = 256 / a.lp, dc = 256 - dg * a.lp;
-  for (int e = tid; e < total; e += 256) {
-    const uint64_t row = row0 + g;
-    if (c < a.l) {
-      long long I = 0;
-      double xt = 0.0;
+  long long csum = 0;
+  double fsum = 0.0;
+  if (c < a.l) {
+#pragma unroll 4
+    for (int g = g0; g < kKB; g += rpp) {
+      const uint64_t row = row0 + g;
       if (row >= a.r0 && row < a.r1) {
-        const double x = Xb[e] * s_scale[g];
-        I = llrint(x * s_up[c]);
-        xt = (double)I * s_dn[c];
-        if (a.writeback) Xb[e] = xt / s_scale[g];
+        const double sj = s_scale[g];
+        const double x = Xb[g * a.lp + c] * sj;
+        const long long I = llrint(x * up);
+        const double xt = (double)I * dn;
+        if (a.writeback) Xb[g * a.lp + c] = xt / sj;
+        csum += I;
+        fsum += s_f[g] * xt;
         if (I != 0) {
           const int kp = kpos_of(g);
           long long rem = I;
@@ -479,69 +486,52 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
           img[bimg_offset(c * a.S, kp, a.NP)] = (int8_t)rem;
         }
       }
-      ci[g * a.l + c] = I;
-      if (a.Fpart) fw[g * a.l + c] = s_f[g] * xt;
-    }
-    g += dg;
-    c += dc;
-    if (c >= a.lp) {
-      c -= a.lp;
-      ++g;
     }
   }
+  s_pc[g0 * a.lp + c] = csum;
+  s_pf[g0 * a.lp + c] = fsum;
   __syncthreads();
-  for (int i = tid; i < kKB * a.NP / 16; i += 256)
+  for (int i = tid; i < kKB * a.NP / 16; i += B)
     reinterpret_cast<uint4*>(a.Bimg + (size_t)blockIdx.x * kKB * a.NP)[i] = reinterpret_cast<const uint4*>(img)[i];
-  // column sums in a fixed order: 4 quarter sums of 16 rows per column, then combined
-  {
-    const int q = tid >> 6, cc = tid & 63;  // quarter, column lane
-    for (int c0 = 0; c0 < a.l; c0 += 64) {
-      const int col = c0 + cc;
-      long long sc = 0;
-      double sf = 0.0;
-      if (col < a.l) {
-        for (int r = 16 * q; r < 16 * q + 16; ++r) {
-          sc += ci[r * a.l + col];
-          if (a.Fpart) sf += fw[r * a.l + col];
-        }
-      }
-      __syncthreads();
-      // reuse s_up/s_dn as [4][64] staging (the per-column scales are no longer needed)
-      double* stage_f = s_up;
-      long long* stage_c = reinterpret_cast<long long*>(s_dn);
-      stage_f[q * 64 + cc] = sf;
-      stage_c[q * 64 + cc] = sc;
-      __syncthreads();
-      if (q == 0 && col < a.l) {
-        const long long tc_ = stage_c[cc] + stage_c[64 + cc] + stage_c[128 + cc] + stage_c[192 + cc];
-        if (tc_) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + col), (unsigned long long)tc_);
-        if (a.Fpart)
-          a.Fpart[(size_t)blockIdx.x * a.lp + col] =
-              ((stage_f[cc] + stage_f[64 + cc]) + stage_f[128 + cc]) + stage_f[192 + cc];
-      }
-      __syncthreads();
+  if (g0 == 0 && c < a.l) {
+    long long tc_ = 0;
+    double tf = 0.0;
+    for (int q = 0; q < rpp; ++q) {  // fixed order
+      tc_ += s_pc[q * a.lp + c];
+      tf += s_pf[q * a.lp + c];
     }
+    if (tc_) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + c), (unsigned long long)tc_);
+    if (a.Fpart) a.Fpart[(size_t)blockIdx.x * a.lp + c] = tf;
   }
 }
 
+// threads per block of k_tc_finish_g: every thread owns a PAIR of adjacent columns (16-byte
+// accesses) and walks rows g0, g0 + rows-per-pass, ...
+__host__ __device__ inline int tc_pair_threads(int lp) { return (lp / 2) * (256 / (lp / 2)); }
+
 // G pass finish: G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * C_c - T[j][c] / 2) written to Gout rows
 // (the slice kernel turns s o G into the rounded G~ afterwards); also the column abs-max of
-// W = s o G for that slicing. R is re-zeroed. One block per 64 rows: the rows are one contiguous
-// run of 64*lp values, so every access is flat and coalesced with many loads in flight.
+// W = s o G for that slicing. R is re-zeroed. Blocks walk 64-row groups (contiguous 64*lp values);
+// all loads of a group are issued before the first use (the int64 accumulators come back from L2
+// with long latency right after the GEMM's atomics), running maxima stay in registers.
 __global__ void __launch_bounds__(256)
 k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, const double* __restrict__ F,
               LutParams lut, const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax_in,
               double* __restrict__ Gout, unsigned long long* __restrict__ colmax_out) {
-  __shared__ double s_s[kKB], s_omf[kKB], s_cs[kMaxNP], s_sc[kMaxNP];
-  __shared__ unsigned long long smax[kMaxNP];
-  const int tid = threadIdx.x;
+  constexpr int U = 8;  // row passes per group held in registers (rows-per-pass >= 8 -> 64 rows)
+  __shared__ double s_s[kKB], s_omf[kKB];
+  const int tid = threadIdx.x, B = blockDim.x;
   const int p = 8 * S - 1;
-  for (int c = tid; c < l; c += 256) {
-    s_cs[c] = (double)Csum[c];
-    s_sc[c] = scalbn(1.0, tc_exponent(colmax_in[c]) - p);
-    smax[c] = 0ull;
-  }
-  const int dg = 256 / lp, dc = 256 - dg * lp;
+  const int hp = lp >> 1;
+  const int rpp = B / hp;  // rows per pass, >= 8 for lp <= 64, >= 4 for lp <= 128
+  const int g0 = tid / hp, c = 2 * (tid - g0 * hp);
+  double cs[2] = {0.0, 0.0}, sc[2] = {0.0, 0.0}, m[2] = {0.0, 0.0};
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (c + h < l) {
+      cs[h] = (double)Csum[c + h];
+      sc[h] = scalbn(1.0, tc_exponent(colmax_in[c + h]) - p);
+    }
   for (uint64_t row0 = (uint64_t)blockIdx.x * kKB; row0 < nrows; row0 += (uint64_t)gridDim.x * kKB) {
     __syncthreads();
     if (tid < kKB) {
@@ -553,35 +543,43 @@ k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, c
       s_s[tid] = sj;
       s_omf[tid] = 1.0 - f;
     }
-    __syncthreads();
-    const uint64_t left = nrows - row0;
-    const int total = (int)(left < (uint64_t)kKB ? left : (uint64_t)kKB) * lp;
-    long long* Rb = R + row0 * lp;
-    double* Gb = Gout + row0 * lp;
-    int g = tid / lp, c = tid - g * lp;
-    for (int e = tid; e < total; e += 256) {
-      double gv = 0.0;
-      if (c < l) {
-        const long long T = Rb[e];
-        Rb[e] = 0;
-        const double sj = s_s[g];
-        gv = ((s_omf[g] * s_cs[c] - 0.5 * (double)T) * s_sc[c]) * sj;
-        const double w = fabs(gv * sj);
-        // most entries are far below the running maximum: test before the atomic
-        if ((unsigned long long)__double_as_longlong(w) > smax[c]) atomicMax(&smax[c], (unsigned long long)__double_as_longlong(w));
+    const int nr = (int)min((uint64_t)kKB, nrows - row0);
+    longlong2* Rb = reinterpret_cast<longlong2*>(R + row0 * lp);
+    double2* Gb = reinterpret_cast<double2*>(Gout + row0 * lp);
+    longlong2 T[U];
+    int gb = g0;
+    auto load_batch = [&]() {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = gb + u * rpp;
+        T[u] = (g < nr) ? Rb[g * hp + (c >> 1)] : make_longlong2(0, 0);
       }
-      Gb[e] = gv;
-      g += dg;
-      c += dc;
-      if (c >= lp) {
-        c -= lp;
-        ++g;
+    };
+    load_batch();     // in flight while the first 64 threads finish the per-row scales
+    __syncthreads();  // s_s / s_omf of this group are ready
+    while (true) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int g = gb + u * rpp;
+        if (g < nr) {
+          Rb[g * hp + (c >> 1)] = make_longlong2(0, 0);
+          const double sj = s_s[g], omf = s_omf[g];
+          double2 gv;
+          gv.x = (c < l) ? ((omf * cs[0] - 0.5 * (double)T[u].x) * sc[0]) * sj : 0.0;
+          gv.y = (c + 1 < l) ? ((omf * cs[1] - 0.5 * (double)T[u].y) * sc[1]) * sj : 0.0;
+          m[0] = fmax(m[0], fabs(gv.x * sj));
+          m[1] = fmax(m[1], fabs(gv.y * sj));
+          Gb[g * hp + (c >> 1)] = gv;
+        }
       }
+      gb += rpp * U;
+      if (gb >= nr) break;
+      load_batch();
     }
   }
-  __syncthreads();
-  for (int c = tid; c < l; c += 256)
-    if (smax[c]) atomicMax(&colmax_out[c], smax[c]);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (c + h < l && m[h] > 0.0) atomicMax(&colmax_out[c + h], (unsigned long long)__double_as_longlong(m[h]));
 }
 
 // Fw[c] = sum over the slice kernel's per-block partials, in block order with a fixed tree:
