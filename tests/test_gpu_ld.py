@@ -1,0 +1,88 @@
+"""GPU parity tests (-m gpu) of LD r2 (pcaone_ld_r2, csrc/ld.cuh) against the golden vectors of
+the unmodified reference (ld_r2_big, src/LD.cpp:450-473) and the numpy oracle.
+
+Tolerance: r2 within 1e-12 absolute of the FP64 reference (only the summation order of the dot
+products differs); window tables (integer logic) must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import pcaone_oracle as orc
+from pcaone_b200 import halko, ld, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(packed, N, k=2):
+    p = halko.Param(k=k, svd=1)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    d.prepare()
+    return halko.NormalRsvdOpData(d, p.k, p.oversamples)
+
+
+def _bim(M, nchr=22, step=100):
+    per_chr = (M + nchr - 1) // nchr
+    chrom = np.array([j // per_chr + 1 for j in range(M)])
+    pos = np.array([(j % per_chr + 1) * step for j in range(M)])
+    return chrom, pos
+
+
+def test_ld_windows_match_reference():
+    g = golden("ld_small")
+    M = g["G"].shape[1]
+    chrom, pos = _bim(M)
+    ws, we = ld.divide_pos_by_window(chrom, pos, int(g["ld_bp"]))
+    assert np.array_equal(ws, g["ws"]) and np.array_equal(we, g["we"])
+
+
+def test_ld_r2_vs_golden():
+    g = golden("ld_small")
+    s = golden("ssvd_small")
+    N = int(s["N"])
+    tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), "ld_golden.residuals")
+    g["residuals_file"].tofile(tmp)
+    G = orc.read_residuals(tmp)  # what FileBin::read_all hands to ld_r2_big
+    op = _ctx(s["packed"], N)
+    r2 = ld.ld_r2_big(op, G, g["ws"], g["we"])
+    np.testing.assert_allclose(r2, g["r2"], rtol=0, atol=1e-12)
+    t = op.timers()
+    assert t.ld_pairs == len(g["r2"]) and t.ld_tiles > 0
+    op.close()
+
+
+@pytest.mark.parametrize("N,M,bp,chunk", [(301, 900, 2500, 0), (1000, 3000, 12000, 0), (257, 1500, 7000, 256)])
+def test_ld_r2_dense_vs_oracle(N, M, bp, chunk, monkeypatch):
+    rng = np.random.default_rng(N + M)
+    packed = np.concatenate([synth.pack_codes(c) for _, c in synth.balding_nichols_codes(N, M, k_pop=4, seed=M)])
+    od = orc.OracleData(packed, N)
+    G = od.block(0, M - 1, False) + 0.01 * rng.standard_normal((N, M))   # residual-like dense input
+    G -= G.mean(0, keepdims=True)
+    chrom, pos = _bim(M, nchr=3)
+    ws, we = ld.divide_pos_by_window(chrom, pos, bp)
+    if chunk:
+        monkeypatch.setenv("PCAONE_LD_CHUNK", str(chunk))  # several lead chunks + halos
+    op = _ctx(packed, N)
+    r2 = ld.ld_r2_big(op, G, ws, we)
+    ref = orc.ld_r2(G, ws, we)
+    assert len(r2) == len(ref) and len(ref) > 0
+    np.testing.assert_allclose(r2, ref, rtol=0, atol=1e-12)
+    op.close()
+
+
+def test_ld_r2_from_resident_bed():
+    """G == NULL: centred, unscaled genotypes decoded from the resident packed shard
+    (read_block_initial with standardize = false, src/LD.cpp:403-424)."""
+    N, M = 500, 2000
+    packed = np.concatenate([synth.pack_codes(c) for _, c in synth.balding_nichols_codes(N, M, k_pop=5, seed=3, miss=0.02)])
+    od = orc.OracleData(packed, N)
+    G = od.block(0, M - 1, False)
+    chrom, pos = _bim(M, nchr=2)
+    ws, we = ld.divide_pos_by_window(chrom, pos, 5000)
+    op = _ctx(packed, N)
+    r2 = ld.ld_r2_big(op, None, ws, we)
+    ref = orc.ld_r2(G, ws, we)
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(r2[ok], ref[ok], rtol=0, atol=1e-12)
+    op.close()
