@@ -1,0 +1,241 @@
+// pcaone_b200 host — option parsing. Table-driven (the reference uses the popl library,
+// Cmd.cpp:9-12); flag names, defaults and the post-parse derivations follow Cmd.cpp:141-238.
+#include "cmd.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <iostream>
+#include <vector>
+
+#include "../../include/pcaone_b200.h"
+
+namespace pcaone_host {
+
+namespace {
+
+struct Opt {
+  const char* sname;  // "" if none
+  const char* lname;
+  bool takes_value;
+  const char* help;
+  std::function<void(const std::string&)> set;
+  bool seen = false;
+};
+
+template <class T>
+T parse_num(const std::string& flag, const std::string& s) {
+  try {
+    size_t pos = 0;
+    T v;
+    if constexpr (std::is_same_v<T, double>) {
+      v = std::stod(s, &pos);
+    } else if constexpr (std::is_same_v<T, uint>) {
+      if (!s.empty() && s[0] == '-') throw std::invalid_argument("negative");
+      v = (uint)std::stoul(s, &pos);
+    } else {
+      v = (T)std::stol(s, &pos);
+    }
+    if (pos != s.size()) throw std::invalid_argument("trailing");
+    return v;
+  } catch (const std::exception&) {
+    std::cerr << "Invalid Option Exception: invalid_argument\noption: " << flag << "\nvalue:  " << s << "\n";
+    std::exit(EXIT_FAILURE);
+  }
+}
+
+}  // namespace
+
+int Param::precision_code() const {
+  if (precision == "fp64") return PCAONE_PREC_FP64;
+  if (precision == "int8x2") return PCAONE_PREC_INT8X2;
+  if (precision == "int8x3") return PCAONE_PREC_INT8X3;
+  if (precision == "int8x4") return PCAONE_PREC_INT8X4;
+  throw std::invalid_argument("--precision must be one of fp64, int8x2, int8x3, int8x4");
+}
+
+Param::Param(int argc, char** argv) {
+  bool haploid = false, help = false;
+  uint svd = 2;
+  std::string usvprefix, not_on_path;
+  std::vector<Opt> opts;
+  auto val = [&](const char* s, const char* l, const char* help_, std::function<void(const std::string&)> f) {
+    opts.push_back({s, l, true, help_, std::move(f)});
+  };
+  auto sw = [&](const char* s, const char* l, const char* help_, bool* flag) {
+    opts.push_back({s, l, false, help_, [flag](const std::string&) { *flag = true; }});
+  };
+  auto off_path = [&](const char* s, const char* l, bool takes) {
+    opts.push_back({s, l, takes, nullptr, [&not_on_path, l](const std::string&) { not_on_path = l; }});
+  };
+#define NUM(T, field) [this](const std::string& v) { field = parse_num<T>(#field, v); }
+  sw("h", "help", "print all options", &help);
+  val("m", "memory", "RAM usage in GB unit for out-of-core mode. default is in-core mode", NUM(double, memory));
+  val("n", "threads", "the number of host threads (accepted; the GPU path does not use them)", NUM(uint, threads));
+  val("v", "verbose", "verbosity level for logs. 0: silent; 1: concise; 2: verbose; 3: debug", NUM(uint, verbose));
+  val("d", "svd", "SVD method. 1: single-pass RSVD with power iterations (sSVD); 2: window-based RSVD (winSVD, default)",
+      [&svd](const std::string& v) { svd = parse_num<uint>("svd", v); });
+  val("k", "pc", "top k principal components (PCs) to be calculated", NUM(uint, k));
+  val("C", "scale", "-9: standardize genetic data by sqrt(ploidy*f*(1-f)); 0: do nothing", NUM(int, scale));
+  val("", "maxp", "maximum number of power iterations for RSVD algorithm.", NUM(uint, maxp));
+  sw("S", "no-shuffle", "do not shuffle columns of data for --svd 2 (if not locally correlated).", &noshuffle);
+  val("w", "batches", "the number of mini-batches used by --svd 2.", NUM(uint, bands));
+  val("", "seed", "seeds for reproducing results.", NUM(int, seed));
+  sw("", "emu", "use EMU algorithm for genotype input with missingness.", &emu);
+  val("", "M", "the number of features (eg. SNPs) if already known.", NUM(uint, nsnps));
+  val("", "N", "the number of samples if already known.", NUM(uint, nsamples));
+  val("", "buffer", "memory buffer in GB unit for permuting the data.", NUM(uint, buffer));
+  val("", "oversamples", "the number of oversampling columns for RSVD.", NUM(uint, oversamples));
+  val("", "rand", "the random matrix type. 0: uniform; 1: guassian.", NUM(uint, rand));
+  val("", "maxiter", "maximum number of EM iterations.", NUM(uint, maxiter));
+  val("", "tol-rsvd", "tolerance for RSVD algorithm.", NUM(double, tol));
+  val("", "tol-em", "tolerance for EMU algorithm.", NUM(double, tolem));
+  val("b", "bfile", "prefix of PLINK .bed/.bim/.fam files.", [this](const std::string& v) {
+    filein = v;
+    file_t = FileType::PLINK;
+  });
+  sw("", "haploid", "the plink format represents haploid data.", &haploid);
+  val("F", "match-bim", "the .mbim file to be matched, where the 7th column is allele frequency.",
+      [this](const std::string& v) { filebim = v; });
+  val("P", "USV", "prefix of PCAone .eigvecs/.sigvals/.loadings/.mbim.", [&usvprefix](const std::string& v) { usvprefix = v; });
+  val("o", "out", "prefix of output files. default [pcaone].", [this](const std::string& v) { fileout = v; });
+  sw("V", "printv", "output the right eigenvectors with suffix .loadings.", &printv);
+  sw("D", "ld", "output a binary matrix for downstream LD related analysis.", &ld);
+  sw("R", "print-r2", "print LD R2 to *.ld.gz file for pairwise SNPs within a window controlled by --ld-bp.", &print_r2);
+  val("", "ld-bp", "physical distance threshold in bases for LD window.", NUM(uint, ld_bp));
+  val("", "ld-stats", "0: the ancestry adjusted LD; 1: the standard LD.", NUM(int, ld_stats));
+  val("", "device", "[GPU] CUDA ordinal of the (first) GPU to use.", NUM(int, device));
+  val("", "gpus", "[GPU] shard the SNPs over this many GPUs of the box.", NUM(int, gpus));
+  val("", "precision", "[GPU] GEMM arithmetic: fp64 | int8x2 | int8x3 (default) | int8x4.",
+      [this](const std::string& v) { precision = v; });
+#undef NUM
+  // reference flags whose subsystems are outside the GPU hot path (SURVEY §8 "out of scope")
+  off_path("p", "pgen", true);
+  off_path("B", "binary", true);
+  off_path("c", "csv", true);
+  off_path("g", "bgen", true);
+  off_path("G", "beagle", true);
+  off_path("", "pcangsd", false);
+  off_path("", "hardcall", false);
+  off_path("", "maf", true);
+  off_path("", "project", true);
+  off_path("", "project-bootstrap", true);
+  off_path("", "project-bootstrap-save", false);
+  off_path("", "inbreed", true);
+  off_path("", "selection", true);
+  off_path("", "ld-r2", true);
+  off_path("", "clump", true);
+  off_path("", "clump-names", true);
+  off_path("", "clump-p1", true);
+  off_path("", "clump-p2", true);
+  off_path("", "clump-r2", true);
+  off_path("", "clump-bp", true);
+  off_path("", "scale-factor", true);
+  off_path("", "imaxiter", true);
+  off_path("", "itol", true);
+  off_path("", "ncv", true);
+  off_path("", "tol-maf", true);
+  off_path("", "read-U", true);
+  off_path("", "read-V", true);
+  off_path("", "read-S", true);
+
+  ss << "PCAone-b200 (B200-native randomized-SVD path of PCAone)\nOptions in effect:\n";
+  for (int i = 0; i < argc; ++i) ss << argv[i] << ' ';
+
+  auto usage = [&]() {
+    std::cout << "Usage: PCAone-b200 -b plink_prefix [-k 10] [-d 1|2] [-m GB] [-o out] ...\n\n";
+    for (const auto& o : opts) {
+      if (!o.help) continue;
+      std::string names = (o.sname[0] ? std::string("-") + o.sname + ", " : std::string("    ")) + "--" + o.lname;
+      if (o.takes_value) names += " arg";
+      std::cout << "  " << names << std::string(names.size() < 26 ? 26 - names.size() : 1, ' ') << o.help << "\n";
+    }
+  };
+
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i], value;
+    bool has_inline = false;
+    Opt* hit = nullptr;
+    if (a.rfind("--", 0) == 0) {
+      std::string name = a.substr(2);
+      auto eq = name.find('=');
+      if (eq != std::string::npos) {
+        value = name.substr(eq + 1);
+        name = name.substr(0, eq);
+        has_inline = true;
+      }
+      for (auto& o : opts)
+        if (name == o.lname) hit = &o;
+    } else if (a.size() >= 2 && a[0] == '-') {
+      std::string name = a.substr(1, 1);
+      for (auto& o : opts)
+        if (o.sname[0] && name == o.sname) hit = &o;
+      if (hit && a.size() > 2) {
+        if (!hit->takes_value) hit = nullptr;  // grouped switches are not supported
+        else {
+          value = a.substr(2);
+          has_inline = true;
+        }
+      }
+    }
+    if (!hit) {
+      std::cerr << "unknown option: " << a << "\n";
+      std::exit(EXIT_FAILURE);
+    }
+    if (hit->takes_value && !has_inline) {
+      if (i + 1 >= argc) {
+        std::cerr << "Invalid Option Exception: missing_argument\noption: " << a << "\n";
+        std::exit(EXIT_FAILURE);
+      }
+      value = argv[++i];
+    }
+    hit->seen = true;
+    hit->set(value);
+  }
+  if (help || argc == 1) {
+    usage();
+    std::exit(EXIT_SUCCESS);
+  }
+  try {
+    if (!not_on_path.empty())
+      throw std::invalid_argument("--" + not_on_path +
+                                  " belongs to a PCAone subsystem outside the B200 randomized-SVD path; use the reference "
+                                  "PCAone binary for it");
+    if (svd == 1)
+      svd_t = SvdType::PCAoneAlg1;
+    else if (svd == 2)
+      svd_t = SvdType::PCAoneAlg2;
+    else
+      throw std::invalid_argument("--svd 0 (IRAM) and 3 (full SVD) are outside the B200 randomized-SVD path; use --svd 1 or 2");
+    if (file_t != FileType::PLINK) throw std::invalid_argument("please give the PLINK prefix with -b/--bfile");
+    genetic = true;
+    if (!usvprefix.empty()) {
+      fileU = usvprefix + ".eigvecs";
+      fileE = usvprefix + ".eigvals";
+      fileS = usvprefix + ".sigvals";
+      fileV = usvprefix + ".loadings";
+      if (filebim.empty()) filebim = usvprefix + ".mbim";
+    }
+    if (print_r2) {  // Cmd.cpp:181-184
+      dopca = false;
+      memory /= 2.0;
+    }
+    oversamples = oversamples > k ? oversamples : k;  // Cmd.cpp:216
+    if (haploid && genetic) ploidy = 1;
+    if (memory > 0) out_of_core = true;
+    if (emu)
+      missme = true;
+    else if (dopca)
+      maxiter = 0;
+    if (bands < 4 || bands % 2 != 0)
+      throw std::invalid_argument("the -w/--batches must be a power of 2 and the minimun is 4.");
+    if (svd_t == SvdType::PCAoneAlg2 && !noshuffle) perm = true;
+    if (gpus < 1) throw std::invalid_argument("--gpus must be >= 1");
+    (void)precision_code();
+  } catch (const std::exception& e) {
+    std::cerr << "Exception: " << e.what() << "\n";
+    std::exit(EXIT_FAILURE);
+  }
+}
+
+}  // namespace pcaone_host

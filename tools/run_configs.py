@@ -1,0 +1,240 @@
+"""Run BASELINE.json's five configs on ONE B200 at their named sizes (or a stated scale) and
+print one JSON line per config: time-to-top-k PCs (s), packed GB/s per power-iteration pass,
+and an accuracy / property check. Run under gpurun; results are copied to profiles/.
+
+    python tools/run_configs.py [c1 c2 c3 c4 c5] [--scale S] [--out gpurun_out/configs.jsonl]
+
+The CPU reference (oracle/_ref) is only the checker of config 1 here (the one config the
+reference runs in-core on CPU today); it is never on the measured path.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from pcaone_b200 import _lib, halko, ld, synth  # noqa: E402
+
+
+def _emit(out, rec):
+    line = json.dumps(rec)
+    print(line, flush=True)
+    if out:
+        with open(out, "a") as f:
+            f.write(line + "\n")
+
+
+def _corr_cols(A, B):
+    A = A / np.linalg.norm(A, axis=0)
+    B = B / np.linalg.norm(B, axis=0)
+    return np.abs((A * B).sum(0))
+
+
+def _run(op, p):
+    """computeUSV to convergence; returns (seconds, epochs) device-synchronised."""
+    op.sync()
+    t0 = time.perf_counter()
+    op.computeUSV(p.maxp, p.tol)  # includes the D2H of U, S, V
+    return time.perf_counter() - t0, op.epochs
+
+
+def _pass_time(op, pi_list):
+    """seconds per computeGandH pass (averaged over the given epochs), device-synchronised."""
+    op.sync()
+    t0 = time.perf_counter()
+    for pi in pi_list:
+        op._chk(op.L.pcaone_compute_gandh(op.h, pi))
+    op.sync()
+    return (time.perf_counter() - t0) / len(pi_list)
+
+
+def c1(args, out):
+    N, M, k = 2504, int(100_000 * args.scale), 10
+    packed = synth.torch_packed(N, M, k_pop=k + 4, seed=1, device="cuda:0", chunk=16384)
+    res = {}
+    for name, prec in (("fp64", 0), ("int8x3", 3)):
+        p = halko.Param(k=k, svd=1, maxp=20, tol=1e-4, precision=prec)
+        t0 = time.perf_counter()
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+        op.setFlags(False, True)
+        secs, ep = _run(op, p)
+        total = time.perf_counter() - t0
+        pt = _pass_time(op, [1, 2, 3])
+        res[name] = dict(U=op.U.copy(), S=op.S.copy(), secs=secs, total=total, epochs=ep, pass_s=pt)
+        op.close()
+    rec = {"config": "C1", "workload": f"sSVD in-memory N={N} M={M} k={k}", "bytes_per_pass": M * packed.shape[1]}
+    for name in res:
+        r = res[name]
+        rec[name] = {"time_to_pcs_s": r["secs"], "incl_upload_af_s": r["total"], "epochs": r["epochs"],
+                     "pass_ms": 1e3 * r["pass_s"], "gbs_per_pass": rec["bytes_per_pass"] / r["pass_s"] / 1e9}
+    rec["int8x3_vs_fp64"] = {"eig_rel": float(np.max(np.abs(res["int8x3"]["S"] ** 2 - res["fp64"]["S"] ** 2) / res["fp64"]["S"] ** 2)),
+                             "min_abs_corr": float(_corr_cols(res["int8x3"]["U"], res["fp64"]["U"]).min())}
+    # the reference itself on the same bed (CPU, all cores): time and parity
+    try:
+        from oracle import ref
+        if ref.available() and not args.no_ref:
+            import tempfile
+            tmp = tempfile.mkdtemp(prefix="c1_")
+            synth.write_bed_from_packed(os.path.join(tmp, "s"), packed.cpu().numpy(), N)
+            th = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            r = ref.Ref(f"PCAone -b {tmp}/s -k {k} -d 1 -o {tmp}/o -n {th}", threads=th)
+            r.new_op()
+            r.set_flags(False, True)
+            U, S, V = r.compute_usv(20, 1e-4)
+            cpu_s = time.perf_counter() - t0
+            r.close()
+            rec["reference_cpu"] = {"time_to_pcs_s": cpu_s, "cores": th,
+                                    "eig_rel_fp64": float(np.max(np.abs(res["fp64"]["S"] ** 2 - S ** 2) / S ** 2)),
+                                    "min_abs_corr_fp64": float(_corr_cols(res["fp64"]["U"], U).min()),
+                                    "eig_rel_int8x3": float(np.max(np.abs(res["int8x3"]["S"] ** 2 - S ** 2) / S ** 2)),
+                                    "min_abs_corr_int8x3": float(_corr_cols(res["int8x3"]["U"], U).min())}
+    except Exception as e:  # the checker is optional on the box
+        rec["reference_cpu"] = {"error": str(e)[:200]}
+    _emit(out, rec)
+
+
+def c2(args, out):
+    N, M, k = 10_000, int(1_000_000 * args.scale), 20
+    packed = synth.torch_packed(N, M, k_pop=k + 4, seed=1, device="cuda:0", chunk=16384)
+    rec = {"config": "C2", "workload": f"winSVD in-memory N={N} M={M} k={k} 64 windows", "bytes_per_pass": M * packed.shape[1]}
+    res = {}
+    for name, prec in (("int8x3", 3), ("fp64", 0)):
+        p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, precision=prec)
+        t0 = time.perf_counter()
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+        op.setFlags(False, True)
+        secs, ep = _run(op, p)
+        total = time.perf_counter() - t0
+        secs2, _ = _run(op, p)  # second run: tiles / allocations warm
+        pt = _pass_time(op, [6, 7, 8])
+        res[name] = (op.U.copy(), op.S.copy())
+        rec[name] = {"time_to_pcs_s": secs2, "first_run_s": secs, "incl_upload_af_s": total, "epochs": ep,
+                     "late_pass_ms": 1e3 * pt, "gbs_per_late_pass": rec["bytes_per_pass"] / pt / 1e9}
+        op.close()
+    rec["int8x3_vs_fp64"] = {"eig_rel": float(np.max(np.abs(res["int8x3"][1] ** 2 - res["fp64"][1] ** 2) / res["fp64"][1] ** 2)),
+                             "min_abs_corr": float(_corr_cols(res["int8x3"][0], res["fp64"][0]).min())}
+    _emit(out, rec)
+
+
+def _host_avail_gb():
+    for ln in open("/proc/meminfo"):
+        if ln.startswith("MemAvailable"):
+            return int(ln.split()[1]) / 1e6
+    return 0.0
+
+
+def c3(args, out):
+    N, k = 500_000, 40
+    M = int(500_000 * args.scale)
+    bpr = synth.bytes_per_snp(N)
+    need_gb = M * bpr / 1e9
+    avail = _host_avail_gb()
+    while need_gb * 1.6 > avail and M > 50_000:  # stay well inside host RAM (a dead box is a strike)
+        M //= 2
+        need_gb = M * bpr / 1e9
+    host = torch.empty((M, bpr), dtype=torch.uint8, pin_memory=True)
+    chunk = 20_000
+    for s in range(0, M, chunk):
+        m = min(chunk, M - s)
+        host[s:s + m].copy_(synth.torch_packed(N, m, k_pop=k + 4, seed=100 + s, device="cuda:0", chunk=2048))
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, memory=1.0, precision=3)
+    d = halko.FileBed(p, packed=host, nsamples=N)
+    bs = -(-M // 64)
+    d.start = np.arange(64, dtype=np.uint64) * np.uint64(bs)
+    d.stop = np.minimum(d.start + np.uint64(bs - 1), np.uint64(M - 1))
+    d.nblocks, d.blocksize, d.bandFactor = 64, bs, 1
+    op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+    op.setFlags(False, True)
+    secs, ep = _run(op, p)
+    tm = op.timers(reset=True)
+    pt = _pass_time(op, [6, 7])
+    U = op.U
+    orth = float(np.abs(U.T @ U - np.eye(k)).max())
+    rec = {"config": "C3", "workload": f"winSVD out-of-core (64 host-streamed blocks) N={N} M={M} k={k} l={2 * k} int8x3, 1 GPU",
+           "host_mem_avail_gb": avail, "bytes_per_pass": M * bpr, "time_to_pcs_s": secs, "epochs": ep,
+           "late_pass_ms": 1e3 * pt, "gbs_per_late_pass": M * bpr / pt / 1e9,
+           "h2d_gb_total": tm.h2d_bytes / 1e9, "tc_ranges": int(tm.tc_ranges), "fp64_ranges": int(tm.fp64_ranges),
+           "U_orthonormality_err": orth, "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
+    op.close()
+    _emit(out, rec)
+
+
+def c4(args, out):
+    N, M, k = 50_000, int(500_000 * args.scale), 10
+    packed = synth.torch_packed(N, M, k_pop=k + 4, miss=0.10, seed=4, device="cuda:0", chunk=4096)
+    p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, emu=True, precision=args.c4_prec)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+    op.sync()
+    t0 = time.perf_counter()
+    iters = op.runEM()
+    secs = time.perf_counter() - t0
+    tm = op.timers(reset=True)
+    U = op.U
+    rec = {"config": "C4", "workload": f"EMU winSVD in-memory N={N} M={M} k={k} 10% missing, precision={args.c4_prec}",
+           "bytes_per_pass": M * packed.shape[1], "time_to_pcs_s": secs, "em_iterations": iters,
+           "missing_fraction": op.missing_count() / (N * M), "tc_ranges": int(tm.tc_ranges), "fp64_ranges": int(tm.fp64_ranges),
+           "U_orthonormality_err": float(np.abs(U.T @ U - np.eye(k)).max()), "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
+    op.close()
+    _emit(out, rec)
+
+
+def c5(args, out):
+    N, M = 20_000, int(200_000 * args.scale)
+    packed = synth.torch_packed(N, M, k_pop=6, seed=5, device="cuda:0", chunk=8192)
+    p = halko.Param(k=2, svd=1, ld=True)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+    # .bim of the synthetic bed: 22 chromosomes, 100 bp apart; --ld-bp 100000 => ~1000 SNPs per window
+    per = -(-M // 22)
+    chrom = np.minimum(np.arange(M) // per, 21)
+    pos = (np.arange(M) % per + 1) * 100
+    t0 = time.perf_counter()
+    ws, we = ld.divide_pos_by_window(chrom, pos, 100_000)
+    plan_s = time.perf_counter() - t0
+    op.sync()
+    t0 = time.perf_counter()
+    r2 = ld.ld_r2_big(op, None, ws, we)
+    secs = time.perf_counter() - t0
+    tm = op.timers(reset=True)
+    rec = {"config": "C5", "workload": f"LD r2 from the resident bed N={N} M={M}, --ld-bp 100000 (mean window {float(we.mean()):.0f} SNPs)",
+           "pairs": int(r2.size), "host_window_plan_s": plan_s, "r2_total_s": secs, "kernel_ms": tm.ld_ms,
+           "tiles": int(tm.ld_tiles), "gram_tflops_fp64": 2.0 * N * tm.ld_tiles * 128 * 128 / (tm.ld_ms * 1e-3) / 1e12 if tm.ld_ms else None,
+           "r2_range": [float(r2.min()), float(r2.max())], "pairs_per_s": r2.size / secs}
+    op.close()
+    _emit(out, rec)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="multiply every M by this (debug)")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--c4-prec", type=int, default=0)
+    args = ap.parse_args()
+    _lib.load()
+    fns = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+    for w in args.which:
+        t0 = time.perf_counter()
+        try:
+            fns[w](args, args.out)
+        except Exception as e:
+            _emit(args.out, {"config": w.upper(), "error": repr(e)[:500]})
+        torch.cuda.empty_cache()
+        print(f"# {w} done in {time.perf_counter() - t0:.1f} s wall", file=sys.stderr, flush=True)
+
+
+if __name__ == "__main__":
+    main()
