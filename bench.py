@@ -46,7 +46,7 @@ def _peaks():
 
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML
-    (nvidia_ml_py) every 100 ms; falls back to one `nvidia-smi` query when NVML is unavailable.
+    (nvidia_ml_py) every 20 ms; falls back to one `nvidia-smi` query when NVML is unavailable.
     (A polling `nvidia-smi -lms` child process contends for the driver lock and slows down a
     launch-bound timed region several-fold, so it is not used.)"""
 
@@ -85,7 +85,7 @@ class ClockSampler:
                 self.samples.append((sm, mx, rs))
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def stop(self):
         if self.nv is None:
@@ -101,7 +101,7 @@ class ClockSampler:
         sm = [x[0] for x in self.samples]
         mx = [x[1] for x in self.samples]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": reasons, "samples": len(sm), "source": "nvml in-process, 100 ms"}
+                "reasons": reasons, "samples": len(sm), "source": "nvml in-process, 20 ms"}
 
     def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -248,13 +248,20 @@ def main():
         o._chk(o.L.pcaone_compute_gandh(o.h, i))
         o._chk(o.L.pcaone_small_stage(o.h))
 
-    for i in range(args.warmup):
-        step(op, i)
-    op.sync()
-    op.enable_timing(True)
-    op.timers(reset=True)
+    # NVML is initialised and the sampler thread started BEFORE the warm-up (nvmlInit costs ~30 ms
+    # of driver lock, which must not land in the timed region); its samples are cleared below.
     sampler = ClockSampler(local)
     sampler.start()
+    op.enable_timing(True)
+    for i in range(args.warmup):
+        step(op, i)
+    # one more untimed replica of the timed loop so that every (pi -> schedule) code path, cuda
+    # function attribute and workspace of the timed steps has been touched once
+    for i in range(args.steps):
+        step(op, i)
+    op.sync()
+    op.timers(reset=True)
+    sampler.samples.clear()
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -361,6 +368,7 @@ def main():
                 "config": {"workload": f"configs[1]: winSVD in-memory, N={n} x M={m} SNPs per GPU, k={K}, l={l}, "
                                        f"{BANDS} windows, no-shuffle; step = one computeUSV epoch (pi = step index)",
                            "l2": "inputs (2.5 GB packed per GPU) are larger than L2; no flush needed",
+                           "warmup_note": f"{args.warmup} warm-up steps + one untimed replica of the {args.steps} timed steps",
                            "parallelism": f"snp-shard x{world}"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                 "clocks": clocks}
