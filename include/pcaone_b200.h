@@ -78,6 +78,11 @@ int  pcaone_abi_version(void);
 void* pcaone_stream(pcaone_ctx* ctx);                  /* the cudaStream_t all work runs on */
 int  pcaone_sync(pcaone_ctx* ctx);
 int  pcaone_set_allreduce(pcaone_ctx* ctx, pcaone_allreduce_fn fn, void* user);
+/* Page-locked host buffers for the packed bed (FileBed::inbed, FilePlink.hpp:43-46): a host that
+ * reads the .bed into one of these gets full-rate cudaMemcpyAsync in upload / streaming. */
+int  pcaone_alloc_pinned(void** out, size_t bytes);
+void pcaone_free_pinned(void* p);
+int  pcaone_device_count(void);                        /* usable CUDA devices; 0 = none */
 
 /* ---- genotype sources (Data::prepare, Data.cpp:14-85) ----------------------------- */
 /* FileBed::read_all (FilePlink.cpp:26-120): keep the packed shard resident in HBM.

@@ -46,7 +46,7 @@ SYMBOLS = [
     "pcaone_set_flags", "pcaone_set_omega", "pcaone_get_omega", "pcaone_set_usv", "pcaone_get_usv", "pcaone_get_GH",
     "pcaone_set_H", "pcaone_compute_gandh", "pcaone_small_stage", "pcaone_compute_usv", "pcaone_run_em",
     "pcaone_orth_omega", "pcaone_mev", "pcaone_init_omega", "pcaone_shuffle_indices", "pcaone_ld_r2",
-    "pcaone_get_timers", "pcaone_enable_timing",
+    "pcaone_get_timers", "pcaone_enable_timing", "pcaone_alloc_pinned", "pcaone_free_pinned", "pcaone_device_count",
 ]
 
 _lib = None
@@ -85,6 +85,12 @@ def load():
         "pcaone_shuffle_indices": [u64, vp], "pcaone_ld_r2": [vp, vp, u64, vp, vp, u64, vp],
         "pcaone_get_timers": [vp, C.POINTER(Timers), i32], "pcaone_enable_timing": [vp, i32],
     }
+    L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.pcaone_alloc_pinned.restype = C.c_int
+    L.pcaone_free_pinned.argtypes = [C.c_void_p]
+    L.pcaone_free_pinned.restype = None
+    L.pcaone_device_count.argtypes = []
+    L.pcaone_device_count.restype = C.c_int
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args

@@ -1459,6 +1459,22 @@ void pcaone_destroy(pcaone_ctx* c) {
 }
 
 void* pcaone_stream(pcaone_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int pcaone_alloc_pinned(void** out, size_t bytes) {
+  if (!out) return 1;
+  *out = nullptr;
+  return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable) == cudaSuccess ? 0 : 1;
+}
+void pcaone_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int pcaone_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 int pcaone_sync(pcaone_ctx* c) { CTX_GUARD(c, PCA_CUDA(cudaStreamSynchronize(c->stream))); }
 int pcaone_set_allreduce(pcaone_ctx* c, pcaone_allreduce_fn fn, void* user) {
   CTX_GUARD(c, {

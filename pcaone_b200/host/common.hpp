@@ -9,6 +9,7 @@
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -72,6 +73,8 @@ class Logger {
  public:
   std::ofstream file;
   bool is_screen = false;
+  // ranks > 0 of an in-process multi-GPU job keep quiet (rank 0 speaks for the job)
+  static inline thread_local bool muted = false;
 
   template <class... A>
   void print(const A&... a) {
@@ -96,6 +99,7 @@ class Logger {
   }
 
  private:
+  std::mutex mu_;
   template <class T, class... A>
   static void join(std::ostringstream& os, const T& t, const A&... a) {
     os << t;
@@ -105,6 +109,8 @@ class Logger {
     }
   }
   void emit(const std::string& s, bool err) {
+    if (muted && !err) return;
+    std::lock_guard<std::mutex> lk(mu_);
     if (file.is_open()) file << s << std::endl;
     if (err)
       std::cerr << s << std::endl;

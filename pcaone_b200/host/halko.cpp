@@ -1,0 +1,218 @@
+// pcaone_b200 host — RsvdOpData family and run_pca_with_halko on top of the C-ABI
+// (include/pcaone_b200.h). Control flow, log lines and the order of setFlags / computeUSV /
+// flip_UV / writers follow /root/reference/src/Halko.cpp:271-345; the passes themselves are
+// pcaone_compute_usv / pcaone_run_em on the device.
+#include "halko.hpp"
+
+#include <atomic>
+#include <condition_variable>
+#include <thread>
+
+#ifdef PCAONE_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace pcaone_host {
+
+void RsvdOpData::setFlags(bool is_update, bool is_standardize) {
+  update = is_update;
+  standardize = is_standardize;
+  data->check(pcaone_set_flags(data->ctx, update ? 1 : 0, standardize ? 1 : 0));
+}
+
+void RsvdOpData::initOmg() {
+  // the reference's seeded libstdc++ stream (RSVD.hpp:20-59), generated on the host by the
+  // library's helper so that Omega is identical by construction, then kept in HBM
+  Omg.resize(cols(), size());
+  if (pcaone_init_omega((uint64)cols(), (uint32_t)size(), data->params.seed, data->params.rand ? 1 : 0, Omg.data()))
+    cao.error("initOmg failed");
+  Omg2 = Omg;
+  data->check(pcaone_set_omega(data->ctx, Omg.data()));
+}
+
+void RsvdOpData::gandh_device(Mat2D& G, Mat2D& H, int pi) {
+  data->check(pcaone_compute_gandh(data->ctx, pi));
+  if (G.rows() != (uint64)rows() || G.cols() != (uint64)size()) G.resize(rows(), size());
+  if (H.rows() != (uint64)cols() || H.cols() != (uint64)size()) H.resize(cols(), size());
+  data->check(pcaone_get_GH(data->ctx, G.data(), H.data()));
+}
+
+void RsvdOpData::fetchUSV() {
+  U.resize(cols(), ranks());
+  V.resize(rows(), ranks());
+  S.resize(ranks());
+  data->check(pcaone_get_usv(data->ctx, U.data(), S.data(), V.data()));
+}
+
+void RsvdOpData::computeUSV(int p, double tol) {
+  data->check(pcaone_compute_usv(data->ctx, p, tol, &diff, &epochs));
+  if (data->params.verbose > 1) cao.print(tick.date(), "running of epoch =", epochs - 1, ", diff =", diff);
+  cao.print(tick.date(), "stops at epoch =", epochs);
+  fetchUSV();
+}
+
+int RsvdOpData::runEM() {
+  int iters = 0;
+  data->check(pcaone_run_em(data->ctx, &iters));
+  fetchUSV();
+  return iters;
+}
+
+static RsvdOpData* compute_pca(Data* data, const Param& params) {
+  RsvdOpData* rsvd;
+  if (params.svd_t == SvdType::PCAoneAlg2) {
+    if (params.ld) cao.warn("You are recommended to use --svd 1 for outputting the LD residual matrix");
+    cao.print(tick.date(), "initialize window-based RSVD (winSVD) with",
+              params.out_of_core ? "out-of-core" : "in-core");
+    rsvd = new FancyRsvdOpData(data, params.k, params.oversamples);
+  } else {
+    cao.print(tick.date(), "initialize single-pass RSVD (sSVD) with", params.out_of_core ? "out-of-core" : "in-core");
+    rsvd = new NormalRsvdOpData(data, params.k, params.oversamples);
+  }
+  if (!params.missme) {
+    rsvd->setFlags(false, params.genetic ? !params.ld : false);
+    rsvd->computeUSV(params.maxp, params.tol);
+  } else {
+    if (data->p_miss == 0.0 && !params.out_of_core) cao.warn("there is no missing values");
+    cao.print(tick.date(), "run EM-PCA. maxiter =", params.maxiter);
+    const int iters = rsvd->runEM();  // Halko.cpp:290-319 incl. the final standardised EMU pass
+    cao.print(tick.date(), "individual allele frequencies estimated, EM iterations =", iters);
+  }
+  return rsvd;
+}
+
+static void write_pca(Data* data, RsvdOpData* rsvd, const Param& params) {
+  Mat2D VT;
+  if (params.ld) {
+    VT.resize(rsvd->V.cols(), rsvd->V.rows());
+    for (uint64 i = 0; i < rsvd->V.rows(); ++i)
+      for (uint64 j = 0; j < rsvd->V.cols(); ++j) VT(j, i) = rsvd->V(i, j);
+    data->write_residuals(rsvd->S, rsvd->U, VT);
+  }
+  Mat1D E(rsvd->S.size());
+  for (uint64 i = 0; i < E.size(); ++i) E(i) = rsvd->S(i) * rsvd->S(i) / (double)data->nsnps;
+  data->write_eigs_files(E, rsvd->S, rsvd->U, rsvd->V);
+}
+
+void run_pca_with_halko(Data* data, const Param& params, const std::function<void(RsvdOpData*)>& before_write) {
+  RsvdOpData* rsvd = compute_pca(data, params);
+  if (before_write) before_write(rsvd);
+  if (data->F.size() != data->nsnps && params.out_of_core && data->shard.world == 1) {
+    data->F.resize(data->nsnps);  // out-of-core: frequencies were computed during the first pass
+    data->check(pcaone_get_F(data->ctx, data->F.data()));
+  }
+  if (data->shard.rank == 0) write_pca(data, rsvd, params);
+  delete rsvd;
+  cao.print(tick.date(), "PCAone - Randomized SVD done");
+}
+
+void make_plink2_eigenvec_file(int K, const std::string& fout, const std::string& fin, const std::string& fam) {
+  std::ifstream ifam(fam), ifin(fin);
+  std::ofstream ofs(fout);
+  ofs << "#FID\tIID";
+  for (int i = 0; i < K; i++) ofs << "\tPC" << i + 1;
+  ofs << "\n";
+  std::string line1, line2;
+  while (std::getline(ifam, line1)) {
+    std::istringstream is(line1);
+    std::string fid, iid;
+    is >> fid >> iid;
+    std::getline(ifin, line2);
+    ofs << fid << "\t" << iid << "\t" << line2 << std::endl;
+  }
+}
+
+// ---------------------------------------------------------------------------- multi-GPU
+#ifdef PCAONE_WITH_NCCL
+namespace {
+struct NcclHook {
+  ncclComm_t comm;
+};
+int nccl_allreduce(void* user, void* buf, uint64_t count, void* stream) {
+  auto* h = static_cast<NcclHook*>(user);
+  return ncclAllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, h->comm, (cudaStream_t)stream) == ncclSuccess
+             ? 0
+             : 1;
+}
+class Barrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int count, waiting = 0, gen = 0;
+
+ public:
+  explicit Barrier(int n) : count(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const int g = gen;
+    if (++waiting == count) {
+      waiting = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return g != gen; });
+    }
+  }
+};
+}  // namespace
+#endif
+
+void run_pca_sharded(const Param& params) {
+#ifndef PCAONE_WITH_NCCL
+  (void)params;
+  cao.error("this binary was built without NCCL; --gpus > 1 is unavailable");
+#else
+  const int g = params.gpus;
+  if (pcaone_device_count() < params.device + g) cao.error("--gpus exceeds the number of CUDA devices");
+  if (params.missme) cao.error("--emu with --gpus > 1 is not supported yet (flip_UV across SNP shards)");
+  std::vector<int> devs(g);
+  for (int i = 0; i < g; ++i) devs[i] = params.device + i;
+  std::vector<ncclComm_t> comms(g);
+  if (ncclCommInitAll(comms.data(), g, devs.data()) != ncclSuccess) cao.error("ncclCommInitAll failed");
+  Mat2D Vfull;
+  Mat1D Ffull;
+  Barrier bar(g);
+  std::vector<std::string> errors(g);
+  std::atomic<bool> failed{false};
+  auto worker = [&](int rank) {
+    Logger::muted = rank != 0;
+    try {
+      FileBed data(params, rank, g);
+      data.prepare();
+      NcclHook hook{comms[rank]};
+      data.check(pcaone_set_allreduce(data.ctx, &nccl_allreduce, &hook));
+      run_pca_with_halko(&data, params, [&](RsvdOpData* op) {
+        if (rank == 0) {
+          Vfull.resize(data.nsnps, op->ranks());
+          Ffull.resize(data.nsnps);
+        }
+        bar.wait();
+        Mat1D Floc(data.nsnps_local);
+        data.check(pcaone_get_F(data.ctx, Floc.data()));
+        for (uint64 r = 0; r < data.nsnps_local; ++r) {
+          const uint64 j = data.shard.snps[r];
+          Ffull(j) = Floc(r);
+          for (Index c = 0; c < op->ranks(); ++c) Vfull(j, c) = op->V(r, c);
+        }
+        bar.wait();
+        if (rank == 0) {
+          op->V = Vfull;
+          data.F = Ffull;
+        }
+      });
+      if (rank == 0) cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
+    } catch (const std::exception& e) {
+      errors[rank] = e.what();
+      failed = true;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int r = 0; r < g; ++r) th.emplace_back(worker, r);
+  for (auto& t : th) t.join();
+  for (auto& c : comms) ncclCommDestroy(c);
+  if (failed)
+    for (auto& e : errors)
+      if (!e.empty()) cao.error(e);
+#endif
+}
+
+}  // namespace pcaone_host

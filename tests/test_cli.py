@@ -1,0 +1,167 @@
+"""The C++ front-end `PCAone-b200` (pcaone_b200/host): same flags, same output files as the
+reference CLI (src/Main.cpp, src/Cmd.cpp, Data::write_eigs_files). CPU: option handling and the
+loud failure without a GPU. GPU (-m gpu): the files it writes against the compiled reference
+(oracle/_ref) on the same bed — eigenvalues <= 1e-5 relative (the files carry 6 significant
+digits), PCs / loadings |cos| >= 0.9999 up to sign."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, col_cos
+from pcaone_b200 import synth
+
+BIN = os.path.join(ROOT, "pcaone_b200", "bin", "PCAone-b200")
+
+
+def _run(args, cwd=None, ok=True):
+    r = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, cwd=cwd, timeout=600)
+    if ok:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r
+
+
+def test_cli_binary_is_built_and_prints_reference_flags():
+    assert os.path.exists(BIN), "run __graft_entry__.build()"
+    out = _run(["--help"]).stdout
+    for flag in ("--bfile", "--pc", "--svd", "--memory", "--batches", "--no-shuffle", "--emu", "--maxp", "--tol-rsvd",
+                 "--print-r2", "--ld-bp", "--printv", "--out", "--seed", "--oversamples", "--gpus", "--precision"):
+        assert flag in out, flag
+
+
+def test_cli_rejects_bad_options(tmp_path):
+    assert _run(["-b", "x", "-w", "3"], ok=False).returncode != 0            # Cmd.cpp:228 bands rule
+    assert _run(["-b", "x", "--svd", "0"], ok=False).returncode != 0          # IRAM is off the GPU path
+    r = _run(["-b", "x", "--bgen", "y"], ok=False)
+    assert r.returncode != 0 and "outside the B200" in r.stderr
+    assert _run(["-b", "x", "-k", "abc"], ok=False).returncode != 0
+    assert _run(["--nope"], ok=False).returncode != 0
+    # a missing / corrupt bed is an error, not a silent fallback
+    r = _run(["-b", str(tmp_path / "missing"), "-o", str(tmp_path / "o")], ok=False)
+    assert r.returncode != 0
+
+
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, 50, 300, k_pop=3, seed=1)
+    r = _run(["-b", prefix, "-k", "2", "-o", str(tmp_path / "o")], ok=False)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+
+
+# ------------------------------------------------------------------------------- GPU
+def _ref(cmd, maxp, em=False):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    r = ref.Ref(cmd, threads=8)
+    r.new_op()
+    if em:
+        U, S, V, _ = r.run_em()
+    else:
+        U, S, V = r.compute_usv(maxp, 0.0)
+    perm = r.perm_indices() if r.perm else None
+    r.close()
+    return U, S, V, perm
+
+
+def _load(prefix, k, M):
+    U = np.loadtxt(prefix + ".eigvecs", ndmin=2)
+    S = np.loadtxt(prefix + ".sigvals", ndmin=1)
+    E = np.loadtxt(prefix + ".eigvals", ndmin=1)
+    V = np.loadtxt(prefix + ".loadings", ndmin=2) if os.path.exists(prefix + ".loadings") else None
+    assert U.shape[1] == k and S.shape == (k,) and E.shape == (k,)
+    assert open(prefix + ".sigvals").readline().startswith("#")
+    np.testing.assert_allclose(E, S ** 2 / M, rtol=2e-5)
+    return U, S, V
+
+
+def _check(prefix, k, N, M, Ur, Sr, Vr, perm):
+    U, S, V = _load(prefix, k, M)
+    assert U.shape[0] == N
+    assert np.max(np.abs(S - Sr) / Sr) < 1e-5, (S, Sr)
+    assert col_cos(U, Ur).min() > 0.9999, col_cos(U, Ur)
+    if V is not None:
+        Vo = Vr
+        if perm is not None:  # the reference's V is in permuted order; .loadings are un-permuted
+            Vo = np.zeros_like(Vr)
+            Vo[perm] = Vr
+        assert V.shape == Vo.shape
+        assert col_cos(V, Vo).min() > 0.9999, col_cos(V, Vo)
+    first = open(prefix + ".eigvecs2").readline().split()
+    assert first[:3] == ["#FID", "IID", "PC1"] and len(first) == 2 + k
+    assert sum(1 for _ in open(prefix + ".eigvecs2")) == N + 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("svd,extra", [(1, []), (2, ["-S"]), (2, []), (1, ["--precision", "fp64"])])
+def test_cli_incore_vs_reference(tmp_path, svd, extra):
+    N, M, k, maxp = 600, 9000, 5, 6
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=7, seed=31)
+    ref_extra = " ".join(e for e in extra if e == "-S")
+    Ur, Sr, Vr, perm = _ref(f"PCAone -b {prefix} -k {k} -d {svd} -o {tmp_path}/r --maxp {maxp} --tol-rsvd 0 -n 8 {ref_extra}", maxp)
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "-k", k, "-d", svd, "-o", out, "--maxp", maxp, "--tol-rsvd", 0, "-V"] + extra)
+    _check(out, k, N, M, Ur, Sr, Vr, perm)
+    mb = [l.split() for l in open(out + ".mbim")]
+    assert len(mb) == M and len(mb[0]) == 7
+    # the 7th column is the allele frequency of the ORIGINAL SNP order
+    codes = synth.unpack_codes(synth.read_bed(prefix)[0], N)
+    g = np.array([1.0, np.nan, 0.5, 0.0])[codes[:50]]
+    np.testing.assert_allclose([float(x[6]) for x in mb[:50]], np.nanmean(g, axis=1), rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("svd", [1, 2])
+def test_cli_out_of_core_vs_reference(tmp_path, svd):
+    N, M, k, maxp, mem = 400, 30000, 4, 7, 0.02
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=6, seed=32)
+    # the reference permutes on disk (<out>.perm.bed); the GPU host applies the same map at read time
+    Ur, Sr, Vr, perm = _ref(f"PCAone -b {prefix} -k {k} -d {svd} -m {mem} -o {tmp_path}/r --maxp {maxp} --tol-rsvd 0 -n 8 -w 16", maxp)
+    out = str(tmp_path / "o")
+    r = _run(["-b", prefix, "-k", k, "-d", svd, "-m", mem, "-o", out, "--maxp", maxp, "--tol-rsvd", 0, "-V", "-w", 16])
+    assert "blocksize" in r.stdout
+    _check(out, k, N, M, Ur, Sr, Vr, perm)
+    assert not os.path.exists(out + ".perm.bed")
+
+
+@pytest.mark.gpu
+def test_cli_emu_vs_reference(tmp_path):
+    N, M, k = 500, 6000, 3
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=5, seed=33, miss=0.08)
+    Ur, Sr, Vr, perm = _ref(f"PCAone -b {prefix} -k {k} -d 1 --emu -o {tmp_path}/r -n 8", 20, em=True)
+    out = str(tmp_path / "o")
+    r = _run(["-b", prefix, "-k", k, "-d", 1, "--emu", "-o", out, "-V"])
+    assert "missingness" in r.stdout
+    U, S, V = _load(out, k, M)
+    assert np.max(np.abs(S - Sr) / Sr) < 1e-4
+    assert col_cos(U, Ur).min() > 0.9999
+
+
+@pytest.mark.gpu
+def test_cli_print_r2_vs_reference(tmp_path):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M = 300, 1500
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=4, seed=34)
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "--print-r2", "--ld-bp", 3000, "-o", out])
+    lines = gzip.open(out + ".ld.gz", "rt").read().splitlines()
+    assert lines[0].split("\t") == ["CHR_A", "BP_A", "SNP_A", "CHR_B", "BP_B", "SNP_B", "R2"]
+    r2 = np.array([float(l.split("\t")[6]) for l in lines[1:]])
+    # reference: in-core bed, centred genotypes, ld_r2_big windows from the same .bim
+    r = ref.Ref(f"PCAone -b {prefix} -k 2 -d 1 -o {tmp_path}/r -n 4", threads=4)
+    want, ws, we = r.ld_r2(prefix + ".bim", 3000)
+    r.close()
+    assert r2.shape == want.shape
+    assert np.abs(r2 - want).max() < 2e-6  # std::to_string keeps 6 decimals
