@@ -57,40 +57,68 @@ __host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
 // T = R^-1 from the Cholesky factor, or V diag(lam^-1/2) when the pivot test fails.
 // Executed by ONE CTA; `Ws` is l*l doubles of shared memory.
 // The result is left in shared memory Ts ([l][lc], zero padded) AND written to global T.
+template <int R>
 __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, double* __restrict__ T,
                                    double* __restrict__ Ws, double* __restrict__ Ts, int lc,
                                    double* __restrict__ jscratch, int* status) {
-  __shared__ double s_piv, s_maxd;
+  // Right-looking Cholesky W = R^T R with the matrix held in REGISTERS: thread (ty, tx) of the
+  // 16 x 16 CTA owns the elements (ty + 16 i, tx + 16 j). Per column: the owners of row j publish
+  // it to a double-buffered shared row, ONE __syncthreads, then every thread updates its own
+  // elements. (The first version kept W in shared memory: 3 barriers and two integer divisions
+  // per column made this single-CTA phase 47 us of a 190 us Omega update.)
+  __shared__ double s_row[2][16 * R];
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < l * l; i += nt) Ws[i] = W[(i / l) * ld + (i % l)];
-  if (tid == 0) {
-    s_fail = 0;
-    double m = 0.0;
-    for (int i = 0; i < l; ++i) m = fmax(m, W[i * ld + i]);
-    s_maxd = m;
-  }
+  const int tx = tid & 15, ty = tid >> 4;
+  double a[R][R];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      a[i][j] = (r < l && c < l) ? W[r * ld + c] : 0.0;
+      if (r == c && r < l) s_row[0][r] = a[i][j];
+    }
+  if (tid == 0) s_fail = 0;
   __syncthreads();
-  const double tol = 64.0 * l * 2.220446049250313e-16 * s_maxd;
+  double maxd = 0.0;
+  for (int i = 0; i < l; ++i) maxd = fmax(maxd, s_row[0][i]);
+  __syncthreads();
+  const double tol = 64.0 * l * 2.220446049250313e-16 * maxd;
+  bool fail = false;
   for (int j = 0; j < l; ++j) {
-    if (tid == 0) {
-      const double d = Ws[j * l + j];
-      if (!(d > tol)) s_fail = 1;
-      s_piv = sqrt(d > tol ? d : 1.0);
-      Ws[j * l + j] = s_piv;
+    const int b = j & 1, jt = j >> 4;
+    if (ty == (j & 15)) {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (i == jt) {
+#pragma unroll
+          for (int jj = 0; jj < R; ++jj) s_row[b][tx + 16 * jj] = a[i][jj];
+        }
     }
     __syncthreads();
-    if (s_fail) break;
-    const double inv = 1.0 / s_piv;
-    for (int c = j + 1 + tid; c < l; c += nt) Ws[j * l + c] *= inv;
-    __syncthreads();
-    const int m = l - j - 1;
-    for (int idx = tid; idx < m * m; idx += nt) {
-      const int r = j + 1 + idx / m, c = j + 1 + idx % m;
-      if (c >= r) Ws[r * l + c] -= Ws[j * l + r] * Ws[j * l + c];
+    const double d = s_row[b][j];
+    if (!(d > tol)) {  // uniform: every thread reads the same pivot
+      fail = true;
+      break;
     }
-    __syncthreads();
+    const double invd = 1.0 / d;
+    if (tid < l) Ws[j * l + tid] = tid >= j ? s_row[b][tid] * (1.0 / sqrt(d)) : 0.0;  // row j of R
+    double rr[R], rc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) rr[i] = s_row[b][ty + 16 * i] * invd;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) rc[jj] = s_row[b][tx + 16 * jj];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const int r = ty + 16 * i, c = tx + 16 * jj;
+        if (r > j && c >= r) a[i][jj] -= rr[i] * rc[jj];
+      }
   }
+  if (fail && tid == 0) s_fail = 1;
+  __syncthreads();
   for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
   __syncthreads();
   if (!s_fail) {
@@ -368,7 +396,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   grid.sync();
   stamp();
   // ---------------- P3: T1
-  if (blockIdx.x == 0) orth_factor(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
+  if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
   __threadfence();
   stamp();
   grid.sync();
@@ -404,7 +432,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   stamp();
   // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
   if (blockIdx.x == 0) {
-    orth_factor(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
+    orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
     if (a.Ttot) {
       for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
         const int r = idx / lp, c = idx - r * lp;
@@ -440,23 +468,52 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       }
       (void)r1_save;
       __syncthreads();
-      // sign-modified LU replay of the Householder sign decisions (see k_householder_signs)
-      __shared__ double s_piv2;
-      for (int i = 0; i < l; ++i) {
-        if (tid == 0) {
-          const double c0 = Ws[i * l + i];
-          const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
-          a.hsign[i] = beta;
-          s_piv2 = c0 - beta;
+      // sign-modified LU replay of the Householder sign decisions (see k_householder_signs), with
+      // the l x l block in registers: per step the owners publish row i and column i, one barrier
+      __shared__ double s_lr[2][16 * R], s_lc[2][16 * R];
+      double w[R][R];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = ty + 16 * i, c = tx + 16 * j;
+          w[i][j] = (r < l && c < l) ? Ws[r * l + c] : 0.0;
+        }
+      for (int i0 = 0; i0 < l; ++i0) {
+        const int b = i0 & 1, it = i0 >> 4;
+        if (ty == (i0 & 15)) {
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+            if (i == it) {
+#pragma unroll
+              for (int j = 0; j < R; ++j) s_lr[b][tx + 16 * j] = w[i][j];
+            }
+        }
+        if (tx == (i0 & 15)) {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (j == it) {
+#pragma unroll
+              for (int i = 0; i < R; ++i) s_lc[b][ty + 16 * i] = w[i][j];
+            }
         }
         __syncthreads();
-        const double inv = 1.0 / s_piv2;
-        const int m = l - i - 1;
-        for (int idx = tid; idx < m * m; idx += kOrthThreads) {
-          const int r = i + 1 + idx / m, c = i + 1 + idx % m;
-          Ws[r * l + c] -= Ws[r * l + i] * Ws[i * l + c] * inv;
-        }
-        __syncthreads();
+        const double c0 = s_lr[b][i0];
+        const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
+        if (tid == 0) a.hsign[i0] = beta;
+        const double inv = 1.0 / (c0 - beta);
+        double cr[R], rc[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) cr[i] = s_lc[b][ty + 16 * i] * inv;
+#pragma unroll
+        for (int j = 0; j < R; ++j) rc[j] = s_lr[b][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            if (r > i0 && c > i0) w[i][j] -= cr[i] * rc[j];
+          }
       }
     } else {
       for (int c = tid; c < l; c += kOrthThreads) a.hsign[c] = 1.0;

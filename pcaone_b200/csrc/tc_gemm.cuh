@@ -36,14 +36,17 @@ constexpr int kKB = 64;        // contraction entries per k-block = one 16-byte 
 constexpr int kStageKB = 2;    // k-blocks per pipeline stage (128 contraction entries = 4 UMMAs per row tile)
 constexpr int kNS = 4;         // pipeline stages: A ring in TMEM + B ring in shared memory
 constexpr int kAcol0 = 256;    // first TMEM column of the A ring (accumulators use [0,256))
-constexpr int kPF = 4;         // stages of packed loads in flight per decode thread (2 x 16 B each)
+constexpr int kDG = 2;         // decode groups: group g owns the pipeline stages with (stage counter & 1) == g
+constexpr int kPF = 4;         // own stages of packed loads in flight per decode thread (cp.async ring; x kDG stages of lookahead)
 constexpr int kMaxNP = 256;
 constexpr uint32_t kChunkBytes = kRowTile * 16;  // one (row tile, k-block) chunk of the tiled operand
 
-__host__ __device__ constexpr int tc_threads(int RT) { return 128 + 128 * RT; }
-__host__ __device__ constexpr size_t tc_scratch_bytes(int RT) { return (size_t)4 * RT * 32 * 17 * 8; }
+__host__ __device__ constexpr int tc_threads(int RT) { return 128 + kDG * 128 * RT; }
+__host__ __device__ constexpr size_t tc_scratch_bytes(int RT) { return (size_t)kDG * 4 * RT * 32 * 17 * 8; }
+// packed-operand ring: every decode thread owns kPF slots of kStageKB x 16 bytes
+__host__ __device__ constexpr size_t tc_ring_bytes(int RT) { return (size_t)kPF * kStageKB * kDG * 128 * RT * 16; }
 __host__ __device__ inline size_t tc_smem_bytes(int RT, int NP) {
-  return (size_t)kNS * kStageKB * kKB * NP + tc_scratch_bytes(RT);
+  return (size_t)kNS * kStageKB * kKB * NP + tc_scratch_bytes(RT) + tc_ring_bytes(RT);
 }
 
 // position inside a k-block at which the decode puts source entry g (see decode64)
@@ -121,8 +124,17 @@ __device__ __forceinline__ void umma_i8_ts_x4(uint32_t d_tmem, uint32_t a_tmem, 
 // Pipeline (one CTA per SM, persistent over work items = (row-tile group, K split)):
 //   warp 0      B producer   : bulk-copies one stage (128 x NP int8) of the slice image into smem
 //   warp 1      UMMA issuer  : per stage 4 UMMAs per row tile, then ONE tcgen05.commit frees the stage
-//   warps 4..   decode warps : 4 per row tile (one per TMEM lane quadrant); each thread owns one
-//                              output row: 2 x 16-byte packed loads -> 128 int8 -> tcgen05.st
+//   warps 4..   decode warps : kDG groups of 4 per row tile (one per TMEM lane quadrant); each thread
+//                              owns one output row: 2 x 16-byte packed loads -> 128 int8 -> tcgen05.st.
+//                              The groups take alternate stages: one stage costs a decode warp a
+//                              SERIAL chain of ~900 cycles (barrier wait, tcgen05 fences, st + wait::st,
+//                              arrive: ~600 cycles measured with the decode and the UMMAs compiled
+//                              out, plus ~300 of decode) against 550 cycles of UMMA work, so a single
+//                              group paced the kernel at 57-65 % tensor-pipe utilisation (ncu).
+//                              The packed bytes arrive through a per-thread cp.async ring in shared
+//                              memory, kPF stages (~3 us of tensor work) ahead of the decode, so the
+//                              HBM latency never reaches the decode warps (round-1 ncu: the single
+//                              largest stall was the scoreboard wait on a 4-deep register ring)
 //   full[s]  : 4*RT decode-warp arrivals + the B producer's expect_tx arrival + the copied bytes
 //   empty[s] : the issuer's tcgen05.commit
 // After the last stage of an item the decode warps drain the s32 accumulators (epilogue).
@@ -145,7 +157,7 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
       mbar_init(&empty[i], 1);
     }
     mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 4 * RT);
+    mbar_init(&acc_empty, kDG * 4 * RT);
     mbar_fence_init();
   }
   tc_fence_before();
@@ -155,7 +167,6 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
 
   const uint32_t n_rtp = (a.nrt + RT - 1) / RT;
   const uint32_t n_items = n_rtp * a.nsplit;
-
   if (warp == 0) {
     // ------------------------------------------------ B producer
     if (lane == 0) {
@@ -175,42 +186,54 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
     }
   } else if (warp == 1) {
     // ------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = idesc_i8(kRowTile, (int)a.NP);
-      const uint32_t lbo = (a.NP >> 3) * 128, sbo = 128;
-      const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(Bs), lbo, sbo);
-      const uint64_t dk = (uint64_t)((2 * lbo) >> 4);         // one K step (32 entries)
-      const uint64_t dstage = (uint64_t)(stage_bytes >> 4);   // one stage
-      uint32_t sit = 0, n = 0;
-      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-        const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
-        const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
-        const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
-        const uint32_t ntile = min((uint32_t)RT, a.nrt - rtp * RT);
-        mbar_wait(&acc_empty, (n & 1) ^ 1);
+    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow
+    // the descriptor / TMEM-address arithmetic stays on the uniform datapath. (Issued from a
+    // single divergent lane the loop was ~90 SASS instructions per stage, most of them R2UR
+    // moves feeding UTCIMMA, and that one thread paced the tensor pipe.)
+    const uint32_t idesc = idesc_i8(kRowTile, (int)a.NP);
+    const uint32_t lbo = (a.NP >> 3) * 128, sbo = 128;
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(Bs), lbo, sbo);
+    const uint64_t dk = (uint64_t)((2 * lbo) >> 4);         // one K step (32 entries)
+    const uint64_t dstage = (uint64_t)(stage_bytes >> 4);   // one stage
+    uint32_t sit = 0, n = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
+      const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
+      const uint32_t kb_end = min(a.kb0 + a.nkb, kb_begin + a.kb_per_split);
+      const uint32_t nst = (kb_end - kb_begin + kStageKB - 1) / kStageKB;
+      const bool two = RT > 1 && (a.nrt - rtp * RT) > 1;
+      mbar_wait(&acc_empty, (n & 1) ^ 1);
+      tc_fence_after();
+      uint32_t accflag = 0;
+#pragma unroll 1
+      for (uint32_t st = 0; st < nst; ++st, ++sit) {
+        const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        uint32_t accflag = 0;
-        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB, ++sit) {
-          const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint64_t bd = desc0 + s * dstage;
           const uint32_t at = tbase + kAcol0 + s * (RT * 32);
           umma_i8_ts_x4(tbase, at, bd, idesc, accflag, dk);
-          if (RT > 1 && ntile > 1) umma_i8_ts_x4(tbase + a.NP, at + 32, bd, idesc, accflag, dk);
+          if (two) umma_i8_ts_x4(tbase + a.NP, at + 32, bd, idesc, accflag, dk);
           umma_commit(&empty[s]);
-          accflag = 1;
         }
-        umma_commit(&acc_full);
+        __syncwarp();
+        accflag = 1;
       }
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ decode warps (A producer) + epilogue
-    const int t = (warp - 4) >> 2, q = warp & 3;
+    const int dw = warp - 4;
+    const int g = dw / (4 * RT);  // decode group
+    const int t = (dw % (4 * RT)) >> 2, q = warp & 3;
     const uint32_t rloc = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    long long* my_scratch = scratch + (size_t)(warp - 4) * 32 * 17;
-    uint32_t sit = 0, n = 0;
+    long long* my_scratch = scratch + (size_t)dw * 32 * 17;
+    const uint32_t ring_hstride = kDG * 128 * RT * 16;
+    const uint32_t ring0 = smem_u32(smem + (size_t)kNS * stage_bytes + tc_scratch_bytes(RT)) + (threadIdx.x - 128) * 16;
+    uint32_t sit0 = 0, n = 0;  // sit0: stage counter at the start of the item (all groups count every stage)
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const uint32_t sp = item / n_rtp, rtp = item - sp * n_rtp;
       const uint32_t kb_begin = a.kb0 + sp * a.kb_per_split;
@@ -218,53 +241,72 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
       const uint32_t ntile = min((uint32_t)RT, a.nrt - rtp * RT);
       const bool active = (uint32_t)t < ntile;
       const uint32_t rt = a.rt0 + rtp * RT + t;
+      const uint32_t nst = (kb_end - kb_begin + kStageKB - 1) / kStageKB;
+      const uint32_t first = ((sit0 & 1u) == (uint32_t)g) ? 0u : 1u;  // my first stage of this item
       if (active) {
         const uint8_t* p = a.PA + (uint64_t)rt * a.stride_rt + (uint64_t)rloc * 16;
-        // register ring: kPF stages (2 packed loads each) in flight per thread. Loads are
-        // unconditional (clamped) so that every ring slot keeps its own registers.
-        uint4 buf[kPF][kStageKB];
-#pragma unroll
-        for (int j = 0; j < kPF; ++j)
-#pragma unroll
-          for (int h = 0; h < kStageKB; ++h)
-            buf[j][h] = ldg_stream16(p + (uint64_t)min(kb_begin + kStageKB * j + h, a.kb_valid_last) * a.stride_kb);
-        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB * kPF) {
-#pragma unroll
-          for (int j = 0; j < kPF; ++j) {
-            const uint32_t kbj = kb + kStageKB * j;
-            uint32_t o[32];
-            decode64(buf[j][0], o);
-            decode64(buf[j][1], o + 16);
+        // cp.async ring: slot i of this thread = ring0 + (i * kStageKB + h) * ring_hstride.
+        // One commit group per own stage, committed even when the stage is past the item's end (an
+        // empty group), so that wait_group<kPF-1> always means "my oldest stage has landed".
+        auto issue = [&](uint32_t st, uint32_t slot) {
+          if (st < nst) {
 #pragma unroll
             for (int h = 0; h < kStageKB; ++h)
-              buf[j][h] = ldg_stream16(p + (uint64_t)min(kbj + kStageKB * kPF + h, a.kb_valid_last) * a.stride_kb);
-            if (kbj < kb_end) {
-              const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
-              mbar_wait(&empty[s], ph ^ 1);
-              tc_fence_after();
-              tmem_st32(tbase + lane_addr + kAcol0 + s * (RT * 32) + t * 32, o);
-              tmem_wait_st();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&full[s]);
-              ++sit;
-            }
+              cp_async16(ring0 + (slot * kStageKB + h) * ring_hstride,
+                         p + (uint64_t)min(kb_begin + kStageKB * st + h, a.kb_valid_last) * a.stride_kb);
           }
+          cp_async_commit();
+        };
+#pragma unroll 1
+        for (uint32_t j = 0; j < (uint32_t)kPF; ++j) issue(first + kDG * j, j);
+        uint32_t slot = 0;
+        bool st_pending = false;
+        uint32_t pend_s = 0;
+        // the arrival for a stage is deferred until my next stage has been decoded, so the
+        // tcgen05.st latency overlaps that decode instead of stalling the warp
+        auto publish = [&]() {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[pend_s]);
+        };
+#pragma unroll 1
+        for (uint32_t st = first; st < nst; st += kDG) {
+          cp_async_wait<kPF - 1>();
+          const uint4 q0 = lds128(ring0 + (slot * kStageKB + 0) * ring_hstride);
+          const uint4 q1 = lds128(ring0 + (slot * kStageKB + 1) * ring_hstride);
+          uint32_t o[32];
+          decode64(q0, o);
+          decode64(q1, o + 16);
+          issue(st + kDG * kPF, slot);  // refill the slot just consumed (its bytes are in registers)
+          slot = (slot + 1 == (uint32_t)kPF) ? 0 : slot + 1;
+          if (st_pending) publish();
+          const uint32_t sit = sit0 + st;
+          const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          tc_fence_after();
+          tmem_st32(tbase + lane_addr + kAcol0 + s * (RT * 32) + t * 32, o);
+          st_pending = true;
+          pend_s = s;
         }
+        if (st_pending) publish();
+        cp_async_wait<0>();  // only empty groups can be pending here
       } else {
         // idle tile of a ragged last group: keep the stage barriers in step
-        for (uint32_t kb = kb_begin; kb < kb_end; kb += kStageKB, ++sit) {
+        for (uint32_t st = first; st < nst; st += kDG) {
+          const uint32_t sit = sit0 + st;
           const uint32_t s = sit % kNS, ph = (sit / kNS) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[s]);
         }
       }
+      sit0 += nst;
       // ---- epilogue: s32 slice sums -> one int64 per (row, column) -> integer atomics
       mbar_wait(&acc_full, n & 1);
       tc_fence_after();
       const long long row0 = (long long)rt * kRowTile + q * 32;  // first row of this warp
-      for (uint32_t c0 = 0; c0 < a.l; c0 += 16) {
+      for (uint32_t c0 = 16 * g; c0 < a.l; c0 += 16 * kDG) {  // the groups take alternate 16-column blocks
         if (active) {
           uint32_t v[S][16];
 #pragma unroll
