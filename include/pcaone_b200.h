@@ -168,6 +168,7 @@ typedef struct pcaone_timers {
   double tc_g_ms, tc_h_ms;         /* k_tc_gemm alone (inside gemm_g_ms / gemm_h_ms), G pass / H pass */
   double ld_ms;                    /* k_ld_tiles (pcaone_ld_r2) */
   uint64_t ld_tiles, ld_pairs;     /* 128 x 128 Gram tiles computed / r2 values produced */
+  uint64_t tc_miss_ranges;         /* of tc_ranges: ranges with missing calls (count + mask GEMM pairs) */
 } pcaone_timers;
 int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
 int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */

@@ -103,13 +103,17 @@ struct pcaone_ctx {
   int8_t *d_BimgO = nullptr, *d_BimgW = nullptr;       // B operand images: Omega, W = s o G of the current range
   size_t bimgW_kb = 0;
   long long* d_Racc = nullptr;                         // int64 accumulators
+  long long* d_Racc2 = nullptr;                        // int64 accumulators of the missing-mask products
+  int8_t* d_BimgD = nullptr;                           // B image of D = (f - 1) o W (mask operand of the H pass)
+  size_t R2_rows = 0, bimgD_kb = 0;
   size_t R_rows = 0;
   unsigned long long* d_tcs = nullptr;                 // [5][lp]: Omega colmax, Omega Csum, W colmax, W Csum, Fw
   double* d_Fpart = nullptr;
   bool omega_img_valid = false;
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
   std::vector<uint64_t> nmiss_prefix;
-  uint64_t tc_ranges = 0, fp64_ranges = 0;
+  uint64_t tc_ranges = 0, fp64_ranges = 0, tc_miss_ranges = 0;
+  bool g_is_q = false;                                 // d_G holds Q = G T after small_stage (else raw G)
   double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
   int fused_orth = 1;                                  // PCAONE_FUSED_ORTH=0 selects the multi-kernel path
 
@@ -319,7 +323,7 @@ void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG,
   c->tm.kernel_launches += 2;
 }
 
-void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
+void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows, bool miss) {
   if (!c->d_tcs) {
     dmalloc(&c->d_tcs, (size_t)5 * c->lp);
     PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)5 * c->lp * sizeof(unsigned long long), c->stream));
@@ -333,6 +337,17 @@ void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows) {
     c->R_rows = need_rows;
   }
   const size_t need_kb = max_range_rows / tc::kKB + 4;
+  if (miss && need_rows > c->R2_rows) {
+    if (c->d_Racc2) cudaFree(c->d_Racc2);
+    dmalloc(&c->d_Racc2, need_rows * c->lp);
+    PCA_CUDA(cudaMemsetAsync(c->d_Racc2, 0, need_rows * c->lp * sizeof(long long), c->stream));
+    c->R2_rows = need_rows;
+  }
+  if (miss && need_kb > c->bimgD_kb) {
+    if (c->d_BimgD) cudaFree(c->d_BimgD);
+    dmalloc(&c->d_BimgD, need_kb * tc::kKB * c->NP);
+    c->bimgD_kb = need_kb;
+  }
   if (need_kb > c->bimgW_kb) {
     if (c->d_BimgW) cudaFree(c->d_BimgW);
     if (c->d_Fpart) cudaFree(c->d_Fpart);
@@ -367,20 +382,21 @@ void tc_fetch_nmiss(pcaone_ctx* c, uint64_t s, uint64_t n) {
   }
 }
 
-template <int S, int RT>
+template <int S, int RT, int MODE>
 void tc_launch_st(pcaone_ctx* c, const tc::TcGemmArgs& a, int grid) {
   const size_t smem = tc::tc_smem_bytes(RT, c->NP);
   static size_t attr = 0;
   if (smem > attr) {
-    PCA_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<S, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCA_CUDA(cudaFuncSetAttribute(tc::k_tc_gemm<S, RT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  tc::k_tc_gemm<S, RT><<<grid, tc::tc_threads(RT), smem, c->stream>>>(a);
+  tc::k_tc_gemm<S, RT, MODE><<<grid, tc::tc_threads(RT), smem, c->stream>>>(a);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
 }
 
-void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a) {
+// mode: tc::kPlain / kNonMiss / kMask (what the packed operand decodes to); R: int64 accumulators
+void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a, int mode, long long* R) {
   // split-K so that (row-tile groups x splits) fills the SMs in whole waves
   const uint32_t n_rtp = (a.nrt + c->RT - 1) / c->RT;
   const uint32_t epi_cost = 24;  // epilogue + pipeline fill, in k-block units
@@ -403,16 +419,21 @@ void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a) {
   a.NP = c->NP;
   a.l = c->l;
   a.lp = c->lp;
-  a.R = c->d_Racc;
-#define TC_CASE(S_, RT_) \
-  if (c->slices == S_ && c->RT == RT_) { tc_launch_st<S_, RT_>(c, a, grid); return; }
+  a.R = R;
+#define TC_CASE(S_, RT_)                                                                        \
+  if (c->slices == S_ && c->RT == RT_) {                                                        \
+    if (mode == tc::kPlain) tc_launch_st<S_, RT_, tc::kPlain>(c, a, grid);                      \
+    else if (mode == tc::kNonMiss) tc_launch_st<S_, RT_, tc::kNonMiss>(c, a, grid);             \
+    else tc_launch_st<S_, RT_, tc::kMask>(c, a, grid);                                          \
+    return;                                                                                     \
+  }
   TC_CASE(2, 1) TC_CASE(2, 2) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(4, 1) TC_CASE(4, 2)
 #undef TC_CASE
   throw std::runtime_error("tc_gemm: unsupported slice count");
 }
 
 void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned long long* colmax, const double* F,
-              int writeback, int8_t* Bimg, long long* Csum, double* Fpart, uint32_t* nkb_out) {
+              int writeback, int8_t* Bimg, long long* Csum, double* Fpart, uint32_t* nkb_out, int dmode = 0) {
   tc::TcSliceArgs a{};
   a.X = X;
   a.lp = c->lp;
@@ -426,6 +447,7 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
   a.F = F;
   a.lut = c->lut;
   a.writeback = writeback;
+  a.dmode = dmode;
   a.Bimg = Bimg;
   a.Csum = Csum;
   a.Fpart = Fpart;
@@ -440,8 +462,10 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
 
 // tensor-core version of range_gemms. PG/PH: tiled operands in which the range starts at local
 // row / contraction index `loc0`; snp0 = first SNP of the range in d_G / d_F.
+// `miss`: the range contains missing calls -> every product is run as (non-missing counts, mask) pair.
 void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0,
-                    double* Hacc, bool accumulate) {
+                    double* Hacc, bool accumulate, bool miss) {
+  const int mode = miss ? tc::kNonMiss : tc::kPlain;
   unsigned long long* o_colmax = c->d_tcs;
   long long* o_csum = reinterpret_cast<long long*>(c->d_tcs + c->lp);
   unsigned long long* w_colmax = c->d_tcs + 2 * c->lp;
@@ -473,12 +497,14 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     a.row_r0 = (long long)a.rt0 * tc::kRowTile;
     {
       Timed tk(c, 7);
-      tc_launch(c, a);
+      tc_launch(c, a, mode, c->d_Racc);
+      if (miss) tc_launch(c, a, tc::kMask, c->d_Racc2);
     }
-    long long* Rrow = c->d_Racc + (loc0 - (uint64_t)a.row_r0) * c->lp;
+    const uint64_t roff = (loc0 - (uint64_t)a.row_r0) * c->lp;
     tc::k_tc_finish_g<<<(unsigned)std::min<uint64_t>((nrows + tc::kKB - 1) / tc::kKB, (uint64_t)c->sms * 8),
                         tc::tc_pair_threads(c->lp), 0, c->stream>>>(
-        Rrow, nrows, c->l, c->lp, c->slices, c->d_F + snp0, c->lut, o_csum, o_colmax, c->d_G + snp0 * c->lp, w_colmax);
+        c->d_Racc + roff, miss ? c->d_Racc2 + roff : nullptr, nrows, c->l, c->lp, c->slices, c->d_F + snp0, c->lut, o_csum,
+        o_colmax, c->d_G + snp0 * c->lp, w_colmax);
     PCA_CHECK_LAUNCH();
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
@@ -490,6 +516,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     double* X0 = c->d_G + snp0 * c->lp - loc0 * c->lp;
     const double* F0 = c->d_F + snp0 - loc0;
     tc_slice(c, X0, loc0, loc0 + nrows, w_colmax, F0, 1, c->d_BimgW, w_csum, c->d_Fpart, &nkb_w);
+    if (miss) tc_slice(c, X0, loc0, loc0 + nrows, w_colmax, F0, 0, c->d_BimgD, nullptr, nullptr, nullptr, 1);
     tc::TcGemmArgs a{};
     a.PA = PH;
     a.stride_rt = tc::kChunkBytes;
@@ -505,19 +532,25 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     a.row_r0 = 0;
     {
       Timed tk(c, 8);
-      tc_launch(c, a);
+      tc_launch(c, a, mode, c->d_Racc);
+      if (miss) {
+        a.Bimg = c->d_BimgD;
+        tc_launch(c, a, tc::kMask, c->d_Racc2);
+      }
     }
     double* Fw = reinterpret_cast<double*>(c->d_tcs + 4 * c->lp);
     tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
     PCA_CHECK_LAUNCH();
     tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
-        c->d_Racc, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw, Hacc, accumulate ? 1 : 0);
+        c->d_Racc, miss ? c->d_Racc2 : nullptr, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw, Hacc,
+        accumulate ? 1 : 0);
     PCA_CHECK_LAUNCH();
     c->tm.kernel_launches++;
     c->tm.gemm_h_launches++;
     c->tm.kernel_launches++;
   }
   c->tc_ranges++;
+  if (miss) c->tc_miss_ranges++;
 }
 
 // G rows of the range = X^T Omega ; Hacc (+)= X G. `buf` = streamed block buffer holding P, or -1
@@ -526,21 +559,23 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
 void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate,
                  int buf) {
   if (nrows == 0) return;
-  bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu);
+  // EMU update passes fill every missing entry with its own FP64 value: FP64 kernels
+  const bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu);
+  bool has_miss = false;
   if (use_tc) {
     uint64_t miss = tc_missing_in(c, snp0, nrows);
     if (miss == UINT64_MAX) {
       tc_fetch_nmiss(c, snp0, nrows);
       miss = tc_missing_in(c, snp0, nrows);
     }
-    use_tc = miss == 0;
+    has_miss = miss != 0;
   }
   if (!use_tc) {
     range_gemms_fp64(c, P, nrows, snp0, Hacc, accumulate);
     c->fp64_ranges++;
     return;
   }
-  tc_alloc(c, std::max<uint64_t>(nrows, c->max_block));
+  tc_alloc(c, std::max<uint64_t>(nrows, c->max_block), has_miss);
   if (buf < 0) {
     if (!c->tiles_valid) {
       if (!c->d_PG) {
@@ -550,14 +585,14 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
       tc_build_tiles(c, c->d_packed, c->M, c->d_PG, c->d_PH, c->stream);
       c->tiles_valid = true;
     }
-    range_gemms_tc(c, c->d_PG, c->d_PH, snp0, nrows, snp0, Hacc, accumulate);
+    range_gemms_tc(c, c->d_PG, c->d_PH, snp0, nrows, snp0, Hacc, accumulate, has_miss);
   } else {
     if (!c->d_PGb[buf]) {
       PCA_CUDA(cudaMalloc((void**)&c->d_PGb[buf], tc_pg_bytes(c, c->max_block)));
       PCA_CUDA(cudaMalloc((void**)&c->d_PHb[buf], tc_ph_bytes(c, c->max_block)));
     }
     tc_build_tiles(c, P, nrows, c->d_PGb[buf], c->d_PHb[buf], c->stream);
-    range_gemms_tc(c, c->d_PGb[buf], c->d_PHb[buf], 0, nrows, snp0, Hacc, accumulate);
+    range_gemms_tc(c, c->d_PGb[buf], c->d_PHb[buf], 0, nrows, snp0, Hacc, accumulate, has_miss);
   }
 }
 
@@ -741,10 +776,12 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
 }
 
 // Q = orth(A) in two passes (CholeskyQR2); Q may alias A. Ttot (optional) = T1*T2, Q = A*Ttot.
-void orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Ttot, bool sharded_rows) {
+// Q == nullptr: only Ttot is wanted (the caller applies it later); returns false if Q was not formed.
+bool orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Ttot, bool sharded_rows,
+           bool factors_only = false) {
   if (orth_fused_ok(c) && !(sharded_rows && c->cfg.world > 1)) {
-    orth_fused(c, A, rows, Q, nullptr, Ttot, false, false);
-    return;
+    orth_fused(c, A, rows, factors_only ? nullptr : Q, nullptr, Ttot, false, false);
+    return !factors_only;
   }
   ts_gemm_tn(c, A, c->l, A, c->l, rows, c->d_W, sharded_rows);
   gram_factor(c, c->d_W, c->d_T1);
@@ -753,6 +790,7 @@ void orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Tto
   gram_factor(c, c->d_W, c->d_T2);
   ts_rightmult(c, Q, c->l, c->d_T2, c->l, rows, Q);
   if (Ttot) small_matmul(c, c->d_T1, 0, c->d_T2, 0, c->l, c->l, c->l, Ttot);
+  return true;
 }
 
 void flip_omg(pcaone_ctx* c, const double* pre) {
@@ -1049,7 +1087,9 @@ void compute_gandh(pcaone_ctx* c, int pi) {
 void small_stage(pcaone_ctx* c) {
   Timed t(c, 3);
   // G = Q R twice (CholeskyQR2); T = R^-1 so that Q = G T and B^T = H R^-1 = H T
-  orth2(c, c->d_G, c->M, c->d_G, c->d_T, true);
+  // Only T is needed per epoch; Q itself enters the result once, as V = Q U_B (Halko.cpp:89), which
+  // finalize_usv forms as G (T U_B): the M x l matrix Q is never written.
+  c->g_is_q = orth2(c, c->d_G, c->M, c->d_G, c->d_T, true, true);
   ts_rightmult(c, c->d_H, c->l, c->d_T, c->l, c->N, c->d_Bt);
   // SVD of B^T (N x l): Gram -> Cholesky -> one-sided Jacobi on the triangular factor
   ts_gemm_tn(c, c->d_Bt, c->l, c->d_Bt, c->l, c->N, c->d_W, false);
@@ -1077,7 +1117,12 @@ double device_mev(pcaone_ctx* c, const double* X, const double* Y, uint64_t rows
 void finalize_usv(pcaone_ctx* c) {
   const uint64_t bytes = c->N * c->lp * sizeof(double);
   PCA_CUDA(cudaMemcpyAsync(c->d_U, c->d_Ucur, bytes, cudaMemcpyDeviceToDevice, c->stream));
-  ts_rightmult(c, c->d_G, c->l, c->d_Vr, c->k, c->M, c->d_V);
+  if (c->g_is_q) {
+    ts_rightmult(c, c->d_G, c->l, c->d_Vr, c->k, c->M, c->d_V);
+  } else {
+    small_matmul(c, c->d_T, 0, c->d_Vr, 0, c->l, c->l, c->k, c->d_Z);
+    ts_rightmult(c, c->d_G, c->l, c->d_Z, c->k, c->M, c->d_V);
+  }
   PCA_CUDA(cudaMemcpyAsync(c->d_S, c->d_sigma, c->k * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   c->have_usv = true;
 }
@@ -1439,7 +1484,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
-                  (void*)c->d_Racc, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
+                  (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -1794,10 +1839,11 @@ int pcaone_get_timers(pcaone_ctx* c, pcaone_timers* out, int reset) {
     resolve_timers(c);
     c->tm.tc_ranges = c->tc_ranges;
     c->tm.fp64_ranges = c->fp64_ranges;
+    c->tm.tc_miss_ranges = c->tc_miss_ranges;
     if (out) *out = c->tm;
     if (reset) {
       c->tm = pcaone_timers{};
-      c->tc_ranges = c->fp64_ranges = 0;
+      c->tc_ranges = c->fp64_ranges = c->tc_miss_ranges = 0;
     }
   });
 }

@@ -30,7 +30,7 @@ __host__ __device__ constexpr int orth_tile_rows(int R) { return R <= 4 ? 64 : 3
 
 struct OrthArgs {
   const double* A;   // [rows][lp] input (H or G); may alias Q
-  double* Q;         // [rows][lp] output
+  double* Q;         // [rows][lp] output; nullptr = factors only (Ttot with Q = A Ttot): phases P7/P8 are skipped
   double* Q2;        // Omega2 for flipOmg (read, then overwritten with the new Omega) or nullptr
   uint64_t rows;
   int l, lp;
@@ -523,6 +523,11 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   stamp();
   grid.sync();
   stamp();
+  if (!a.Q) {  // factors only (uniform across the grid)
+    if (blockIdx.x == 0)
+      for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
+    return;
+  }
   // ---------------- P7: Q = (A T1) T2 o hsign ; partial flip sums
   if (blockIdx.x != 0) load_T(a.T2g, T2s);
   double hs[R];

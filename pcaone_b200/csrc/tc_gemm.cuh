@@ -22,8 +22,12 @@
 //  * centring, scaling by sqrt(ploidy)/sqrt(F(1-F)) and the column-sum (rank-1) terms are applied
 //    in FP64 by the finish kernels below.
 //
-// Missing genotypes (code 01) and the EMU fill are not expressible as u in {0,1,2}: ranges that
-// contain them run on the FP64 DMMA kernels (gemm_fp64.cuh) instead — still on the GPU.
+// Missing genotypes (code 01) are mean-imputed (value 0 after centring). A range that contains
+// them runs every GEMM twice on the same machinery: once with u = 0 at the missing entries and
+// once with the 0/1 missing mask as the packed operand, whose product takes the missing entries
+// out of the centring term (see the finish kernels). The EMU fill (a different FP64 value per
+// missing entry) is not expressible this way: EMU update passes run on the FP64 DMMA kernels
+// (gemm_fp64.cuh) instead — still on the GPU.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -59,13 +63,23 @@ __host__ __device__ __forceinline__ uint32_t bimg_offset(int n, int kp, int NP) 
   return (uint32_t)(((kp >> 4) * (NP >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (kp & 15));
 }
 
-// 64 two-bit codes (one uint4) -> 64 int8 values u = popcount(code), 4 per word.
+// What the A operand holds for a 2-bit code (FilePlink.cpp:39-47; code 01 = missing):
+//   kPlain   u = popcount(code)                   {00,01,10,11} -> {0,1,1,2}  (ranges WITHOUT missing calls)
+//   kNonMiss u = popcount(code), 0 where missing  {00,01,10,11} -> {0,0,1,2}
+//   kMask    1 where missing                      {00,01,10,11} -> {0,1,0,0}
+// A range with missing calls runs the GEMM twice (kNonMiss and kMask): the mask product removes the
+// missing entries from the centring term, i.e. mean imputation (FilePlink.cpp:194-197, lut[01] = 0).
+enum : int { kPlain = 0, kNonMiss = 1, kMask = 2 };
+
+// 64 two-bit codes (one uint4) -> 64 int8 values, 4 per word.
 // Word 4x+w, byte b holds source entry 16x + w + 4b  (=> kpos_of).
+template <int MODE>
 __device__ __forceinline__ void decode64(const uint4& q, uint32_t* o) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
-    const uint32_t t = (w[x] & 0x55555555u) + ((w[x] >> 1) & 0x55555555u);
+    const uint32_t lo = w[x] & 0x55555555u, hi = (w[x] >> 1) & 0x55555555u;
+    const uint32_t t = MODE == kPlain ? lo + hi : MODE == kNonMiss ? hi + (hi & lo) : lo & ~hi;
     o[4 * x + 0] = t & 0x03030303u;
     o[4 * x + 1] = (t >> 2) & 0x03030303u;
     o[4 * x + 2] = (t >> 4) & 0x03030303u;
@@ -138,7 +152,7 @@ __device__ __forceinline__ void umma_i8_ts_x4(uint32_t d_tmem, uint32_t a_tmem, 
 //   full[s]  : 4*RT decode-warp arrivals + the B producer's expect_tx arrival + the copied bytes
 //   empty[s] : the issuer's tcgen05.commit
 // After the last stage of an item the decode warps drain the s32 accumulators (epilogue).
-template <int S, int RT>
+template <int S, int RT, int MODE>
 __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kNS], empty[kNS], acc_full, acc_empty;
@@ -276,8 +290,8 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
           const uint4 q0 = lds128(ring0 + (slot * kStageKB + 0) * ring_hstride);
           const uint4 q1 = lds128(ring0 + (slot * kStageKB + 1) * ring_hstride);
           uint32_t o[32];
-          decode64(q0, o);
-          decode64(q1, o + 16);
+          decode64<MODE>(q0, o);
+          decode64<MODE>(q1, o + 16);
           issue(st + kDG * kPF, slot);  // refill the slot just consumed (its bytes are in registers)
           slot = (slot + 1 == (uint32_t)kPF) ? 0 : slot + 1;
           if (st_pending) publish();
@@ -460,6 +474,7 @@ struct TcSliceArgs {
   const double* F;                    // per-row allele frequency (indexed like X rows) or nullptr
   LutParams lut;
   int writeback;                      // X[row][c] <- X~[row][c] / s_row  (G~ for the QR stage)
+  int dmode;                          // slice D = (f_row - 1) * s_row * X instead (mask operand of the H pass); image only
   int8_t* Bimg;                       // out: [nkb][64*NP]
   long long* Csum;                    // out (atomic): sum_rows I[row][c]
   double* Fpart;                      // out: [gridDim.x][lp] partial sums of f_row * X~[row][c], or nullptr
@@ -511,7 +526,8 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
       const uint64_t row = row0 + g;
       if (row >= a.r0 && row < a.r1) {
         const double sj = s_scale[g];
-        const double x = Xb[g * a.lp + c] * sj;
+        double x = Xb[g * a.lp + c] * sj;
+        if (a.dmode) x *= s_f[g] - 1.0;
         const long long I = llrint(x * up);
         const double xt = (double)I * dn;
         if (a.writeback) Xb[g * a.lp + c] = xt / sj;
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
   __syncthreads();
   for (int i = tid; i < kKB * a.NP / 16; i += B)
     reinterpret_cast<uint4*>(a.Bimg + (size_t)blockIdx.x * kKB * a.NP)[i] = reinterpret_cast<const uint4*>(img)[i];
-  if (g0 == 0 && c < a.l) {
+  if (g0 == 0 && c < a.l && !a.dmode) {
     long long tc_ = 0;
     double tf = 0.0;
     for (int q = 0; q < rpp; ++q) {  // fixed order
@@ -551,13 +567,15 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
 // accesses) and walks rows g0, g0 + rows-per-pass, ...
 __host__ __device__ inline int tc_pair_threads(int lp) { return (lp / 2) * (256 / (lp / 2)); }
 
-// G pass finish: G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * C_c - T[j][c] / 2) written to Gout rows
+// G pass finish: G[j][c] = s_j * 2^(e_c-p) * ((1 - f_j) * (C_c - K[j][c]) - T[j][c] / 2) written to Gout rows;
+// K = R2 = mask product (sum of the Omega~ integers over the samples whose call is missing at SNP j),
+// nullptr for ranges without missing calls. C_c - K is an exact integer below 2^53
 // (the slice kernel turns s o G into the rounded G~ afterwards); also the column abs-max of
 // W = s o G for that slicing. R is re-zeroed. Blocks walk 64-row groups (contiguous 64*lp values);
 // all loads of a group are issued before the first use (the int64 accumulators come back from L2
 // with long latency right after the GEMM's atomics), running maxima stay in registers.
 __global__ void __launch_bounds__(256)
-k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, const double* __restrict__ F,
+k_tc_finish_g(long long* __restrict__ R, long long* __restrict__ R2, uint64_t nrows, int l, int lp, int S, const double* __restrict__ F,
               LutParams lut, const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax_in,
               double* __restrict__ Gout, unsigned long long* __restrict__ colmax_out) {
   constexpr int U = 8;  // row passes per group held in registers (rows-per-pass >= 8 -> 64 rows)
@@ -568,10 +586,12 @@ k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, c
   const int rpp = B / hp;  // rows per pass, >= 8 for lp <= 64, >= 4 for lp <= 128
   const int g0 = tid / hp, c = 2 * (tid - g0 * hp);
   double cs[2] = {0.0, 0.0}, sc[2] = {0.0, 0.0}, m[2] = {0.0, 0.0};
+  long long csi[2] = {0, 0};
 #pragma unroll
   for (int h = 0; h < 2; ++h)
     if (c + h < l) {
-      cs[h] = (double)Csum[c + h];
+      csi[h] = Csum[c + h];
+      cs[h] = (double)csi[h];
       sc[h] = scalbn(1.0, tc_exponent(colmax_in[c + h]) - p);
     }
   for (uint64_t row0 = (uint64_t)blockIdx.x * kKB; row0 < nrows; row0 += (uint64_t)gridDim.x * kKB) {
@@ -587,14 +607,16 @@ k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, c
     }
     const int nr = (int)min((uint64_t)kKB, nrows - row0);
     longlong2* Rb = reinterpret_cast<longlong2*>(R + row0 * lp);
+    longlong2* R2b = R2 ? reinterpret_cast<longlong2*>(R2 + row0 * lp) : nullptr;
     double2* Gb = reinterpret_cast<double2*>(Gout + row0 * lp);
-    longlong2 T[U];
+    longlong2 T[U], K[U];
     int gb = g0;
     auto load_batch = [&]() {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int g = gb + u * rpp;
         T[u] = (g < nr) ? Rb[g * hp + (c >> 1)] : make_longlong2(0, 0);
+        K[u] = (R2b && g < nr) ? R2b[g * hp + (c >> 1)] : make_longlong2(0, 0);
       }
     };
     load_batch();     // in flight while the first 64 threads finish the per-row scales
@@ -605,10 +627,16 @@ k_tc_finish_g(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S, c
         const int g = gb + u * rpp;
         if (g < nr) {
           Rb[g * hp + (c >> 1)] = make_longlong2(0, 0);
+          double c0 = cs[0], c1 = cs[1];
+          if (R2b) {
+            R2b[g * hp + (c >> 1)] = make_longlong2(0, 0);
+            c0 = (double)(csi[0] - K[u].x);
+            c1 = (double)(csi[1] - K[u].y);
+          }
           const double sj = s_s[g], omf = s_omf[g];
           double2 gv;
-          gv.x = (c < l) ? ((omf * cs[0] - 0.5 * (double)T[u].x) * sc[0]) * sj : 0.0;
-          gv.y = (c + 1 < l) ? ((omf * cs[1] - 0.5 * (double)T[u].y) * sc[1]) * sj : 0.0;
+          gv.x = (c < l) ? ((omf * c0 - 0.5 * (double)T[u].x) * sc[0]) * sj : 0.0;
+          gv.y = (c + 1 < l) ? ((omf * c1 - 0.5 * (double)T[u].y) * sc[1]) * sj : 0.0;
           m[0] = fmax(m[0], fabs(gv.x * sj));
           m[1] = fmax(m[1], fabs(gv.y * sj));
           Gb[g * hp + (c >> 1)] = gv;
@@ -638,7 +666,9 @@ __global__ void __launch_bounds__(256) k_tc_reduce_fpart(const double* __restric
 }
 
 // H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c. R is re-zeroed.
-__global__ void k_tc_finish_h(long long* __restrict__ R, uint64_t nrows, int l, int lp, int S,
+// Ranges with missing calls add + 2^(e_c-p) * K[i][c], K = R2 = mask product with the image of
+// D~ = round((f_j - 1) W~_j): removes (1 - f_j) W~_j for the SNPs j missing in sample i.
+__global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__ R2, uint64_t nrows, int l, int lp, int S,
                               const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax,
                               const double* __restrict__ Fw, double* __restrict__ Hacc, int accumulate) {
   __shared__ double sFw[kMaxNP], sScale[kMaxNP], sC[kMaxNP];
@@ -656,7 +686,11 @@ __global__ void k_tc_finish_h(long long* __restrict__ R, uint64_t nrows, int l, 
     if (c < l) {
       const long long T = R[idx];
       R[idx] = 0;
-      const double h = sScale[c] * (sC[c] - 0.5 * (double)T) - sFw[c];
+      double h = sScale[c] * (sC[c] - 0.5 * (double)T) - sFw[c];
+      if (R2) {
+        h += sScale[c] * (double)R2[idx];
+        R2[idx] = 0;
+      }
       Hacc[idx] = accumulate ? Hacc[idx] + h : h;
     } else if (!accumulate) {
       Hacc[idx] = 0.0;

@@ -8,7 +8,7 @@ What is checked, and to which tolerance:
   * U, S, V against the numpy oracle / golden vectors of the unmodified reference at the
     north_star tolerance (eigenvalues <= 1e-6 relative, |cos| >= 0.9999);
   * bit-reproducibility across runs (integer atomics), ragged shapes, out-of-core streaming,
-    and the per-range fallback to the FP64 kernels where genotypes are missing."""
+    and mean imputation of missing calls by count + mask product pairs on the same kernels."""
 import numpy as np
 import pytest
 
@@ -131,8 +131,10 @@ def test_tc_usv_vs_numpy_oracle(N, M, k, svd, bands, S):
     assert_usv_close(op.U, op.S, op.V, U, S_, V)
 
 
-def test_tc_missing_ranges_fall_back_to_fp64():
-    """Windows that contain missing calls run on the FP64 kernels, the others on int8."""
+def test_tc_missing_ranges_run_count_and_mask_products():
+    """Windows that contain missing calls stay on the int8 kernels: every product is run as a
+    (non-missing count, missing mask) pair, which mean-imputes the missing calls (lut[01] = 0,
+    FilePlink.cpp:194-197). No range falls back to the FP64 kernels."""
     N, M, k = 600, 4096, 5
     rng = np.random.default_rng(11)
     codes = np.concatenate([c for _, c in synth.balding_nichols_codes(N, M, k_pop=7, seed=9)])
@@ -142,13 +144,80 @@ def test_tc_missing_ranges_fall_back_to_fp64():
     op.setFlags(False, True)
     op.computeUSV(p.maxp, p.tol)
     t = op.timers()
-    assert t.tc_ranges > 0 and t.fp64_ranges > 0
+    assert t.tc_ranges > 0 and t.fp64_ranges == 0
+    assert 0 < t.tc_miss_ranges < t.tc_ranges
     od = orc.OracleData(packed, N)
     _, windows = orc.incore_windows(M, 8)
     oo = orc.OracleRsvd(od, k, winsvd=True, bands=8, omega=op.Omg, windows=windows)
     oo.set_flags(False, True)
     U, S, V = oo.compute_usv(6, 0.0)
     assert_usv_close(op.U, op.S, op.V, U, S, V)
+
+
+@pytest.mark.parametrize("S", [2, 3, 4])
+@pytest.mark.parametrize("N,M,k,miss", [(500, 3000, 5, 0.02), (129, 777, 3, 0.3), (1000, 2100, 20, 0.001)])
+def test_tc_products_with_missing_calls(S, N, M, k, miss):
+    """The rounding contract with mean-imputed missing calls. The G pass stays exact (the weight
+    1 - f_j of the mask term belongs to the OUTPUT row); in the H pass the mask operand
+    D = (f_j - 1) W~_j is itself rounded to 8S-1 bits, so the MISSING entries of X are imputed with
+    0 +- 2^-(8S) of the column scale: H == X G~ to that bound instead of FP64 noise."""
+    packed = _packed(N, M, k + 2, 300 + N, miss=miss)
+    op, d, p = _op(packed, N, k=k, svd=1, precision=S)
+    op.setFlags(False, True)
+    G, H = op.computeGandH(0)
+    t = op.timers()
+    assert t.tc_ranges == 1 and t.tc_miss_ranges == 1 and t.fp64_ranges == 0
+    od = orc.OracleData(packed, N)
+    assert np.array_equal(op.F(), od.F)
+    X = od.block(0, M - 1, True)
+    Omt, _ = _round_slices(op.Omg, S)
+    sd = np.sqrt(od.F * (1 - od.F))
+    s = np.where(sd > 1e-9, np.sqrt(2.0) / np.maximum(sd, 1e-300), 1.0)
+    W = (X.T @ Omt) * s[:, None]
+    Wt, e = _round_slices(W, S)
+    ulp = 2.0 ** (e - (8 * S - 1))
+    assert np.all(np.abs(G * s[:, None] - Wt) <= 1.01 * ulp[None, :])
+    Href = X @ G
+    nmiss_max = int((od.codes == 1).sum(0).max())          # missing calls of the worst sample
+    bound = ulp[None, :] * nmiss_max + 1e-12 * np.abs(Href).max()
+    assert np.all(np.abs(H - Href) <= bound)
+    rel = np.abs(H - Href).max() / np.abs(Href).max()
+    print((S, N, M, miss), "H rel err", rel)
+    assert rel <= 2.0 ** (-(8 * S - 4))
+    op.close()
+
+
+@pytest.mark.parametrize("svd,memory", [(1, 0.0), (2, 0.0), (2, 0.004)])
+def test_tc_usv_with_missing_vs_numpy_oracle(svd, memory):
+    """1 % missing calls everywhere (every range takes the count + mask route), in-core and streamed."""
+    N, M, k, bands = 640, 6000, 6, 8
+    packed = _packed(N, M, k + 2, 4242, miss=0.01)
+    kw = dict(k=k, svd=svd, bands=bands, maxp=7 if svd == 2 else 4, tol=0.0, precision=3)
+    if memory:
+        kw["memory"] = memory
+    op, d, p = _op(packed, N, **kw)
+    op.setFlags(False, True)
+    op.computeUSV(p.maxp, p.tol)
+    t = op.timers()
+    assert t.tc_ranges > 0 and t.tc_miss_ranges == t.tc_ranges and t.fp64_ranges == 0
+    # the same run on the FP64 DMMA kernels (which decode code 01 through the LUT)
+    kw["precision"] = 0
+    op2, d2, p2 = _op(packed, N, omega=op.Omg, **kw)
+    op2.setFlags(False, True)
+    op2.computeUSV(p.maxp, p.tol)
+    assert op.epochs == op2.epochs
+    print("svd", svd, "mem", memory, "S rel err vs fp64", np.max(np.abs(op.S - op2.S) / op2.S))
+    assert_usv_close(op.U, op.S, op.V, op2.U, op2.S, op2.V)
+    if not memory:
+        od = orc.OracleData(packed, N)
+        windows = None
+        if svd == 2:
+            od.permute(d.perm)
+            _, windows = orc.incore_windows(M, bands)
+        oo = orc.OracleRsvd(od, k, winsvd=svd == 2, bands=bands, omega=op.Omg, windows=windows)
+        oo.set_flags(False, True)
+        U, S_, V = oo.compute_usv(p.maxp, 0.0)
+        assert_usv_close(op.U, op.S, op.V, U, S_, V)
 
 
 def test_tc_ooc_equals_incore():
