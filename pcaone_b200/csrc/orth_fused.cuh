@@ -66,20 +66,27 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
   // it to a double-buffered shared row, ONE __syncthreads, then every thread updates its own
   // elements. (The first version kept W in shared memory: 3 barriers and two integer divisions
   // per column made this single-CTA phase 47 us of a 190 us Omega update.)
-  __shared__ double s_row[2][16 * R];
+  // The inverse comes out of the SAME loop: with L = R^T, forward substitution L Y = I in its
+  // right-looking form is the same rank-1 update applied to a second register tile B (= I on
+  // entry): Y[j][:] = B[j][:] / L[j][j], B[r][:] -= L[r][j] Y[j][:] for r > j, and T = R^-1 = Y^T.
+  // (A separate back substitution, one thread per column, was a serial chain of ~l^2/2 dependent
+  // shared-memory FMAs: half of this phase.)
+  __shared__ double s_row[2][16 * R], s_brow[2][16 * R];
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tx = tid & 15, ty = tid >> 4;
-  double a[R][R];
+  double a[R][R], bi[R][R];
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int r = ty + 16 * i, c = tx + 16 * j;
       a[i][j] = (r < l && c < l) ? W[r * ld + c] : 0.0;
+      bi[i][j] = (r == c && r < l) ? 1.0 : 0.0;
       if (r == c && r < l) s_row[0][r] = a[i][j];
     }
   if (tid == 0) s_fail = 0;
+  for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
   __syncthreads();
   double maxd = 0.0;
   for (int i = 0; i < l; ++i) maxd = fmax(maxd, s_row[0][i]);
@@ -93,7 +100,10 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
       for (int i = 0; i < R; ++i)
         if (i == jt) {
 #pragma unroll
-          for (int jj = 0; jj < R; ++jj) s_row[b][tx + 16 * jj] = a[i][jj];
+          for (int jj = 0; jj < R; ++jj) {
+            s_row[b][tx + 16 * jj] = a[i][jj];
+            s_brow[b][tx + 16 * jj] = bi[i][jj];
+          }
         }
     }
     __syncthreads();
@@ -103,35 +113,27 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
       break;
     }
     const double invd = 1.0 / d;
-    if (tid < l) Ws[j * l + tid] = tid >= j ? s_row[b][tid] * (1.0 / sqrt(d)) : 0.0;  // row j of R
-    double rr[R], rc[R];
+    if (tid <= j) Ts[tid * lc + j] = s_brow[b][tid] * (1.0 / sqrt(d));  // column j of T = row j of Y
+    double rr[R], rc[R], bc[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) rr[i] = s_row[b][ty + 16 * i] * invd;
 #pragma unroll
-    for (int jj = 0; jj < R; ++jj) rc[jj] = s_row[b][tx + 16 * jj];
+    for (int jj = 0; jj < R; ++jj) {
+      rc[jj] = s_row[b][tx + 16 * jj];
+      bc[jj] = s_brow[b][tx + 16 * jj];
+    }
 #pragma unroll
     for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int jj = 0; jj < R; ++jj) {
         const int r = ty + 16 * i, c = tx + 16 * jj;
         if (r > j && c >= r) a[i][jj] -= rr[i] * rc[jj];
+        if (r > j && c <= j) bi[i][jj] -= rr[i] * bc[jj];
       }
   }
   if (fail && tid == 0) s_fail = 1;
   __syncthreads();
-  for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
-  __syncthreads();
   if (!s_fail) {
-    // T = R^-1 (upper triangular), one column per thread, all in shared memory
-    for (int c = tid; c < l; c += nt) {
-      Ts[c * lc + c] = 1.0 / Ws[c * l + c];
-      for (int r = c - 1; r >= 0; --r) {
-        double s = 0.0;
-        for (int p = r + 1; p <= c; ++p) s += Ws[r * l + p] * Ts[p * lc + c];
-        Ts[r * lc + c] = -s / Ws[r * l + r];
-      }
-    }
-    __syncthreads();
     for (int i = tid; i < l * ld; i += nt) {
       const int r = i / ld, c = i - r * ld;
       T[i] = c < l ? Ts[r * lc + c] : 0.0;
@@ -139,6 +141,8 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
     __syncthreads();
     return;
   }
+  for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
+  __syncthreads();
   // ---- eigen route (SVQB): one-sided Jacobi on W in global scratch (rare, slow path)
   double* Aj = jscratch;            // column-major l x l
   double* Vj = Aj + (size_t)l * l;  // column-major l x l
