@@ -34,9 +34,10 @@ enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cm
 /* GEMM arithmetic. FP64: DMMA tensor cores. INT8Xs: error-free Ozaki scheme on
  * the tcgen05 int8 tensor cores — Omega / G are rounded once to s signed 8-bit slices per entry
  * (8s-1 bits against the column maximum) and the products are then exact integers; ranges with
- * missing genotypes and EMU update passes still run on the FP64 kernels. */
+ * missing genotypes run each product as a (non-missing count, missing mask) pair on the same
+ * kernels (mean imputation); EMU update passes still run on the FP64 kernels. */
 enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_INT8X2 = 2, PCAONE_PREC_INT8X3 = 3, PCAONE_PREC_INT8X4 = 4 };
-enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2 };
+enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3 };
 
 /* Mirrors the fields of `Param` (Cmd.hpp:16-98) that the hot path reads. */
 typedef struct pcaone_config {
@@ -158,6 +159,20 @@ int pcaone_shuffle_indices(uint64_t n, uint32_t* out);
  * r2_out receives sum_w (we[w]-1) values in the reference's output order. */
 int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
                  uint64_t nwin, double* r2_out);
+
+/* ---- generic dense matrix: RsvdOpOnePass / RsvdOnePass / RsvdOne (RSVD.hpp:92-362) ----------
+ * The same passes on a dense FP64 matrix A (rows x cols, column-major, as Eigen hands it over)
+ * instead of packed genotypes. The context is created with nsnps = max(rows, cols),
+ * nsamples = min(rows, cols) (a wide matrix is used transposed, RSVD.hpp:113-121), k, oversamples
+ * (here NOT forced to >= k: size = k + os, RSVD.hpp:109), precision = PCAONE_PREC_FP64,
+ * out_of_core = 1 and svd = PCAONE_SVD_WINSVD when windows > 0. Omega (nsamples x (k + os)) comes
+ * from the host RNG through pcaone_set_omega (pcaone_init_omega(n, size, 1, gaussian) reproduces
+ * the default-seeded engine of RSVD.hpp:123). pcaone_dense_rsvd runs computeGandH(G, H, p[, windows])
+ * and computeUSV; pcaone_get_usv then returns U = nsamples x k (svd.matrixV()), S, and
+ * V = nsnps x k (G * svd.matrixU()): RsvdOne::matrixU() is V here when rows >= cols, else U.
+ * finder: 1 = QR (implemented); 2 = LU range finder (RSVD.hpp:150-153) is rejected. */
+int pcaone_upload_dense(pcaone_ctx* ctx, const double* A, uint64_t rows, uint64_t cols);
+int pcaone_dense_rsvd(pcaone_ctx* ctx, uint32_t p, uint32_t windows, int finder);
 
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct pcaone_timers {

@@ -237,3 +237,16 @@ def householder_q(A):
     Q = _f(A.shape)
     lib().ref_householder_q(_p(A), C.c_longlong(A.shape[0]), C.c_longlong(A.shape[1]), _p(Q))
     return Q
+
+
+def rsvd_one(A, k, os_=10, rand=1, p=3, windows=0, finder=1):
+    """PCAone::RsvdOne<MatrixXd>(A, k, os, rand); setRangeFinder(finder); compute(p, windows)
+    (RSVD.hpp:327-362) -> U (rows x k), S (k), V (cols x k)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    r, c = A.shape
+    U, S, V = _f((r, k)), np.zeros(k), _f((c, k))
+    rc = lib().ref_rsvd_one(_p(A), C.c_longlong(r), C.c_longlong(c), int(k), int(os_), int(rand), int(p), int(windows),
+                            int(finder), _p(U), _p(S), _p(V))
+    if rc:
+        raise RuntimeError("reference failed: " + lib().ref_last_error().decode())
+    return U, S, V

@@ -16,6 +16,7 @@
 //   flip_UV / mev    (src/Utils.cpp:118,194)
 //   PCAone::flipOmg  (src/RSVD.hpp:80)
 //   calc_sds / divide_pos_by_window (src/LD.cpp:48,154)
+//   PCAone::RsvdOne  (src/RSVD.hpp:327-362, the dense-matrix front-end PCAoneR binds)
 #define _DECLARE_TOOLBOX_HERE
 #include <omp.h>
 
@@ -412,6 +413,22 @@ long long ref_ld_r2(void* h, const char* filebim, int ld_bp, double* out, long l
 int ref_write_residuals(void* h) {
   RefCtx* c = (RefCtx*)h;
   return guarded([&] { c->data->write_residuals(c->op->S, c->op->U, c->op->V.transpose()); });
+}
+
+// PCAone::RsvdOne<MatrixXd> (RSVD.hpp:327-362) on a dense column-major matrix: the reference's own
+// template, instantiated here. U: rows x k, S: k, V: cols x k. Returns non-zero if it throws.
+int ref_rsvd_one(const double* A, long long rows, long long cols, int k, int os, int rand, int p, int windows,
+                 int finder, double* U, double* S, double* V) {
+  return guarded([&] {
+    Eigen::Map<const Eigen::MatrixXd> M(A, rows, cols);
+    Eigen::MatrixXd mat = M;
+    PCAone::RsvdOne<Eigen::MatrixXd> rsvd(mat, (uint32_t)k, (uint32_t)os, (uint32_t)rand);
+    rsvd.setRangeFinder(finder);
+    rsvd.compute((uint32_t)p, (uint32_t)windows);
+    Eigen::Map<Eigen::MatrixXd>(U, rows, k) = rsvd.matrixU();
+    Eigen::Map<Eigen::VectorXd>(S, k) = rsvd.singularValues();
+    Eigen::Map<Eigen::MatrixXd>(V, cols, k) = rsvd.matrixV();
+  });
 }
 
 }  // extern "C"

@@ -1,0 +1,203 @@
+// pcaone_b200 — the same two power-iteration products for a GENERIC dense FP64 matrix
+// (reference: RsvdOpOnePass::computeGandH, src/RSVD.hpp:137-166 and the window variant :168-252 —
+// the PCAoneR entry point).
+//
+//   k_dense_g :  G_b   = D_b * Omega          D_b = rows [r0, r0 + nrows) of the tall matrix
+//   k_dense_h :  Hpart = D_b^T * G_b          (split over the rows of the range)
+//
+// D is the tall orientation of the input (rows >= cols; a wide input is used transposed, exactly
+// like `trans` in RSVD.hpp:113-121), row-major [rows][ldd] doubles in HBM, ldd = cols rounded up
+// to 8 with zero padding. Only the operand loader differs from gemm_fp64.cuh: the A fragments of
+// the FP64 tensor-core MMAs (DMMA m8n8k4) come from a cp.async-staged tile of doubles instead of
+// being decoded from 2-bit codes. Everything downstream (Omega update, QR(G) x2, SVD of the core)
+// is the same device code as for genotypes.
+#pragma once
+#include "common.cuh"
+
+namespace pcaone {
+
+constexpr int kDenseThreads = 256;
+constexpr int kDenseRows = 128;  // output rows per CTA (8 warps x 16)
+constexpr int kDenseKC = 32;     // contraction chunk per pipeline stage
+constexpr int kDenseLDA = kDenseKC + 4;    // row-major A tile [128][36]: 36 = 4 (mod 16) -> conflict-free A fragments
+constexpr int kDenseLDT = kDenseRows + 4;  // k-major A tile [32][132] for the transposed product
+
+template <int NT>
+struct DenseSmem {
+  static constexpr int LP = NT * 8;
+  static constexpr int LDB = smem_ld(LP);
+  static constexpr size_t kStageG = ((size_t)kDenseRows * kDenseLDA + (size_t)kDenseKC * LDB) * sizeof(double);
+  static constexpr size_t kStageH = ((size_t)kDenseKC * kDenseLDT + (size_t)kDenseKC * LDB) * sizeof(double);
+};
+
+// G[r][c] = sum_i D[r0 + r][i] * Omega[i][c],  r < nrows, i < ncols (ldd >= ncols, pad columns zero)
+template <int NT>
+__global__ void __launch_bounds__(kDenseThreads)
+k_dense_g(const double* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t ncols,
+          const double* __restrict__ Omg,  // [ncols][8NT]
+          double* __restrict__ G) {        // [nrows][8NT]
+  using SM = DenseSmem<NT>;
+  constexpr int LP = SM::LP, LDB = SM::LDB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + SM::kStageG)};
+  double* Bs[2] = {As[0] + kDenseRows * kDenseLDA, As[1] + kDenseRows * kDenseLDA};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t row0 = blockIdx.x * kDenseRows;
+  const int nchunks = (int)((ncols + kDenseKC - 1) / kDenseKC);
+
+  auto load = [&](int chunk, int stage) {
+    const uint32_t k0 = (uint32_t)chunk * kDenseKC;
+    constexpr int APIECES = kDenseKC / 2;  // 16-byte pieces per A row
+    for (int idx = tid; idx < kDenseRows * APIECES; idx += kDenseThreads) {
+      const int r = idx / APIECES, pc = idx - r * APIECES;
+      const uint32_t row = row0 + r, k = k0 + 2 * pc;
+      const bool ok = row < nrows && k < ldd;
+      cp_async16(As[stage] + r * kDenseLDA + 2 * pc, D + (uint64_t)(ok ? row : 0) * ldd + (ok ? k : 0), ok ? 16 : 0);
+    }
+    constexpr int BPIECES = LP / 2;
+    for (int idx = tid; idx < kDenseKC * BPIECES; idx += kDenseThreads) {
+      const int r = idx / BPIECES, pc = idx - r * BPIECES;
+      const uint32_t i = k0 + r;
+      const bool ok = i < ncols;
+      cp_async16(Bs[stage] + r * LDB + 2 * pc, Omg + (uint64_t)(ok ? i : 0) * LP + 2 * pc, ok ? 16 : 0);
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[u][n][0] = acc[u][n][1] = 0.0;
+
+  load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c + 1 < nchunks) load(c + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* A = As[st] + (warp * 16 + g) * kDenseLDA + t;
+    const double* B = Bs[st] + t * LDB + g;
+#pragma unroll
+    for (int s = 0; s < kDenseKC / 4; ++s) {
+      const double a0 = A[4 * s], a1 = A[8 * kDenseLDA + 4 * s];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const double b = B[4 * s * LDB + 8 * n];
+        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+        dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t row = row0 + warp * 16 + 8 * u + g;
+    if (row < nrows) {
+      double* out = G + (uint64_t)row * LP + 2 * t;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<double2*>(out + 8 * n) = make_double2(acc[u][n][0], acc[u][n][1]);
+    }
+  }
+}
+
+// Hpart[split][i][c] = sum_{r in split} D[r][i] * G[r][c],  i < ncols; grid = (col tiles of 128, splits)
+template <int NT>
+__global__ void __launch_bounds__(kDenseThreads)
+k_dense_h(const double* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t ncols,
+          const double* __restrict__ G,    // [nrows][8NT]
+          double* __restrict__ Hpart,      // [splits][ncols][8NT]
+          uint32_t rows_per_split) {
+  using SM = DenseSmem<NT>;
+  constexpr int LP = SM::LP, LDB = SM::LDB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + SM::kStageH)};
+  double* Bs[2] = {As[0] + kDenseKC * kDenseLDT, As[1] + kDenseKC * kDenseLDT};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t i0 = blockIdx.x * kDenseRows;
+  const uint32_t rbeg = blockIdx.y * rows_per_split;
+  const uint32_t rend = min(nrows, rbeg + rows_per_split);
+  const int nchunks = rend > rbeg ? (int)((rend - rbeg + kDenseKC - 1) / kDenseKC) : 0;
+
+  auto load = [&](int chunk, int stage) {
+    const uint32_t r0 = rbeg + (uint32_t)chunk * kDenseKC;
+    constexpr int APIECES = kDenseRows / 2;
+    for (int idx = tid; idx < kDenseKC * APIECES; idx += kDenseThreads) {
+      const int r = idx / APIECES, pc = idx - r * APIECES;
+      const uint32_t row = r0 + r, i = i0 + 2 * pc;
+      const bool ok = row < rend && i < ldd;
+      cp_async16(As[stage] + r * kDenseLDT + 2 * pc, D + (uint64_t)(ok ? row : 0) * ldd + (ok ? i : 0), ok ? 16 : 0);
+    }
+    constexpr int BPIECES = LP / 2;
+    for (int idx = tid; idx < kDenseKC * BPIECES; idx += kDenseThreads) {
+      const int r = idx / BPIECES, pc = idx - r * BPIECES;
+      const uint32_t row = r0 + r;
+      const bool ok = row < rend;
+      cp_async16(Bs[stage] + r * LDB + 2 * pc, G + (uint64_t)(ok ? row : 0) * LP + 2 * pc, ok ? 16 : 0);
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[u][n][0] = acc[u][n][1] = 0.0;
+
+  if (nchunks > 0) load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c + 1 < nchunks) load(c + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* A = As[st] + t * kDenseLDT + warp * 16 + g;
+    const double* B = Bs[st] + t * LDB + g;
+#pragma unroll
+    for (int s = 0; s < kDenseKC / 4; ++s) {
+      const double a0 = A[4 * s * kDenseLDT], a1 = A[4 * s * kDenseLDT + 8];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const double b = B[4 * s * LDB + 8 * n];
+        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+        dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  double* Hp = Hpart + (uint64_t)blockIdx.y * ncols * LP;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t i = i0 + warp * 16 + 8 * u + g;
+    if (i < ncols) {
+      double* out = Hp + (uint64_t)i * LP + 2 * t;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<double2*>(out + 8 * n) = make_double2(acc[u][n][0], acc[u][n][1]);
+    }
+  }
+}
+
+// col-major (rows x cols, ld = rows) -> row-major [rows][ldd], 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) k_dense_transpose_in(const double* __restrict__ src, uint64_t rows, uint64_t cols,
+                                                             double* __restrict__ dst, uint32_t ldd) {
+  __shared__ double tile[32][33];
+  const uint64_t r0 = (uint64_t)blockIdx.x * 32, c0 = (uint64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const uint64_t r = r0 + tx, c = c0 + j;
+    tile[j][tx] = (r < rows && c < cols) ? src[c * rows + r] : 0.0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const uint64_t r = r0 + j, c = c0 + tx;
+    if (r < rows && c < ldd) dst[r * ldd + c] = tile[tx][j];
+  }
+}
+
+}  // namespace pcaone

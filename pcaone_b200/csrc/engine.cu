@@ -25,6 +25,7 @@
 #include "tall_skinny.cuh"
 #include "orth_fused.cuh"
 #include "tc_gemm.cuh"
+#include "dense_gemm.cuh"
 #include "ld.cuh"
 
 using namespace pcaone;
@@ -52,6 +53,8 @@ struct pcaone_ctx {
 
   // genotype source
   int source = -1;
+  double* d_dense = nullptr;  // PCAONE_SRC_DENSE: tall orientation of a generic matrix, row-major [M][ldd]
+  uint32_t ldd = 0;
   uint8_t* d_packed = nullptr;  // resident, M x pitch
   const uint8_t* h_packed = nullptr;
   pcaone_read_block_fn reader = nullptr;
@@ -553,12 +556,70 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
   if (miss) c->tc_miss_ranges++;
 }
 
+// ---------------------------------------------------------------- generic dense matrix (RsvdOpOnePass)
+template <int NT>
+void dense_g_nt(pcaone_ctx* c, const double* D, uint32_t nrows, double* G) {
+  const size_t smem = 2 * DenseSmem<NT>::kStageG;
+  static bool attr = false;
+  if (!attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_dense_g<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k_dense_g<NT><<<ceil_div(nrows, kDenseRows), kDenseThreads, smem, c->stream>>>(D, c->ldd, nrows, (uint32_t)c->N,
+                                                                                   c->d_Omg, G);
+  PCA_CHECK_LAUNCH();
+}
+template <int NT>
+void dense_h_nt(pcaone_ctx* c, const double* D, uint32_t nrows, const double* G, uint32_t splits, uint32_t rps) {
+  const size_t smem = 2 * DenseSmem<NT>::kStageH;
+  static bool attr = false;
+  if (!attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_dense_h<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(ceil_div(c->N, kDenseRows), splits);
+  k_dense_h<NT><<<grid, kDenseThreads, smem, c->stream>>>(D, c->ldd, nrows, (uint32_t)c->N, G, c->d_Hpart, rps);
+  PCA_CHECK_LAUNCH();
+}
+
+// rows [r0, r0 + nrows) of the tall matrix: G rows = D_b Omega ; Hacc (+)= D_b^T G_b   (RSVD.hpp:139-144)
+void range_gemms_dense(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc, bool accumulate) {
+  const double* D = c->d_dense + r0 * c->ldd;
+  double* G = c->d_G + r0 * c->lp;
+  {
+    Timed t(c, 0);
+    NT_DISPATCH(dense_g_nt, c, D, nrows, G);
+    c->tm.gemm_g_launches++;
+    c->tm.kernel_launches++;
+  }
+  const uint32_t tiles = ceil_div(c->N, kDenseRows);
+  uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
+  splits = std::min<uint32_t>(splits, c->max_splits);
+  splits = std::min<uint32_t>(splits, (uint32_t)ceil_div(nrows, kDenseKC));
+  const uint32_t rps = (uint32_t)round_up((size_t)ceil_div(nrows, splits), kDenseKC);
+  splits = ceil_div(nrows, rps);
+  {
+    Timed t(c, 1);
+    NT_DISPATCH(dense_h_nt, c, D, nrows, G, splits, rps);
+    const uint64_t count = c->N * c->lp;
+    k_reduce_partials<<<grid_for(count, 256, c->sms), 256, 0, c->stream>>>(c->d_Hpart, splits, count, Hacc,
+                                                                           accumulate ? 1 : 0);
+    PCA_CHECK_LAUNCH();
+    c->tm.gemm_h_launches++;
+    c->tm.kernel_launches += 2;
+  }
+}
+
 // G rows of the range = X^T Omega ; Hacc (+)= X G. `buf` = streamed block buffer holding P, or -1
 // when P points into the resident shard. Ranges without missing genotypes (and no EMU fill) run
 // on the int8 tensor-core kernels when the context was created with a PCAONE_PREC_INT8* mode.
 void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate,
                  int buf) {
   if (nrows == 0) return;
+  if (c->source == PCAONE_SRC_DENSE) {
+    range_gemms_dense(c, snp0, nrows, Hacc, accumulate);
+    return;
+  }
   // EMU update passes fill every missing entry with its own FP64 value: FP64 kernels
   const bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu);
   bool has_miss = false;
@@ -983,7 +1044,7 @@ void zero_async(pcaone_ctx* c, double* p, uint64_t n) { PCA_CUDA(cudaMemsetAsync
 void compute_gandh(pcaone_ctx* c, int pi) {
   if (c->source < 0) throw std::runtime_error("no genotype source set");
   if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("EMU update pass without U,S,V");
-  const bool ooc = c->source != PCAONE_SRC_RESIDENT;
+  const bool ooc = c->source == PCAONE_SRC_HOST || c->source == PCAONE_SRC_FILE;
   const bool win = c->cfg.svd == PCAONE_SVD_WINSVD;
   c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
   const uint64_t HN = c->N * c->lp;
@@ -996,7 +1057,7 @@ void compute_gandh(pcaone_ctx* c, int pi) {
   if (ooc) {
     if (c->blk_start.empty()) throw std::runtime_error("out-of-core source needs pcaone_set_blocks");
     alloc_stream_buffers(c);
-  } else if (!c->af_done) {
+  } else if (!c->af_done && c->source != PCAONE_SRC_DENSE) {
     throw std::runtime_error("call pcaone_allele_freq before the first pass");
   }
 
@@ -1155,6 +1216,80 @@ void compute_usv(pcaone_ctx* c, int p, double tol) {
   PCA_CUDA(cudaMemcpyAsync(c->d_U, c->d_Ucur, ubytes, cudaMemcpyDeviceToDevice, c->stream));
   c->last_diff = diff;
   c->last_epochs = epochs;
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// RsvdOpOnePass::computeGandH (RSVD.hpp:137-166 plain, :168-252 windows) followed by
+// RsvdOnePass::computeUSV (RSVD.hpp:281-313) on the dense source: a fixed number of power
+// iterations, no convergence test. Result: d_U (ncol side, = svd.matrixV()), d_V (nrow side,
+// = G * svd.matrixU()), d_S.
+void dense_onepass(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder) {
+  if (c->source != PCAONE_SRC_DENSE) throw std::runtime_error("dense_rsvd: call pcaone_upload_dense first");
+  if (finder != 1)
+    throw std::runtime_error("dense_rsvd: only the QR range finder (finder = 1, RSVD.hpp:147-149) is implemented");
+  if (!c->have_omg0) throw std::runtime_error("call pcaone_set_omega before dense_rsvd");
+  const uint64_t HN = c->N * c->lp;
+  PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->omega_img_valid = false;
+  auto full_pass = [&]() { range_gemms(c, nullptr, (uint32_t)c->M, 0, c->d_H, false, -1); };
+  full_pass();
+  if (windows == 0) {
+    for (uint32_t pi = 0; pi < p; ++pi) {
+      update_omega(c, c->d_H, false);  // Omg = householderQ(H) * I, no flipOmg (RSVD.hpp:146-149)
+      full_pass();
+    }
+  } else {
+    if (windows % 2 != 0) throw std::runtime_error("windows must be a power of 2, ie. windows=2^x.");
+    if (std::pow(2.0, (double)p) < (double)windows) throw std::runtime_error("pow(2, p) >= windows has to be met");
+    const uint64_t bs = (c->M + windows - 1) / windows;
+    if (bs < windows || (uint64_t)(windows - 1) * bs >= c->M)
+      throw std::runtime_error("window size is smaller than number of windows because given matrix is too small");
+    if (!c->d_H1) throw std::runtime_error("dense_rsvd with windows needs a context created with svd = PCAONE_SVD_WINSVD");
+    zero_async(c, c->d_H1, HN);
+    zero_async(c, c->d_H2, HN);
+    auto update = [&](bool zero_h1) {
+      k_add2<<<grid_for(HN, 256, c->sms), 256, 0, c->stream>>>(c->d_H1, c->d_H2, c->d_H, HN);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+      update_omega(c, c->d_H, true);
+      zero_async(c, zero_h1 ? c->d_H1 : c->d_H2, HN);
+    };
+    uint64_t band = 1;
+    for (uint32_t pi = 0; pi <= p; ++pi) {
+      if (std::pow(2.0, (double)pi) >= (double)windows) {
+        zero_async(c, c->d_H1, HN);
+        zero_async(c, c->d_H2, HN);
+      }
+      band = std::min<uint64_t>(band * 2, windows);
+      const double half_prev = pi > 0 ? std::pow(2.0, (double)pi - 1.0) : 0.0;
+      const bool early = pi > 0 && std::pow(2.0, (double)pi) < (double)windows;
+      uint64_t i = 1, j = 1;
+      for (uint64_t b = 0; b < windows; ++b, ++i, ++j) {
+        const uint64_t start = b * bs, stop = std::min<uint64_t>((b + 1) * bs, c->M) - 1;
+        const uint32_t n = (uint32_t)(stop - start + 1);
+        if (early && (double)j <= half_prev) {
+          range_gemms(c, nullptr, n, start, c->d_H1, true, -1);
+          if ((double)j == half_prev) update(false);  // complementary power iteration (RSVD.hpp:207-214)
+        } else if (i <= band / 2) {
+          range_gemms(c, nullptr, n, start, c->d_H1, true, -1);
+        } else {
+          range_gemms(c, nullptr, n, start, c->d_H2, true, -1);
+        }
+        if (b + 1 >= band) {
+          if (i == band) {
+            update(true);
+            i = 0;
+          } else if (i == band / 2) {
+            update(false);
+          }
+        }
+      }
+    }
+  }
+  small_stage(c);
+  finalize_usv(c);
+  PCA_CUDA(cudaMemcpyAsync(c->d_U, c->d_Ucur, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   PCA_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -1484,7 +1619,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
-                  (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
+                  (void*)c->d_dense, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -1827,6 +1962,41 @@ int pcaone_mev(pcaone_ctx* c, const double* X, const double* Y, uint64_t rows, u
     cudaFree(dy);
     *out = r;
   });
+}
+
+int pcaone_upload_dense(pcaone_ctx* c, const double* A, uint64_t rows, uint64_t cols) {
+  CTX_GUARD(c, {
+    const bool trans = rows < cols;  // RSVD.hpp:113-121: a wide matrix is used transposed
+    const uint64_t nrow = trans ? cols : rows, ncol = trans ? rows : cols;
+    if (nrow != c->M || ncol != c->N)
+      throw std::runtime_error("upload_dense: context must be created with nsnps = max(rows, cols), nsamples = min(rows, cols)");
+    if (c->cfg.precision != PCAONE_PREC_FP64) throw std::runtime_error("upload_dense: the dense source runs in FP64");
+    if (c->cfg.world > 1) throw std::runtime_error("upload_dense: single-GPU only");
+    c->ldd = (uint32_t)round_up(c->N, 8);
+    if (!c->d_dense) dmalloc(&c->d_dense, c->M * (size_t)c->ldd);
+    if (trans) {
+      // A^T in row-major is A in column-major: rows of length N, re-pitched to ldd
+      PCA_CUDA(cudaMemsetAsync(c->d_dense, 0, c->M * (size_t)c->ldd * sizeof(double), c->stream));
+      PCA_CUDA(cudaMemcpy2DAsync(c->d_dense, (size_t)c->ldd * sizeof(double), A, c->N * sizeof(double),
+                                 c->N * sizeof(double), c->M, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      double* stage = nullptr;
+      dmalloc(&stage, c->M * c->N);
+      PCA_CUDA(cudaMemcpyAsync(stage, A, c->M * c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      dim3 grid((unsigned)ceil_div(c->M, 32), (unsigned)ceil_div(c->ldd, 32));
+      k_dense_transpose_in<<<grid, 256, 0, c->stream>>>(stage, c->M, c->N, c->d_dense, c->ldd);
+      PCA_CHECK_LAUNCH();
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      cudaFree(stage);
+    }
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->tm.h2d_bytes += c->M * c->N * sizeof(double);
+    c->source = PCAONE_SRC_DENSE;
+  });
+}
+
+int pcaone_dense_rsvd(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder) {
+  CTX_GUARD(c, dense_onepass(c, p, windows, finder));
 }
 
 int pcaone_ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,

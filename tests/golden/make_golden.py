@@ -132,6 +132,19 @@ def main():
                         flip_omg=O1, flipU=Uf, flipV=Vf, omega_7x3_seed9=ref.init_omega(7, 3, 9, True),
                         omega_uniform=ref.init_omega(7, 3, 9, False), shuffle10=ref.permute_indices(10),
                         plink_perm=r_perm())
+    # ---- G: dense front-end RsvdOne (RSVD.hpp:327-362): tall, wide, plain and windowed
+    rng = np.random.default_rng(21)
+    def lowrank(r, c, kk):
+        return (rng.standard_normal((r, kk)) * np.linspace(20, 5, kk)) @ rng.standard_normal((kk, c)) \
+            + 0.05 * rng.standard_normal((r, c))
+    At, Aw = lowrank(301, 57, 6), lowrank(45, 260, 5)
+    out = {"A_tall": At, "A_wide": Aw, "k": 4, "os": 6,
+           "omega_tall": ref.init_omega(57, 10, 1, True), "omega_wide": ref.init_omega(45, 10, 1, True)}
+    for name, A in (("tall", At), ("wide", Aw)):
+        for p_, w_ in ((3, 0), (5, 4), (3, 8)):
+            U, S, V = ref.rsvd_one(A, 4, 6, 1, p=p_, windows=w_)
+            out[f"{name}_p{p_}_w{w_}_U"], out[f"{name}_p{p_}_w{w_}_S"], out[f"{name}_p{p_}_w{w_}_V"] = U, S, V
+    np.savez_compressed(os.path.join(OUT, "rsvd_one.npz"), **out)
     print("golden written to", OUT)
 
 

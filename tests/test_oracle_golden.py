@@ -1,6 +1,7 @@
 """CPU: the numpy oracle (oracle/pcaone_oracle.py) against golden vectors produced by the
 unmodified reference (tests/golden/make_golden.py). This is what pins the oracle."""
 import numpy as np
+import pytest
 
 from conftest import assert_usv_close, col_cos, golden
 from oracle import pcaone_oracle as orc
@@ -182,3 +183,28 @@ def test_helpers():
     assert np.array_equal(O1, h["flip_omg"]) and np.array_equal(O2, h["flip_omg2"])
     U, V = orc.flip_uv(A, B)
     assert np.array_equal(U, h["flipU"]) and np.array_equal(V, h["flipV"])
+
+
+@pytest.mark.parametrize("name", ["tall", "wide"])
+@pytest.mark.parametrize("p,w", [(3, 0), (5, 4), (3, 8)])
+def test_rsvd_one_restatement_vs_reference(name, p, w):
+    """oracle.rsvd_one (numpy restatement of RSVD.hpp:92-362) against PCAone::RsvdOne<MatrixXd>
+    outputs generated from the unmodified reference (tests/golden/rsvd_one.npz)."""
+    g = golden("rsvd_one")
+    A, k, os_ = g[f"A_{name}"], int(g["k"]), int(g["os"])
+    U, S, V = orc.rsvd_one(A, k, os_, g[f"omega_{name}"], p, w)
+    Ur, Sr, Vr = g[f"{name}_p{p}_w{w}_U"], g[f"{name}_p{p}_w{w}_S"], g[f"{name}_p{p}_w{w}_V"]
+    assert U.shape == Ur.shape and V.shape == Vr.shape
+    assert np.max(np.abs(S - Sr) / Sr) < 1e-12
+    assert col_cos(U, Ur).min() > 1 - 1e-12 and col_cos(V, Vr).min() > 1 - 1e-12
+
+
+def test_rsvd_one_restatement_argument_checks():
+    A = np.random.default_rng(0).standard_normal((40, 12))
+    om = np.zeros((12, 6))
+    with pytest.raises(RuntimeError):
+        orc.rsvd_one(A, 3, 3, om, 3, 3)      # windows must be even
+    with pytest.raises(RuntimeError):
+        orc.rsvd_one(A, 3, 3, om, 1, 4)      # 2^p >= windows
+    with pytest.raises(RuntimeError):
+        orc.rsvd_one(A, 3, 3, om, 4, 16)     # block smaller than the number of windows
