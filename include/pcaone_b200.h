@@ -37,7 +37,7 @@ enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cm
  * missing genotypes run each product as a (non-missing count, missing mask) pair on the same
  * kernels (mean imputation); EMU update passes still run on the FP64 kernels. */
 enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_INT8X2 = 2, PCAONE_PREC_INT8X3 = 3, PCAONE_PREC_INT8X4 = 4 };
-enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3 };
+enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3, PCAONE_SRC_DOSAGE = 4 };
 
 /* Mirrors the fields of `Param` (Cmd.hpp:16-98) that the hot path reads. */
 typedef struct pcaone_config {
@@ -159,6 +159,17 @@ int pcaone_shuffle_indices(uint64_t n, uint32_t* out);
  * r2_out receives sum_w (we[w]-1) values in the reference's output order. */
 int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
                  uint64_t nwin, double* r2_out);
+
+/* ---- BGEN-style dosages (FileBgen::read_all / read_block_initial, FileBgen.cpp:15-168) ----------
+ * The host keeps the container parsing (`var.minor_allele_dosage`, FileBgen.cpp:26) and hands over
+ * what that call yields: one row of nsamples floats per variant, NaN = missing, SNP-major
+ * [nsnps][nsamples]. The device keeps the floats (4 bytes per genotype) and fuses
+ * value = NaN ? 0 : (d / 2 - F_j) [* sqrt(ploidy) / sqrt(F_j (1 - F_j))] into the operand load of the
+ * same FP64 tensor-core products; pcaone_allele_freq computes F_j = mean(d / 2) over non-missing
+ * (FileBgen.cpp:27-41), pcaone_decode_block returns the dense block for parity. After this call the
+ * context behaves like a resident genotype shard (sSVD / winSVD, pcaone_permute_resident,
+ * pcaone_set_blocks). precision must be PCAONE_PREC_FP64; --emu is rejected for this source. */
+int pcaone_upload_dosage(pcaone_ctx* ctx, const float* dosage, uint64_t nsnps, int device_ptr);
 
 /* ---- generic dense matrix: RsvdOpOnePass / RsvdOnePass / RsvdOne (RSVD.hpp:92-362) ----------
  * The same passes on a dense FP64 matrix A (rows x cols, column-major, as Eigen hands it over)

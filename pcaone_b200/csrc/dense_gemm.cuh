@@ -5,6 +5,12 @@
 //   k_dense_g :  G_b   = D_b * Omega          D_b = rows [r0, r0 + nrows) of the tall matrix
 //   k_dense_h :  Hpart = D_b^T * G_b          (split over the rows of the range)
 //
+// The same kernels with DOS = true read FLOAT32 DOSAGES (BGEN `minor_allele_dosage`, one row of N
+// floats per variant, NaN = missing; reference FileBgen.cpp:15-72 in-core, :86-168 blocks) and fuse
+// the reference's decode into the fragment load: value = NaN ? 0 : (d / 2 - F_j) * s_j with
+// s_j = sqrt(ploidy) / sqrt(F_j (1 - F_j)) when standardising — mean imputation, centring and
+// scaling, never materialising the N x M double matrix (4 bytes per genotype in HBM).
+//
 // D is the tall orientation of the input (rows >= cols; a wide input is used transposed, exactly
 // like `trans` in RSVD.hpp:113-121), row-major [rows][ldd] doubles in HBM, ldd = cols rounded up
 // to 8 with zero padding. Only the operand loader differs from gemm_fp64.cuh: the A fragments of
@@ -22,12 +28,53 @@ constexpr int kDenseKC = 32;     // contraction chunk per pipeline stage
 constexpr int kDenseLDA = kDenseKC + 4;    // row-major A tile [128][36]: 36 = 4 (mod 16) -> conflict-free A fragments
 constexpr int kDenseLDT = kDenseRows + 4;  // k-major A tile [32][132] for the transposed product
 
+constexpr int kDosLDA = kDenseKC + 4;     // float row-major A tile: 36 = 4 (mod 32) -> conflict-free
+constexpr int kDosLDT = kDenseRows + 8;   // float k-major A tile: 136 = 8 (mod 32) -> conflict-free
+
+__device__ __forceinline__ double dosage_value(float d, double F, double s) {
+  return isnan(d) ? 0.0 : __dmul_rn(__dsub_rn((double)d * 0.5, F), s);
+}
+
+// allele frequency of dosage rows: F_j = sum(d / 2 over non-NaN) / #non-NaN (0 if none),
+// FileBgen.cpp:27-41. One warp per variant; the double sum is a fixed-order lane/shuffle tree (the
+// reference's own OpenMP reduction is not reproducible run to run, so this is tolerance-level).
+__global__ void __launch_bounds__(256) k_dosage_af(const float* __restrict__ D, uint32_t ldd, uint32_t N, uint64_t rows,
+                                                    double* __restrict__ F, uint32_t* __restrict__ nmiss) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t j = warp; j < rows; j += nwarps) {
+    const float* row = D + j * ldd;
+    double gs = 0.0;
+    uint32_t gc = 0;
+    for (uint32_t i = lane; i < N; i += 32) {
+      const float d = row[i];
+      if (!isnan(d)) {
+        gs += (double)d * 0.5;
+        gc += 1;
+      }
+    }
+    gs = warp_sum(gs);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gc += __shfl_xor_sync(0xffffffffu, gc, o);
+    if (lane == 0) {
+      F[j] = gc ? gs / (double)gc : 0.0;
+      nmiss[j] = N - gc;
+    }
+  }
+}
+
 template <int NT>
 struct DenseSmem {
   static constexpr int LP = NT * 8;
   static constexpr int LDB = smem_ld(LP);
   static constexpr size_t kStageG = ((size_t)kDenseRows * kDenseLDA + (size_t)kDenseKC * LDB) * sizeof(double);
   static constexpr size_t kStageH = ((size_t)kDenseKC * kDenseLDT + (size_t)kDenseKC * LDB) * sizeof(double);
+  // dosage variants: the A tile holds floats; the H kernel also stages F_r and s_r of the chunk
+  static constexpr size_t kDosA_G = (size_t)kDenseRows * kDosLDA * sizeof(float);
+  static constexpr size_t kDosA_H = (size_t)kDenseKC * kDosLDT * sizeof(float);
+  static constexpr size_t kDosStageG = kDosA_G + (size_t)kDenseKC * LDB * sizeof(double);
+  static constexpr size_t kDosStageH = kDosA_H + (size_t)kDenseKC * LDB * sizeof(double) + 2 * kDenseKC * sizeof(double);
 };
 
 // G[r][c] = sum_i D[r0 + r][i] * Omega[i][c],  r < nrows, i < ncols (ldd >= ncols, pad columns zero)
@@ -180,6 +227,200 @@ k_dense_h(const double* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t n
       for (int n = 0; n < NT; ++n)
         *reinterpret_cast<double2*>(out + 8 * n) = make_double2(acc[u][n][0], acc[u][n][1]);
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// dosage variants: A tile = float dosages, decoded in the fragment load
+// ------------------------------------------------------------------------------------------
+
+// G[r][c] = sum_i x(r, i) * Omega[i][c], x(r, i) = dosage_value(D[r][i], F[r], s[r]); rows = variants
+template <int NT>
+__global__ void __launch_bounds__(kDenseThreads)
+k_dos_g(const float* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t ncols, const double* __restrict__ F,
+        LutParams lp, const double* __restrict__ Omg, double* __restrict__ G) {
+  using SM = DenseSmem<NT>;
+  constexpr int LP = SM::LP, LDB = SM::LDB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw + SM::kDosStageG)};
+  double* Bs[2] = {reinterpret_cast<double*>(smem_raw + SM::kDosA_G),
+                   reinterpret_cast<double*>(smem_raw + SM::kDosStageG + SM::kDosA_G)};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t row0 = blockIdx.x * kDenseRows;
+  const int nchunks = (int)((ncols + kDenseKC - 1) / kDenseKC);
+  double fj[2], sj[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t row = row0 + warp * 16 + 8 * u + g;
+    fj[u] = row < nrows ? F[row] : 0.0;
+    sj[u] = row < nrows ? snp_scale(fj[u], lp) : 0.0;
+  }
+
+  auto load = [&](int chunk, int stage) {
+    const uint32_t k0 = (uint32_t)chunk * kDenseKC;
+    constexpr int APIECES = kDenseKC / 4;  // 16-byte pieces (4 floats) per A row
+    for (int idx = tid; idx < kDenseRows * APIECES; idx += kDenseThreads) {
+      const int r = idx / APIECES, pc = idx - r * APIECES;
+      const uint32_t row = row0 + r, k = k0 + 4 * pc;
+      const bool ok = row < nrows && k < ldd;
+      cp_async16(As[stage] + r * kDosLDA + 4 * pc, D + (uint64_t)(ok ? row : 0) * ldd + (ok ? k : 0), ok ? 16 : 0);
+    }
+    constexpr int BPIECES = LP / 2;
+    for (int idx = tid; idx < kDenseKC * BPIECES; idx += kDenseThreads) {
+      const int r = idx / BPIECES, pc = idx - r * BPIECES;
+      const uint32_t i = k0 + r;
+      const bool ok = i < ncols;
+      cp_async16(Bs[stage] + r * LDB + 2 * pc, Omg + (uint64_t)(ok ? i : 0) * LP + 2 * pc, ok ? 16 : 0);
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[u][n][0] = acc[u][n][1] = 0.0;
+
+  load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c + 1 < nchunks) load(c + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* A = As[st] + (warp * 16 + g) * kDosLDA + t;
+    const double* B = Bs[st] + t * LDB + g;
+#pragma unroll
+    for (int s = 0; s < kDenseKC / 4; ++s) {
+      const double a0 = dosage_value(A[4 * s], fj[0], sj[0]);
+      const double a1 = dosage_value(A[8 * kDosLDA + 4 * s], fj[1], sj[1]);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const double b = B[4 * s * LDB + 8 * n];
+        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+        dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t row = row0 + warp * 16 + 8 * u + g;
+    if (row < nrows) {
+      double* out = G + (uint64_t)row * LP + 2 * t;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<double2*>(out + 8 * n) = make_double2(acc[u][n][0], acc[u][n][1]);
+    }
+  }
+}
+
+// Hpart[split][i][c] = sum_{r in split} x(r, i) * G[r][c]; i = samples, r = variants of the range
+template <int NT>
+__global__ void __launch_bounds__(kDenseThreads)
+k_dos_h(const float* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t ncols, const double* __restrict__ F,
+        LutParams lp, const double* __restrict__ G, double* __restrict__ Hpart, uint32_t rows_per_split) {
+  using SM = DenseSmem<NT>;
+  constexpr int LP = SM::LP, LDB = SM::LDB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As[2];
+  double *Bs[2], *Fs[2];
+#pragma unroll
+  for (int st = 0; st < 2; ++st) {
+    unsigned char* base = smem_raw + st * SM::kDosStageH;
+    As[st] = reinterpret_cast<float*>(base);
+    Bs[st] = reinterpret_cast<double*>(base + SM::kDosA_H);
+    Fs[st] = Bs[st] + kDenseKC * LDB;  // [0, KC): F_r, [KC, 2KC): s_r
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t i0 = blockIdx.x * kDenseRows;
+  const uint32_t rbeg = blockIdx.y * rows_per_split;
+  const uint32_t rend = min(nrows, rbeg + rows_per_split);
+  const int nchunks = rend > rbeg ? (int)((rend - rbeg + kDenseKC - 1) / kDenseKC) : 0;
+
+  auto load = [&](int chunk, int stage) {
+    const uint32_t r0 = rbeg + (uint32_t)chunk * kDenseKC;
+    constexpr int APIECES = kDenseRows / 4;
+    for (int idx = tid; idx < kDenseKC * APIECES; idx += kDenseThreads) {
+      const int r = idx / APIECES, pc = idx - r * APIECES;
+      const uint32_t row = r0 + r, i = i0 + 4 * pc;
+      const bool ok = row < rend && i < ldd;
+      cp_async16(As[stage] + r * kDosLDT + 4 * pc, D + (uint64_t)(ok ? row : 0) * ldd + (ok ? i : 0), ok ? 16 : 0);
+    }
+    constexpr int BPIECES = LP / 2;
+    for (int idx = tid; idx < kDenseKC * BPIECES; idx += kDenseThreads) {
+      const int r = idx / BPIECES, pc = idx - r * BPIECES;
+      const uint32_t row = r0 + r;
+      const bool ok = row < rend;
+      cp_async16(Bs[stage] + r * LDB + 2 * pc, G + (uint64_t)(ok ? row : 0) * LP + 2 * pc, ok ? 16 : 0);
+    }
+    if (tid < kDenseKC) {  // plain stores: visible after the __syncthreads that follows the wait
+      const uint32_t row = r0 + tid;
+      const double f = row < rend ? F[row] : 0.0;
+      Fs[stage][tid] = f;
+      Fs[stage][kDenseKC + tid] = row < rend ? snp_scale(f, lp) : 0.0;
+    }
+  };
+
+  double acc[2][NT][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[u][n][0] = acc[u][n][1] = 0.0;
+
+  if (nchunks > 0) load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    if (c + 1 < nchunks) load(c + 1, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* A = As[st] + t * kDosLDT + warp * 16 + g;
+    const double* B = Bs[st] + t * LDB + g;
+    const double* Fc = Fs[st];
+#pragma unroll
+    for (int s = 0; s < kDenseKC / 4; ++s) {
+      const double f = Fc[4 * s + t], sc = Fc[kDenseKC + 4 * s + t];
+      const double a0 = dosage_value(A[4 * s * kDosLDT], f, sc);
+      const double a1 = dosage_value(A[4 * s * kDosLDT + 8], f, sc);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const double b = B[4 * s * LDB + 8 * n];
+        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+        dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  double* Hp = Hpart + (uint64_t)blockIdx.y * ncols * LP;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint32_t i = i0 + warp * 16 + 8 * u + g;
+    if (i < ncols) {
+      double* out = Hp + (uint64_t)i * LP + 2 * t;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        *reinterpret_cast<double2*>(out + 8 * n) = make_double2(acc[u][n][0], acc[u][n][1]);
+    }
+  }
+}
+
+// dense decode of dosage rows [start, start + nrows) -> col-major N x nrows doubles (Eigen layout
+// of data->G), for read_block parity checks (FileBgen.cpp:96-110)
+__global__ void k_dosage_decode(const float* __restrict__ D, uint32_t ldd, uint32_t N, uint64_t nrows,
+                                const double* __restrict__ F, LutParams lp, double* __restrict__ out) {
+  const uint64_t total = nrows * N;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = idx / N;
+    const uint32_t i = (uint32_t)(idx - r * N);
+    const double f = F[r];
+    out[idx] = dosage_value(D[r * ldd + i], f, snp_scale(f, lp));
   }
 }
 

@@ -55,6 +55,8 @@ struct pcaone_ctx {
   int source = -1;
   double* d_dense = nullptr;  // PCAONE_SRC_DENSE: tall orientation of a generic matrix, row-major [M][ldd]
   uint32_t ldd = 0;
+  float* d_dos = nullptr;     // PCAONE_SRC_DOSAGE: float dosages, row-major [M][ldf], NaN = missing
+  uint32_t ldf = 0;
   uint8_t* d_packed = nullptr;  // resident, M x pitch
   const uint8_t* h_packed = nullptr;
   pcaone_read_block_fn reader = nullptr;
@@ -610,6 +612,64 @@ void range_gemms_dense(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc,
   }
 }
 
+// ---------------------------------------------------------------- BGEN-style dosages (FileBgen.cpp:15-168)
+template <int NT>
+void dos_g_nt(pcaone_ctx* c, const float* D, uint32_t nrows, const double* F, double* G) {
+  const size_t smem = 2 * DenseSmem<NT>::kDosStageG;
+  static bool attr = false;
+  if (!attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_dos_g<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k_dos_g<NT><<<ceil_div(nrows, kDenseRows), kDenseThreads, smem, c->stream>>>(D, c->ldf, nrows, (uint32_t)c->N, F,
+                                                                                 c->lut, c->d_Omg, G);
+  PCA_CHECK_LAUNCH();
+}
+template <int NT>
+void dos_h_nt(pcaone_ctx* c, const float* D, uint32_t nrows, const double* F, const double* G, uint32_t splits,
+              uint32_t rps) {
+  const size_t smem = 2 * DenseSmem<NT>::kDosStageH;
+  static bool attr = false;
+  if (!attr) {
+    PCA_CUDA(cudaFuncSetAttribute(k_dos_h<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(ceil_div(c->N, kDenseRows), splits);
+  k_dos_h<NT><<<grid, kDenseThreads, smem, c->stream>>>(D, c->ldf, nrows, (uint32_t)c->N, F, c->lut, G, c->d_Hpart,
+                                                        rps);
+  PCA_CHECK_LAUNCH();
+}
+
+// variants [r0, r0 + nrows): G rows = X_b^T Omega ; Hacc (+)= X_b G_b with X decoded from float dosages
+void range_gemms_dosage(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc, bool accumulate) {
+  if (c->update && c->cfg.emu) throw std::runtime_error("--emu on a dosage source is not implemented");
+  const float* D = c->d_dos + r0 * c->ldf;
+  const double* F = c->d_F + r0;
+  double* G = c->d_G + r0 * c->lp;
+  {
+    Timed t(c, 0);
+    NT_DISPATCH(dos_g_nt, c, D, nrows, F, G);
+    c->tm.gemm_g_launches++;
+    c->tm.kernel_launches++;
+  }
+  const uint32_t tiles = ceil_div(c->N, kDenseRows);
+  uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
+  splits = std::min<uint32_t>(splits, c->max_splits);
+  splits = std::min<uint32_t>(splits, (uint32_t)ceil_div(nrows, kDenseKC));
+  const uint32_t rps = (uint32_t)round_up((size_t)ceil_div(nrows, splits), kDenseKC);
+  splits = ceil_div(nrows, rps);
+  {
+    Timed t(c, 1);
+    NT_DISPATCH(dos_h_nt, c, D, nrows, F, G, splits, rps);
+    const uint64_t count = c->N * c->lp;
+    k_reduce_partials<<<grid_for(count, 256, c->sms), 256, 0, c->stream>>>(c->d_Hpart, splits, count, Hacc,
+                                                                           accumulate ? 1 : 0);
+    PCA_CHECK_LAUNCH();
+    c->tm.gemm_h_launches++;
+    c->tm.kernel_launches += 2;
+  }
+}
+
 // G rows of the range = X^T Omega ; Hacc (+)= X G. `buf` = streamed block buffer holding P, or -1
 // when P points into the resident shard. Ranges without missing genotypes (and no EMU fill) run
 // on the int8 tensor-core kernels when the context was created with a PCAONE_PREC_INT8* mode.
@@ -618,6 +678,10 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
   if (nrows == 0) return;
   if (c->source == PCAONE_SRC_DENSE) {
     range_gemms_dense(c, snp0, nrows, Hacc, accumulate);
+    return;
+  }
+  if (c->source == PCAONE_SRC_DOSAGE) {
+    range_gemms_dosage(c, snp0, nrows, Hacc, accumulate);
     return;
   }
   // EMU update passes fill every missing entry with its own FP64 value: FP64 kernels
@@ -1293,9 +1357,9 @@ void dense_onepass(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder) {
   PCA_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// flip_UV(U, V, false), Utils.cpp:136-143. V rows may be sharded: the column maxima are then
-// combined on the host side by the caller-installed allreduce (sum of one-hot winners is not
-// expressible as a sum), so multi-GPU flips use the per-rank maxima gathered through d_scal.
+// flip_UV(U, V, false), Utils.cpp:136-143. V rows may be sharded: every rank then writes its
+// column maxima into its own slot of a zeroed buffer and the sum-allreduce hook acts as an
+// all-gather (k_flip_slot_write / k_flip_slot_pick).
 void flip_uv(pcaone_ctx* c) {
   uint64_t rpc = std::max<uint64_t>(256, (c->M + c->sms - 1) / c->sms);
   int nparts = (int)((c->M + rpc - 1) / rpc);
@@ -1306,7 +1370,17 @@ void flip_uv(pcaone_ctx* c) {
   PCA_CHECK_LAUNCH();
   k_colabsmax_final<<<1, 128, 0, c->stream>>>(pval, psgn, c->d_pidx, nparts, c->k, c->d_scal + 8, c->d_sign);
   PCA_CHECK_LAUNCH();
-  if (c->cfg.world > 1) throw std::runtime_error("flip_UV across SNP shards is not implemented yet");
+  if (c->cfg.world > 1) {
+    if (!c->allreduce) throw std::runtime_error("world > 1 but no allreduce hook installed");
+    double* slots = c->d_part;  // the partials above are consumed
+    k_flip_slot_write<<<1, 256, 0, c->stream>>>(c->d_scal + 8, c->d_sign, c->k, c->cfg.rank, c->cfg.world, slots);
+    PCA_CHECK_LAUNCH();
+    if (c->allreduce(c->allreduce_user, slots, (uint64_t)c->cfg.world * 2 * c->k, c->stream))
+      throw std::runtime_error("allreduce hook failed");
+    k_flip_slot_pick<<<1, 128, 0, c->stream>>>(slots, c->k, c->cfg.world, c->d_sign);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches += 2;
+  }
   k_scale_cols<<<grid_for(c->M * c->k, 256, c->sms), 256, 0, c->stream>>>(c->d_V, c->lp, c->k, c->M, c->d_sign);
   k_scale_cols<<<grid_for(c->N * c->k, 256, c->sms), 256, 0, c->stream>>>(c->d_U, c->lp, c->k, c->N, c->d_sign);
   PCA_CHECK_LAUNCH();
@@ -1619,7 +1693,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
-                  (void*)c->d_dense, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
+                  (void*)c->d_dense, (void*)c->d_dos, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -1739,16 +1813,19 @@ int pcaone_set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop
 
 int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
   CTX_GUARD(c, {
-    if (c->source != PCAONE_SRC_RESIDENT) throw std::runtime_error("permute_resident needs a resident shard");
+    if (c->source != PCAONE_SRC_RESIDENT && c->source != PCAONE_SRC_DOSAGE)
+      throw std::runtime_error("permute_resident needs a resident shard");
+    const bool dos = c->source == PCAONE_SRC_DOSAGE;
+    const uint32_t row_bytes = dos ? c->ldf * (uint32_t)sizeof(float) : c->pitch;  // both multiples of 16
     uint32_t* d_idx = nullptr;
     uint8_t* d_new = nullptr;
     double* d_Fn = nullptr;
     dmalloc(&d_idx, c->M);
-    dmalloc(&d_new, c->M * (size_t)c->pitch);
+    dmalloc(&d_new, c->M * (size_t)row_bytes);
     dmalloc(&d_Fn, c->M);
     PCA_CUDA(cudaMemcpyAsync(d_idx, indices, c->M * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    k_gather_rows<<<grid_for(c->M * (c->pitch >> 4), 256, c->sms), 256, 0, c->stream>>>(c->d_packed, d_new, d_idx, c->M,
-                                                                                       c->pitch);
+    k_gather_rows<<<grid_for(c->M * (row_bytes >> 4), 256, c->sms), 256, 0, c->stream>>>(
+        dos ? reinterpret_cast<const uint8_t*>(c->d_dos) : c->d_packed, d_new, d_idx, c->M, row_bytes);
     k_gather_f64<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, d_Fn, d_idx, c->M);
     PCA_CHECK_LAUNCH();
     PCA_CUDA(cudaStreamSynchronize(c->stream));
@@ -1757,11 +1834,14 @@ int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
     k_gather_u32<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_nmiss, d_nm, d_idx, c->M);
     PCA_CHECK_LAUNCH();
     PCA_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_packed);
+    cudaFree(dos ? (void*)c->d_dos : (void*)c->d_packed);
     cudaFree(c->d_F);
     cudaFree(c->d_nmiss);
     cudaFree(d_idx);
-    c->d_packed = d_new;
+    if (dos)
+      c->d_dos = reinterpret_cast<float*>(d_new);
+    else
+      c->d_packed = d_new;
     c->d_F = d_Fn;
     c->d_nmiss = d_nm;
     c->tiles_valid = false;
@@ -1778,6 +1858,14 @@ int pcaone_allele_freq(pcaone_ctx* c) {
                                                                              c->M, c->d_F, c->d_nmiss);
       PCA_CHECK_LAUNCH();
       c->tm.kernel_launches++;
+    } else if (c->source == PCAONE_SRC_DOSAGE) {
+      Timed t(c, 6);
+      k_dosage_af<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_dos, c->ldf, (uint32_t)c->N, c->M,
+                                                                          c->d_F, c->d_nmiss);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+    } else if (c->source == PCAONE_SRC_DENSE) {
+      throw std::runtime_error("allele_freq: a dense matrix has no allele frequencies");
     } else if (c->source >= 0) {
       if (c->blk_start.empty()) throw std::runtime_error("allele_freq on a streamed source needs pcaone_set_blocks");
       alloc_stream_buffers(c);
@@ -1843,6 +1931,21 @@ int pcaone_decode_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int standa
   CTX_GUARD(c, {
     if (stop < start || stop >= c->M) throw std::runtime_error("decode_block: range out of bounds");
     const uint64_t B = stop - start + 1;
+    if (c->source == PCAONE_SRC_DOSAGE) {  // FileBgen::read_block_initial, FileBgen.cpp:96-110
+      if (!c->af_done) throw std::runtime_error("decode_block: call pcaone_allele_freq first");
+      if (update && c->cfg.emu) throw std::runtime_error("--emu on a dosage source is not implemented");
+      LutParams p = c->lut;
+      p.standardize = (standardize && c->cfg.scale == -9) ? 1 : 0;
+      ensure_stage(c, c->N * B);
+      k_dosage_decode<<<grid_for(c->N * B, 256, c->sms), 256, 0, c->stream>>>(c->d_dos + start * c->ldf, c->ldf,
+                                                                             (uint32_t)c->N, B, c->d_F + start, p,
+                                                                             c->d_stage);
+      PCA_CHECK_LAUNCH();
+      PCA_CUDA(cudaMemcpyAsync(out, c->d_stage, c->N * B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    if (c->source == PCAONE_SRC_DENSE) throw std::runtime_error("decode_block: not a genotype source");
     const uint8_t* P;
     if (c->source == PCAONE_SRC_RESIDENT) {
       P = c->d_packed + start * c->pitch;
@@ -1992,6 +2095,24 @@ int pcaone_upload_dense(pcaone_ctx* c, const double* A, uint64_t rows, uint64_t 
     PCA_CUDA(cudaStreamSynchronize(c->stream));
     c->tm.h2d_bytes += c->M * c->N * sizeof(double);
     c->source = PCAONE_SRC_DENSE;
+  });
+}
+
+int pcaone_upload_dosage(pcaone_ctx* c, const float* dosage, uint64_t nsnps, int device_ptr) {
+  CTX_GUARD(c, {
+    if (nsnps != c->M) throw std::runtime_error("upload_dosage: nsnps does not match the context");
+    if (c->cfg.precision != PCAONE_PREC_FP64) throw std::runtime_error("upload_dosage: the dosage source runs in FP64");
+    if (c->cfg.emu) throw std::runtime_error("--emu on a dosage source is not implemented");
+    c->ldf = (uint32_t)round_up(c->N, 8);
+    if (!c->d_dos) dmalloc(&c->d_dos, c->M * (size_t)c->ldf);
+    PCA_CUDA(cudaMemsetAsync(c->d_dos, 0, c->M * (size_t)c->ldf * sizeof(float), c->stream));
+    PCA_CUDA(cudaMemcpy2DAsync(c->d_dos, (size_t)c->ldf * sizeof(float), dosage, c->N * sizeof(float),
+                               c->N * sizeof(float), c->M, device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    if (!device_ptr) c->tm.h2d_bytes += c->M * c->N * sizeof(float);
+    c->source = PCAONE_SRC_DOSAGE;
+    c->af_done = false;
   });
 }
 

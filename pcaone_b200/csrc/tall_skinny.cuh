@@ -283,6 +283,30 @@ __global__ void k_colabsmax_final(const double* __restrict__ pval, const double*
     out_sgn[c] = sg;
   }
 }
+// SNP-sharded flip_UV: every rank writes (|v|max, sign) of its shard into ITS slot of a zeroed
+// [world][2k] buffer; a sum-allreduce then acts as an all-gather; the winner per column is the
+// largest |v|, lowest rank on ties (contiguous shards: lowest rank = lowest SNP index, the
+// first-occurrence rule of maxCoeff, Utils.cpp:138-139).
+__global__ void k_flip_slot_write(const double* __restrict__ val, const double* __restrict__ sgn, int k, int rank,
+                                  int world, double* __restrict__ slots) {
+  for (int i = threadIdx.x; i < world * 2 * k; i += blockDim.x) {
+    const int r = i / (2 * k), c = i - r * 2 * k;
+    slots[i] = (r != rank) ? 0.0 : (c < k ? val[c] : sgn[c - k]);
+  }
+}
+__global__ void k_flip_slot_pick(const double* __restrict__ slots, int k, int world, double* __restrict__ out_sgn) {
+  for (int c = threadIdx.x; c < k; c += blockDim.x) {
+    double best = -1.0, sg = 1.0;
+    for (int r = 0; r < world; ++r) {
+      const double v = slots[r * 2 * k + c];
+      if (v > best) {
+        best = v;
+        sg = slots[r * 2 * k + k + c];
+      }
+    }
+    out_sgn[c] = sg;
+  }
+}
 __global__ void k_scale_cols(double* __restrict__ A, int ld, int k, uint64_t rows, const double* __restrict__ sign) {
   const uint64_t total = rows * k;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {

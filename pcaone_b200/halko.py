@@ -61,6 +61,7 @@ class Param:
     rand: int = 1               # --rand
     no_shuffle: bool = False    # -S
     emu: bool = False           # --emu
+    maf: float = 0.0            # --maf
     maxiter: int = 100          # --maxiter
     tolem: float = 1e-5         # --tol-em
     scale: int = -9             # -C
@@ -188,6 +189,44 @@ class FileBed:
             self.packed = np.ascontiguousarray(np.asarray(self._load_packed())[self.perm])
 
 
+class FileBgen:
+    """`Data` for BGEN input, in-core (src/FileBgen.cpp:15-72). The container parsing stays on the
+    host side of the boundary: this class takes what `var.minor_allele_dosage()` yields for every
+    variant — `dosages`, float32 [nsnps][nsamples], NaN = missing — and applies the `--maf` filter
+    of FileBgen.cpp:42-45 once the device has computed the allele frequencies. Decode, mean
+    imputation, centring and scaling are fused into the GEMM operand load on the device."""
+
+    def __init__(self, params: Param, dosages):
+        self.params = params
+        if params.out_of_core:
+            raise RuntimeError("FileBgen: only the in-core path (read_all) is mirrored")
+        if params.precision != _lib.PREC_FP64:
+            raise RuntimeError("FileBgen: dosages run on the FP64 kernels (precision = PREC_FP64)")
+        self.dosages = dosages.contiguous() if _is_torch(dosages) else np.ascontiguousarray(dosages, dtype=np.float32)
+        self.nsnps, self.nsamples = int(self.dosages.shape[0]), int(self.dosages.shape[1])
+        self.packed = None
+        self.perm = None
+        self.start = self.stop = None
+        self.nblocks, self.blocksize, self.bandFactor = 1, 0, 1
+        self.keep = None
+
+    def prepare(self):
+        """Variant selection of FileBgen.cpp:42-45: a variant is kept iff af > params.maf (so even
+        with the default --maf 0 an all-zero variant is dropped). Only the SELECTION happens here;
+        the allele frequencies the path uses are computed on the device (pcaone_allele_freq)."""
+        d = self.dosages.cpu().numpy() if _is_torch(self.dosages) else self.dosages
+        with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            af = np.nanmean(d.astype(np.float64) / 2.0, axis=1)
+        keep = np.flatnonzero(np.nan_to_num(af) > self.params.maf)
+        if len(keep) == 0:
+            raise RuntimeError("the number of SNPs after filtering is 0!")
+        if len(keep) != self.nsnps:
+            self.keep = keep
+            self.dosages = np.ascontiguousarray(d[keep])
+            self.nsnps = len(keep)
+
+
 class RsvdOpData:
     """Abstract op (src/Halko.hpp:6-42). Subclasses pick the computeGandH variant."""
     svd = None
@@ -216,7 +255,11 @@ class RsvdOpData:
             cb = _lib.ALLREDUCE_FN(allreduce)
             self._keep.append(cb)
             self._chk(L.pcaone_set_allreduce(self.h, cb, None))
-        if p.out_of_core:
+        if getattr(data, "dosages", None) is not None:
+            on_dev = _is_torch(data.dosages) and data.dosages.is_cuda
+            self._chk(L.pcaone_upload_dosage(self.h, _vp(data.dosages), data.nsnps, int(on_dev)))
+            self._chk(L.pcaone_allele_freq(self.h))
+        elif p.out_of_core:
             if data.packed is not None:
                 self._chk(L.pcaone_set_host_source(self.h, _vp(data.packed), data.nsnps))
             else:

@@ -18,9 +18,9 @@ from pcaone_b200 import dist as pdist  # noqa: E402
 from pcaone_b200 import halko, synth  # noqa: E402
 
 
-def run(svd, packed, N, k, bands, maxp, rank, world, local, hook):
+def run(svd, packed, N, k, bands, maxp, rank, world, local, hook, emu=False):
     M = packed.shape[0]
-    p = halko.Param(k=k, svd=svd, bands=bands, maxp=maxp, tol=0.0, no_shuffle=True, device=local)
+    p = halko.Param(k=k, svd=svd, bands=bands, maxp=maxp, tol=0.0, no_shuffle=True, device=local, emu=emu, maxiter=3)
     if svd == 2:
         idx, start, stop = pdist.shard_windows(M, bands, rank, world)
     else:
@@ -30,8 +30,11 @@ def run(svd, packed, N, k, bands, maxp, rank, world, local, hook):
     d.start, d.stop = start, stop
     cls = halko.FancyRsvdOpData if svd == 2 else halko.NormalRsvdOpData
     op = cls(d, p.k, p.oversamples, rank=rank, world=world, nsnps_total=M, allreduce=hook)
-    op.setFlags(False, True)
-    op.computeUSV(maxp, 0.0)
+    if emu:
+        op.runEM()   # Halko.cpp:290-319: includes flip_UV across the SNP shards after every computeUSV
+    else:
+        op.setFlags(False, True)
+        op.computeUSV(maxp, 0.0)
     return op, idx
 
 
@@ -41,16 +44,22 @@ def main():
     N, M, k = 900, 12800, 6
     packed = np.concatenate([synth.pack_codes(c) for _, c in synth.balding_nichols_codes(N, M, k_pop=8, seed=9)])
     hook = pdist.make_allreduce_hook()
-    for svd, bands, maxp in ((1, 64, 4), (2, 16, 6)):
-        op, idx = run(svd, packed, N, k, bands, maxp, rank, world, local, hook)
+    packed_m = np.concatenate([synth.pack_codes(c)
+                               for _, c in synth.balding_nichols_codes(N, M, k_pop=8, seed=10, miss=0.05)])
+    for svd, bands, maxp, emu in ((1, 64, 4, False), (2, 16, 6, False), (1, 64, 3, True)):
+        if emu:
+            packed = packed_m
+        op, idx = run(svd, packed, N, k, bands, maxp, rank, world, local, hook, emu)
         Vfull = torch.zeros((M, k), dtype=torch.float64, device=f"cuda:{local}")
         Vfull[torch.from_numpy(idx).to(Vfull.device)] = torch.from_numpy(np.ascontiguousarray(op.V)).to(Vfull.device)
         dist.all_reduce(Vfull)
         if rank == 0:
-            ref_op, _ = run(svd, packed, N, k, bands, maxp, 0, 1, local, None)
+            ref_op, _ = run(svd, packed, N, k, bands, maxp, 0, 1, local, None, emu)
             assert_usv_close(op.U, op.S, Vfull.cpu().numpy(), ref_op.U, ref_op.S, ref_op.V, eig_rtol=1e-9,
                              min_corr=1 - 1e-9)
-            print(f"svd={svd} world={world}: sharded == single GPU; S rel err",
+            if emu:  # flip_UV fixed the signs: compare without sign alignment
+                assert np.abs(op.U - ref_op.U).max() < 1e-8
+            print(f"svd={svd} emu={emu} world={world}: sharded == single GPU; S rel err",
                   float(np.max(np.abs(op.S - ref_op.S) / ref_op.S)), flush=True)
             ref_op.close()
         op.close()
