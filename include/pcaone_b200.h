@@ -160,6 +160,13 @@ int pcaone_shuffle_indices(uint64_t n, uint32_t* out);
 int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
                  uint64_t nwin, double* r2_out);
 
+/* ---- IRAM operator: ArnoldiOpData::perform_op (Arnoldi.cpp:18-46, Arnoldi.hpp:6-34) ---------
+ * y = sum over blocks G_b (G_b^T x): x_in, y_out are nsamples doubles on the host (what Spectra's
+ * SymEigsSolver hands to perform_op). Uses the context's source (resident, streamed blocks,
+ * dosages), allele frequencies and the pcaone_set_flags state (update => EMU fill from
+ * pcaone_set_usv); a context with k = 1, oversamples = 0 makes it a GEMV-shaped pass. */
+int pcaone_perform_op(pcaone_ctx* ctx, const double* x_in, double* y_out);
+
 /* ---- BGEN-style dosages (FileBgen::read_all / read_block_initial, FileBgen.cpp:15-168) ----------
  * The host keeps the container parsing (`var.minor_allele_dosage`, FileBgen.cpp:26) and hands over
  * what that call yields: one row of nsamples floats per variant, NaN = missing, SNP-major

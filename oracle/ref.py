@@ -186,6 +186,13 @@ class Ref:
     def standardize_E(self):
         self._chk(lib().ref_standardize_E(self.h))
 
+    def perform_op(self, x, update=False, standardize=True):
+        """ArnoldiOpData(data).perform_op(x) on this (out-of-core) run -> y (N)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        self._chk(lib().ref_perform_op(self.h, int(update), int(standardize), _p(x), _p(y)))
+        return y
+
     def ld_r2(self, filebim, ld_bp):
         nwin = C.c_longlong(0)
         n = lib().ref_ld_r2(self.h, filebim.encode(), int(ld_bp), None, C.c_longlong(0), None, None,

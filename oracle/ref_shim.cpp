@@ -17,6 +17,7 @@
 //   PCAone::flipOmg  (src/RSVD.hpp:80)
 //   calc_sds / divide_pos_by_window (src/LD.cpp:48,154)
 //   PCAone::RsvdOne  (src/RSVD.hpp:327-362, the dense-matrix front-end PCAoneR binds)
+//   ArnoldiOpData::perform_op (src/Arnoldi.cpp:18-46, the IRAM operator)
 #define _DECLARE_TOOLBOX_HERE
 #include <omp.h>
 
@@ -31,6 +32,7 @@
 #include "Data.hpp"
 #include "FileBinary.hpp"
 #include "FilePlink.hpp"
+#include "Arnoldi.hpp"
 #include "Halko.hpp"
 #include "LD.hpp"
 #include "RSVD.hpp"
@@ -413,6 +415,16 @@ long long ref_ld_r2(void* h, const char* filebim, int ld_bp, double* out, long l
 int ref_write_residuals(void* h) {
   RefCtx* c = (RefCtx*)h;
   return guarded([&] { c->data->write_residuals(c->op->S, c->op->U, c->op->V.transpose()); });
+}
+
+// ArnoldiOpData::perform_op (Arnoldi.cpp:18-46) on an out-of-core run: y = sum_b G_b G_b^T x.
+int ref_perform_op(void* h, int update, int standardize, const double* x, double* y) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    ArnoldiOpData op(c->data);
+    op.setFlags(update, standardize);
+    op.perform_op(x, y);
+  });
 }
 
 // PCAone::RsvdOne<MatrixXd> (RSVD.hpp:327-362) on a dense column-major matrix: the reference's own

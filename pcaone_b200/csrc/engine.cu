@@ -878,6 +878,7 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
   static int prof_left = getenv("PCAONE_ORTH_PROF") ? atoi(getenv("PCAONE_ORTH_PROF")) : 0;
   if (prof_left > 0) {
     if (!d_prof) PCA_CUDA(cudaMalloc((void**)&d_prof, 64 * sizeof(unsigned long long)));
+    PCA_CUDA(cudaMemsetAsync(d_prof, 0, 64 * sizeof(unsigned long long), c->stream));
     a.prof = d_prof;
   }
   if ((size_t)c->sms * c->l * c->lp > c->part_doubles) throw std::runtime_error("partial workspace too small");
@@ -891,11 +892,12 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
   }
   if (prof_left > 0) {
     --prof_left;
-    unsigned long long h[32];
+    unsigned long long h[64];
     PCA_CUDA(cudaStreamSynchronize(c->stream));
     PCA_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
     fprintf(stderr, "orth_fused rows=%llu phases(us):", (unsigned long long)rows);
-    for (int i = 1; i < 18; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[i - 1]) * 1e-3);
+    const int np = (int)std::min<unsigned long long>(h[63], 62);
+    for (int i = 1; i < np; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[i - 1]) * 1e-3);
     fprintf(stderr, "\n");
   }
 }
@@ -1281,6 +1283,54 @@ void compute_usv(pcaone_ctx* c, int p, double tol) {
   c->last_diff = diff;
   c->last_epochs = epochs;
   PCA_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// ArnoldiOpData::perform_op (Arnoldi.cpp:18-46): y = sum over blocks G_b (G_b^T x), the operator the
+// IRAM solver (Spectra) iterates. One decode + GEMM pass with x in column 0 of Omega; the current
+// update / standardize flags apply exactly as in computeGandH.
+void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
+  if (c->source < 0) throw std::runtime_error("no genotype source set");
+  const bool ooc = c->source == PCAONE_SRC_HOST || c->source == PCAONE_SRC_FILE;
+  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("perform_op(update) without U,S,V");
+  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
+  const uint64_t HN = c->N * c->lp;
+  ensure_stage(c, c->N);
+  PCA_CUDA(cudaMemcpyAsync(c->d_stage, x_in, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  zero_async(c, c->d_Omg, HN);
+  PCA_CUDA(cudaMemcpy2DAsync(c->d_Omg, (size_t)c->lp * sizeof(double), c->d_stage, sizeof(double), sizeof(double), c->N,
+                             cudaMemcpyDeviceToDevice, c->stream));
+  c->omega_img_valid = false;
+  if (!ooc) {
+    if (!c->af_done && c->source != PCAONE_SRC_DENSE) throw std::runtime_error("call pcaone_allele_freq first");
+    if (c->blk_start.empty()) {
+      range_gemms(c, c->d_packed, (uint32_t)c->M, 0, c->d_H, false, -1);
+    } else {
+      zero_async(c, c->d_H, HN);
+      for (size_t b = 0; b < c->blk_start.size(); ++b)
+        range_gemms(c, c->d_packed + c->blk_start[b] * c->pitch, (uint32_t)(c->blk_stop[b] - c->blk_start[b] + 1),
+                    c->blk_start[b], c->d_H, true, -1);
+    }
+  } else {
+    if (c->blk_start.empty()) throw std::runtime_error("out-of-core source needs pcaone_set_blocks");
+    alloc_stream_buffers(c);
+    zero_async(c, c->d_H, HN);
+    for (uint32_t b = 0; b < c->blk_start.size(); ++b) {
+      const int buf = b & 1;
+      const uint8_t* P = stage_block(c, b, buf);
+      const uint64_t nrows = c->blk_stop[b] - c->blk_start[b] + 1;
+      block_af_if_needed(c, P, c->blk_start[b], nrows);
+      range_gemms(c, P, (uint32_t)nrows, c->blk_start[b], c->d_H, true, buf);
+      PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
+    }
+    c->af_done = true;
+  }
+  allreduce_H(c, c->d_H);
+  PCA_CUDA(cudaMemcpy2DAsync(c->d_stage, sizeof(double), c->d_H, (size_t)c->lp * sizeof(double), sizeof(double), c->N,
+                             cudaMemcpyDeviceToDevice, c->stream));
+  PCA_CUDA(cudaMemcpyAsync(y_out, c->d_stage, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaStreamSynchronize(c->stream));
+  c->tm.h2d_bytes += c->N * sizeof(double);
+  c->tm.d2h_bytes += c->N * sizeof(double);
 }
 
 // RsvdOpOnePass::computeGandH (RSVD.hpp:137-166 plain, :168-252 windows) followed by
@@ -2097,6 +2147,8 @@ int pcaone_upload_dense(pcaone_ctx* c, const double* A, uint64_t rows, uint64_t 
     c->source = PCAONE_SRC_DENSE;
   });
 }
+
+int pcaone_perform_op(pcaone_ctx* c, const double* x_in, double* y_out) { CTX_GUARD(c, perform_op(c, x_in, y_out)); }
 
 int pcaone_upload_dosage(pcaone_ctx* c, const float* dosage, uint64_t nsnps, int device_ptr) {
   CTX_GUARD(c, {

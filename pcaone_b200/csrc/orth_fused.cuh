@@ -71,7 +71,7 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
   // entry): Y[j][:] = B[j][:] / L[j][j], B[r][:] -= L[r][j] Y[j][:] for r > j, and T = R^-1 = Y^T.
   // (A separate back substitution, one thread per column, was a serial chain of ~l^2/2 dependent
   // shared-memory FMAs: half of this phase.)
-  __shared__ double s_row[2][16 * R], s_brow[2][16 * R];
+  __shared__ double s_row[2][16 * R], s_brow[2][16 * R], s_piv[16 * R];
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -112,8 +112,12 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
       fail = true;
       break;
     }
-    const double invd = 1.0 / d;
-    if (tid <= j) Ts[tid * lc + j] = s_brow[b][tid] * (1.0 / sqrt(d));  // column j of T = row j of Y
+    // 1/d is on the serial path of every step: __drcp_rn is the same correctly rounded reciprocal
+    // as 1.0 / d without the generic division sequence; the 1/sqrt(d) scaling of column j of T is
+    // deferred to one parallel pass after the loop (s_piv)
+    const double invd = __drcp_rn(d);
+    if (tid <= j) Ts[tid * lc + j] = s_brow[b][tid];  // column j of T = row j of Y, still times sqrt(d_j)
+    if (tid == 0) s_piv[j] = d;
     double rr[R], rc[R], bc[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) rr[i] = s_row[b][ty + 16 * i] * invd;
@@ -134,6 +138,13 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
   if (fail && tid == 0) s_fail = 1;
   __syncthreads();
   if (!s_fail) {
+    if (tid < l) s_piv[tid] = 1.0 / sqrt(s_piv[tid]);
+    __syncthreads();
+    for (int i = tid; i < l * lc; i += nt) {
+      const int c = i % lc;
+      if (c < l) Ts[i] *= s_piv[c];
+    }
+    __syncthreads();
     for (int i = tid; i < l * ld; i += nt) {
       const int r = i / ld, c = i - r * ld;
       T[i] = c < l ? Ts[r * lc + c] : 0.0;
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
 
   int prof_i = 0;
   auto stamp = [&]() {
-    if (a.prof && blockIdx.x == 0 && tid == 0) {
+    if (a.prof && blockIdx.x == 0 && tid == 0 && prof_i < 62) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
       a.prof[prof_i] = t;
@@ -437,6 +448,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
   if (blockIdx.x == 0) {
     orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
+    stamp();
     if (a.Ttot) {
       for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
         const int r = idx / lp, c = idx - r * lp;
@@ -472,6 +484,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       }
       (void)r1_save;
       __syncthreads();
+      stamp();
       // sign-modified LU replay of the Householder sign decisions (see k_householder_signs), with
       // the l x l block in registers: per step the owners publish row i and column i, one barrier
       __shared__ double s_lr[2][16 * R], s_lc[2][16 * R];
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         const double c0 = s_lr[b][i0];
         const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
         if (tid == 0) a.hsign[i0] = beta;
-        const double inv = 1.0 / (c0 - beta);
+        const double inv = __drcp_rn(c0 - beta);  // == 1.0 / (c0 - beta), correctly rounded
         double cr[R], rc[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) cr[i] = s_lc[b][ty + 16 * i] * inv;
@@ -542,16 +555,34 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = 0.0;
   zero_pad_cols();
   prefetch(r0);
+  stamp();
   for (uint64_t r = r0; r < r1; r += TR) {
     __syncthreads();
     commit_tile();
     prefetch(r + TR);
     __syncthreads();
+    stamp();
+    // Omega2 of this tile first: the loads fly while the two products run (issued one by one
+    // between the stores below they were a chain of dependent L2 round trips, ~8 us per tile)
+    double o2[RI][R];
+    if (a.want_flip) {
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const uint64_t row = r + ty + 16 * i;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int c = tx + 16 * j;
+          o2[i][j] = (row < r1 && c < l) ? a.Q2[row * lp + c] : 0.0;
+        }
+      }
+    }
     double q[RI][R];
     tile_times_T(As, T1s, q);
     store_tile(Qs, q);
     __syncthreads();
+    stamp();
     tile_times_T(Qs, T2s, q);
+    stamp();
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
       const uint64_t row = r + ty + 16 * i;
@@ -562,9 +593,8 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
           if (c < lp) {
             const double qv = c < l ? q[i][j] * hs[j] : 0.0;
             if (a.want_flip && c < l) {
-              const double o2 = a.Q2[row * lp + c];
-              dsum[j] += fabs(o2 - qv);
-              ssum[j] += fabs(o2 + qv);
+              dsum[j] += fabs(o2[i][j] - qv);
+              ssum[j] += fabs(o2[i][j] + qv);
             }
             a.Q[row * lp + c] = qv;
           }
@@ -601,7 +631,13 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   __syncthreads();
   for (int c = tid; c < 2 * l; c += kOrthThreads) {
     double v = 0.0;
-    for (unsigned p = 0; p < gridDim.x; ++p) v += a.part[(size_t)p * pstride + c];
+    for (unsigned p0 = 0; p0 < gridDim.x; p0 += 16) {  // 16 independent loads, then the adds in CTA order
+      double t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = (p0 + u < gridDim.x) ? a.part[(size_t)(p0 + u) * pstride + c] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v += t[u];
+    }
     Qs[c] = v;
   }
   __syncthreads();
@@ -612,14 +648,27 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   __syncthreads();
   const uint64_t total = (r1 - r0) * (uint64_t)lp;
-  for (uint64_t i = tid; i < total; i += kOrthThreads) {
-    const int c = (int)(i % lp);
-    double v = a.Q[r0 * lp + i];
-    if (c < l) v *= As[c];
-    a.Q[r0 * lp + i] = v;
-    a.Q2[r0 * lp + i] = v;
+  constexpr int PB = 8;  // loads of a batch are issued before the first store (independent round trips)
+  for (uint64_t i0 = tid; i0 < total; i0 += (uint64_t)kOrthThreads * PB) {
+    double v[PB];
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
+      v[b] = i < total ? a.Q[r0 * lp + i] : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
+      if (i < total) {
+        const int c = (int)(i % lp);
+        const double w = c < l ? v[b] * As[c] : v[b];
+        a.Q[r0 * lp + i] = w;
+        a.Q2[r0 * lp + i] = w;
+      }
+    }
   }
   stamp();
+  if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[63] = (unsigned long long)prof_i;
 }
 
 }  // namespace pcaone

@@ -51,7 +51,7 @@ class Param:
     filein: str = ""            # -b/--bfile
     fileout: str = "pcaone"     # -o
     k: int = 10                 # -k
-    svd: int = 2                # -d/--svd (1: sSVD, 2: winSVD)
+    svd: int = 2                # -d/--svd (1: sSVD, 2: winSVD; 0: IRAM — only its block plan and operator)
     memory: float = 0.0         # -m GB; > 0 => out_of_core
     maxp: int = 20              # --maxp
     oversamples: int = 10       # --oversamples
@@ -76,8 +76,8 @@ class Param:
     ploidy: int = field(init=False, default=2)
 
     def __post_init__(self):
-        if self.svd not in (1, 2):
-            raise ValueError("only --svd 1 (sSVD) and 2 (winSVD) are on the GPU path")
+        if self.svd not in (0, 1, 2):
+            raise ValueError("only --svd 1 (sSVD), 2 (winSVD) and the operator of 0 (IRAM) are on the GPU path")
         if self.bands < 4 or self.bands % 2 != 0:
             raise ValueError("the -w/--batches must be a power of 2 and the minimun is 4.")
         self.oversamples = max(self.oversamples, self.k)
@@ -90,12 +90,16 @@ class Param:
         return self.k + self.oversamples
 
 
-def ooc_block_plan(N, M, l, memory_gb, winsvd, bands):
-    """Data::prepare, out-of-core branch (src/Data.cpp:42-84)."""
-    m = float(3 * N * l + 2 * M * l + 5 * M) / 134217728
-    if memory_gb > 1.1 * m:
-        m = 0.0
-    blocksize = int(math.ceil(((m + memory_gb) * 134217728 - 3 * N * l - 2 * M * l - 5 * M) / N))
+def ooc_block_plan(N, M, l, memory_gb, winsvd, bands, iram=False):
+    """Data::prepare, out-of-core branch (src/Data.cpp:42-84). `iram`: --svd 0, whose working set
+    is only the N x blocksize block (src/Data.cpp:42-44)."""
+    if iram:
+        blocksize = int(math.ceil(memory_gb * 134217728 / N))
+    else:
+        m = float(3 * N * l + 2 * M * l + 5 * M) / 134217728
+        if memory_gb > 1.1 * m:
+            m = 0.0
+        blocksize = int(math.ceil(((m + memory_gb) * 134217728 - 3 * N * l - 2 * M * l - 5 * M) / N))
     nblocks = int(math.ceil(M / blocksize))
     band_factor = 1
     if nblocks == 1:
@@ -182,7 +186,7 @@ class FileBed:
             self._load_packed()
             return
         self.blocksize, self.nblocks, self.bandFactor, self.start, self.stop = ooc_block_plan(
-            self.nsamples, self.nsnps, p.l, p.memory, p.svd == 2, p.bands)
+            self.nsamples, self.nsnps, p.l, p.memory, p.svd == 2, p.bands, iram=p.svd == 0)
         if p.perm:
             # permute_plink writes <out>.perm.bed; here the rows are permuted in host memory
             self.perm = permute_plink_indices(self.nsnps, self.nsamples, p.bands, p.buffer)
@@ -425,9 +429,30 @@ class FancyRsvdOpData(RsvdOpData):
     svd = _lib.SVD_WINSVD
 
 
+class ArnoldiOpData(NormalRsvdOpData):
+    """src/Arnoldi.hpp:6-34: the operator Spectra's SymEigsSolver iterates, y = G G^T x accumulated
+    over the blocks of the plan (src/Arnoldi.cpp:18-46). Only the operator is mirrored — the IRAM
+    driver itself (Spectra) is host code that stays in PCAone. Built on a context with l = 1."""
+
+    def __init__(self, data, **kw):
+        super().__init__(data, 1, 0, **kw)
+        self.nops = 1
+
+    def perform_op(self, x_in, y_out=None):
+        x = np.ascontiguousarray(x_in, dtype=np.float64)
+        if x.shape != (self.cols(),):
+            raise ValueError("x must have nsamples entries")
+        y = np.zeros(self.cols()) if y_out is None else y_out
+        self._chk(self.L.pcaone_perform_op(self.h, _vp(x), _vp(y)))
+        self.nops += 1
+        return y
+
+
 def run_pca_with_halko(data: FileBed, params: Param, **kw):
     """src/Halko.cpp:271-345 without the file writers: returns the op with U, S, V set
     (eigenvalues are S**2 / nsnps as written at :339)."""
+    if params.svd == 0:
+        raise RuntimeError("--svd 0: only ArnoldiOpData.perform_op is on the GPU; the IRAM driver (Spectra) is host code")
     cls = FancyRsvdOpData if params.svd == 2 else NormalRsvdOpData
     rsvd = cls(data, params.k, params.oversamples, **kw)
     if not params.emu:

@@ -145,6 +145,13 @@ def main():
             U, S, V = ref.rsvd_one(A, 4, 6, 1, p=p_, windows=w_)
             out[f"{name}_p{p_}_w{w_}_U"], out[f"{name}_p{p_}_w{w_}_S"], out[f"{name}_p{p_}_w{w_}_V"] = U, S, V
     np.savez_compressed(os.path.join(OUT, "rsvd_one.npz"), **out)
+    # ---- H: IRAM operator ArnoldiOpData::perform_op (Arnoldi.cpp:18-46) on the out-of-core plan
+    r = ref.Ref(f"PCAone -b {bed} -k {K} -d 0 -m 0.00012 -o {tmp}/h -n 1", threads=thr)
+    s3, e3 = r.block_plan()
+    xa = np.random.default_rng(4).standard_normal(N)
+    np.savez_compressed(os.path.join(OUT, "arnoldi_op.npz"), x=xa, y_std=r.perform_op(xa, False, True),
+                        y_raw=r.perform_op(xa, False, False), start=s3, stop=e3, memory=0.00012)
+    r.close()
     print("golden written to", OUT)
 
 

@@ -208,3 +208,13 @@ def test_rsvd_one_restatement_argument_checks():
         orc.rsvd_one(A, 3, 3, om, 1, 4)      # 2^p >= windows
     with pytest.raises(RuntimeError):
         orc.rsvd_one(A, 3, 3, om, 4, 16)     # block smaller than the number of windows
+
+
+def test_perform_op_restatement_vs_reference():
+    """oracle.perform_op against ArnoldiOpData::perform_op of the unmodified reference."""
+    g, a = golden("ssvd_small"), golden("arnoldi_op")
+    od = orc.OracleData(g["packed"], int(g["N"]))
+    blocks = list(zip(a["start"], a["stop"]))
+    for std, key in ((True, "y_std"), (False, "y_raw")):
+        y = orc.perform_op(od, a["x"], blocks, std)
+        assert np.abs(y - a[key]).max() <= 1e-13 * np.abs(a[key]).max()
