@@ -192,6 +192,13 @@ int pcaone_upload_dosage(pcaone_ctx* ctx, const float* dosage, uint64_t nsnps, i
 int pcaone_upload_dense(pcaone_ctx* ctx, const double* A, uint64_t rows, uint64_t cols);
 int pcaone_dense_rsvd(pcaone_ctx* ctx, uint32_t p, uint32_t windows, int finder);
 
+/* LD pruning (ld_prune_big, LD.cpp:240-268 — SURVEY 8f-2): the same banded r2 tiles, kept on the
+ * device and consumed by a greedy kernel that walks the windows in lead order. af: per-SNP allele
+ * frequency (7th column of the .mbim) or NULL = always prune the partner; keep_out: nsnps bytes,
+ * 1 = kept (what write_pruned_snp_ids splits into .ld.prune.in / .ld.prune.out). */
+int pcaone_ld_prune(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
+                    uint64_t nwin, const double* af, double r2_tol, uint8_t* keep_out);
+
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct pcaone_timers {
   double gemm_g_ms, gemm_h_ms, orth_ms, small_ms, h2d_ms, allreduce_ms, decode_ms;

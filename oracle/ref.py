@@ -186,6 +186,13 @@ class Ref:
     def standardize_E(self):
         self._chk(lib().ref_standardize_E(self.h))
 
+    def ld_prune(self, filebim, ld_bp, r2_tol, fileout):
+        """ld_prune_big on data->G (LD.cpp:240-268) -> boolean keep mask."""
+        keep = np.zeros(int(self.M), dtype=np.uint8)
+        self._chk(lib().ref_ld_prune(self.h, filebim.encode(), int(ld_bp), C.c_double(r2_tol), fileout.encode(),
+                                     _p(keep), C.c_longlong(int(self.M))))
+        return keep.astype(bool)
+
     def perform_op(self, x, update=False, standardize=True):
         """ArnoldiOpData(data).perform_op(x) on this (out-of-core) run -> y (N)."""
         x = np.ascontiguousarray(x, dtype=np.float64)

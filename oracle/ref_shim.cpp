@@ -22,6 +22,7 @@
 #include <omp.h>
 
 #include <chrono>
+#include <fstream>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -409,6 +410,48 @@ long long ref_ld_r2(void* h, const char* filebim, int ld_bp, double* out, long l
     }
   });
   return rc ? -1 : n;
+}
+
+// ld_prune_big (LD.cpp:240-268) on data->G with the windows of divide_pos_by_window; the keep mask
+// is recovered from the reference's own writer output (<fileout>.ld.prune.in holds the kept lines
+// of the bim in order): keep_out[i] = 1 iff line i of filebim was written there.
+int ref_ld_prune(void* h, const char* filebim, int ld_bp, double r2_tol, const char* fileout, unsigned char* keep_out,
+                 long long nsnps) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    SNPld snp;
+    get_snp_pos_bim(snp, filebim);
+    divide_pos_by_window(snp, ld_bp);
+    ld_prune_big(c->data->G, snp, r2_tol, fileout, filebim);
+    std::ifstream fin(filebim), fkept(std::string(fileout) + ".ld.prune.in");
+    std::string line, kept;
+    bool have = (bool)std::getline(fkept, kept);
+    long long i = 0;
+    while (std::getline(fin, line) && i < nsnps) {
+      if (line.empty()) continue;
+      // compare the first six tab/space separated fields
+      auto norm = [](const std::string& s) {
+        std::string o;
+        int f = 0;
+        bool in = false;
+        for (char ch : s) {
+          if (ch == ' ' || ch == '\t') {
+            if (in) { ++f; in = false; if (f == 6) break; o.push_back('\t'); }
+          } else { o.push_back(ch); in = true; }
+        }
+        while (!o.empty() && o.back() == '\t') o.pop_back();
+        return o;
+      };
+      if (have && norm(line) == norm(kept)) {
+        keep_out[i] = 1;
+        have = (bool)std::getline(fkept, kept);
+      } else {
+        keep_out[i] = 0;
+      }
+      ++i;
+    }
+    if (have) throw std::runtime_error("ref_ld_prune: kept list does not align with the bim");
+  });
 }
 
 // Data::write_residuals (Data.cpp:242-291) via the reference writer.

@@ -1483,8 +1483,10 @@ void set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint
 // ---------------------------------------------------------------- LD r2 (LD.cpp:450-473)
 // Banded tile Gram on the FP64 tensor cores (ld.cuh). The SNP axis is walked in chunks of lead
 // SNPs (+ a halo of the widest window) sized to the free HBM, so M x N need not fit at once.
+// With `keep_out` the r^2 values stay on the device and feed the greedy pruning kernel chunk by
+// chunk (ld_prune_big, LD.cpp:240-268); r2_out may then be NULL.
 void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
-           double* r2_out) {
+           double* r2_out, const double* af = nullptr, double r2_tol = 0.0, unsigned char* keep_out = nullptr) {
   const uint64_t N = c->N;
   if (N < 2) throw std::runtime_error("ld_r2: needs at least two samples");
   if (!G) {
@@ -1492,7 +1494,10 @@ void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, co
       throw std::runtime_error("ld_r2: G == NULL needs a resident packed shard with allele frequencies");
     if (nsnps != c->M) throw std::runtime_error("ld_r2: nsnps must equal the resident shard size");
   }
-  if (nwin == 0) return;
+  if (nwin == 0) {
+    if (keep_out) memset(keep_out, 1, nsnps);
+    return;
+  }
   std::vector<uint64_t> offs(nwin + 1, 0);
   uint64_t maxwe = 1;
   for (uint64_t w = 0; w < nwin; ++w) {
@@ -1517,13 +1522,16 @@ void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, co
   const uint64_t max_rows = std::min<uint64_t>(nsnps, leads + halo);
 
   double *d_Gs = nullptr, *d_raw = nullptr, *d_isd = nullptr, *d_out = nullptr;
-  int32_t *d_winof = nullptr, *d_we = nullptr;
+  int32_t *d_winof = nullptr, *d_we = nullptr, *d_ws = nullptr;
+  unsigned char* d_keep = nullptr;
+  double* d_af = nullptr;
   uint64_t* d_offs = nullptr;
   int2* d_tiles = nullptr;
   size_t out_cap = 0, tiles_cap = 0;
   auto cleanup = [&]() {
     cudaFree(d_Gs); cudaFree(d_raw); cudaFree(d_isd); cudaFree(d_out);
     cudaFree(d_winof); cudaFree(d_we); cudaFree(d_offs); cudaFree(d_tiles);
+    cudaFree(d_ws); cudaFree(d_keep); cudaFree(d_af);
   };
   try {
     dmalloc(&d_Gs, max_rows * Np);
@@ -1534,6 +1542,16 @@ void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, co
     dmalloc(&d_offs, nwin + 1);
     PCA_CUDA(cudaMemcpyAsync(d_we, we, nwin * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     PCA_CUDA(cudaMemcpyAsync(d_offs, offs.data(), (nwin + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    if (keep_out) {
+      dmalloc(&d_ws, nwin);
+      dmalloc(&d_keep, nsnps);
+      PCA_CUDA(cudaMemcpyAsync(d_ws, ws, nwin * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      PCA_CUDA(cudaMemsetAsync(d_keep, 1, nsnps, c->stream));
+      if (af) {
+        dmalloc(&d_af, nsnps);
+        PCA_CUDA(cudaMemcpyAsync(d_af, af, nsnps * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      }
+    }
     static bool attr = false;
     if (!attr) {
       PCA_CUDA(cudaFuncSetAttribute(ld::k_ld_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ld::kSmemBytes));
@@ -1611,11 +1629,24 @@ void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, co
         c->tm.ld_tiles += tiles.size();
         c->tm.ld_pairs += nout;
         c->tm.kernel_launches += 3;
-        PCA_CUDA(cudaMemcpyAsync(r2_out + offs[w_lo], d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        c->tm.d2h_bytes += nout * sizeof(double);
+        if (keep_out) {
+          ld::k_ld_prune<<<1, 1024, 0, c->stream>>>(d_out, offs[w_lo], d_offs, d_ws, d_we, w_lo, w_hi, d_af, r2_tol,
+                                                     d_keep);
+          PCA_CHECK_LAUNCH();
+          c->tm.kernel_launches++;
+        }
+        if (r2_out) {
+          PCA_CUDA(cudaMemcpyAsync(r2_out + offs[w_lo], d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+          c->tm.d2h_bytes += nout * sizeof(double);
+        }
       }
       PCA_CUDA(cudaStreamSynchronize(c->stream));  // winof / tiles host vectors are reused
       w_lo = w_hi;
+    }
+    if (keep_out) {
+      PCA_CUDA(cudaMemcpyAsync(keep_out, d_keep, nsnps, cudaMemcpyDeviceToHost, c->stream));
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      c->tm.d2h_bytes += nsnps;
     }
   } catch (...) {
     cleanup();
@@ -2145,6 +2176,14 @@ int pcaone_upload_dense(pcaone_ctx* c, const double* A, uint64_t rows, uint64_t 
     PCA_CUDA(cudaStreamSynchronize(c->stream));
     c->tm.h2d_bytes += c->M * c->N * sizeof(double);
     c->source = PCAONE_SRC_DENSE;
+  });
+}
+
+int pcaone_ld_prune(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
+                    const double* af, double r2_tol, uint8_t* keep_out) {
+  CTX_GUARD(c, {
+    if (!keep_out) throw std::runtime_error("ld_prune: keep_out is NULL");
+    ld_r2(c, G, nsnps, ws, we, nwin, nullptr, af, r2_tol, keep_out);
   });
 }
 

@@ -169,5 +169,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_ld_tiles(const LdArgs a) {
   }
 }
 
+
+// Greedy LD pruning over the r^2 values of one chunk (reference ld_prune_big, LD.cpp:252-266):
+// windows in ascending lead order; a window is skipped when its lead was pruned before; inside a
+// window every partner k still kept with r^2 > tol prunes o = k (no allele frequencies) or the
+// one of {lead, k} with the smaller MAF (`MAF(af[k]) > MAF(af[i]) ? i : k`). The windows are a
+// serial chain through keep[], the partners of one window are independent (the reference runs them
+// as an OpenMP parallel for): ONE CTA walks the windows, its threads take the partners.
+__global__ void __launch_bounds__(1024) k_ld_prune(const double* __restrict__ r2, uint64_t out0,
+                                                    const uint64_t* __restrict__ offs, const int32_t* __restrict__ ws,
+                                                    const int32_t* __restrict__ we, uint64_t w_lo, uint64_t w_hi,
+                                                    const double* __restrict__ af, double r2_tol,
+                                                    unsigned char* keep) {
+  __shared__ int s_lead_kept;
+  for (uint64_t w = w_lo; w < w_hi; ++w) {
+    const int i = ws[w], n = we[w];
+    if (threadIdx.x == 0) s_lead_kept = ((volatile unsigned char*)keep)[i];
+    __syncthreads();
+    const int kept = s_lead_kept;
+    if (kept) {
+      const double* rw = r2 + (offs[w] - out0);
+      const double mi = af ? (af[i] > 0.5 ? 1.0 - af[i] : af[i]) : 0.0;
+      for (int j = 1 + (int)threadIdx.x; j < n; j += (int)blockDim.x) {
+        const int k = i + j;
+        const double v = rw[j - 1];
+        if (((volatile unsigned char*)keep)[k] && v > r2_tol) {
+          int o = k;
+          if (af) {
+            const double mk = af[k] > 0.5 ? 1.0 - af[k] : af[k];
+            o = mk > mi ? i : k;
+          }
+          keep[o] = 0;
+        }
+      }
+    }
+    __syncthreads();  // keep[] of this window is final before the next lead is read
+  }
+}
+
 }  // namespace ld
 }  // namespace pcaone

@@ -55,3 +55,26 @@ def ld_r2_big(op, G, ws, we):
         nsnps = op.rows()
     op._chk(op.L.pcaone_ld_r2(op.h, _vp(G), C.c_uint64(nsnps), _vp(ws), _vp(we), C.c_uint64(len(ws)), _vp(out)))
     return out
+
+
+def ld_prune_big(op, G, ws, we, r2_tol, af=None):
+    """Greedy LD pruning (src/LD.cpp:240-268): returns the boolean keep mask that
+    write_pruned_snp_ids (:170-190) splits into .ld.prune.in / .ld.prune.out. `af` is the 7th
+    column of the .mbim (then the lower-MAF SNP of a pair goes) or None (the partner goes)."""
+    ws = np.ascontiguousarray(ws, dtype=np.int32)
+    we = np.ascontiguousarray(we, dtype=np.int32)
+    if G is not None:
+        G = np.asfortranarray(G, dtype=np.float64)
+        if G.shape[0] != op.cols():
+            raise RuntimeError("ld_prune_big: G must have one row per sample")
+        nsnps = G.shape[1]
+    else:
+        nsnps = op.rows()
+    if af is not None:
+        af = np.ascontiguousarray(af, dtype=np.float64)
+        if af.shape != (nsnps,):
+            raise RuntimeError("ld_prune_big: af must have one entry per SNP")
+    keep = np.zeros(nsnps, dtype=np.uint8)
+    op._chk(op.L.pcaone_ld_prune(op.h, _vp(G), C.c_uint64(nsnps), _vp(ws), _vp(we), C.c_uint64(len(ws)), _vp(af),
+                                 C.c_double(r2_tol), _vp(keep)))
+    return keep.astype(bool)

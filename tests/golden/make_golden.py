@@ -145,6 +145,20 @@ def main():
             U, S, V = ref.rsvd_one(A, 4, 6, 1, p=p_, windows=w_)
             out[f"{name}_p{p_}_w{w_}_U"], out[f"{name}_p{p_}_w{w_}_S"], out[f"{name}_p{p_}_w{w_}_V"] = U, S, V
     np.savez_compressed(os.path.join(OUT, "rsvd_one.npz"), **out)
+    # ---- E2: LD pruning (ld_prune_big, LD.cpp:240-268) on the same residuals, with the .mbim allele
+    # frequencies (lower-MAF SNP of a pair goes) and with a 6-column bim (the partner goes)
+    r = ref.Ref(f"PCAone -B {tmp}/e.residuals -F {tmp}/e.mbim --print-r2 --ld-bp 1000 -o {tmp}/e3 -n 1", threads=thr)
+    af = np.array([float(ln.split()[6]) for ln in open(f"{tmp}/e.mbim")])
+    with open(f"{tmp}/e6.bim", "w") as f6:
+        for ln in open(f"{tmp}/e.mbim"):
+            f6.write("\t".join(ln.split()[:6]) + "\n")
+    pr = {}
+    for tol_ in (0.02, 0.1):
+        pr[f"keep_af_{tol_}"] = r.ld_prune(f"{tmp}/e.mbim", 1000, tol_, f"{tmp}/p_af_{tol_}")
+        pr[f"keep_noaf_{tol_}"] = r.ld_prune(f"{tmp}/e6.bim", 1000, tol_, f"{tmp}/p_no_{tol_}")
+    r.close()
+    np.savez_compressed(os.path.join(OUT, "ld_prune_small.npz"), af=af, tols=np.array([0.02, 0.1]), **pr)
+
     # ---- H: IRAM operator ArnoldiOpData::perform_op (Arnoldi.cpp:18-46) on the out-of-core plan
     r = ref.Ref(f"PCAone -b {bed} -k {K} -d 0 -m 0.00012 -o {tmp}/h -n 1", threads=thr)
     s3, e3 = r.block_plan()

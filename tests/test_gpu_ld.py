@@ -86,3 +86,44 @@ def test_ld_r2_from_resident_bed():
     ok = np.isfinite(ref)
     np.testing.assert_allclose(r2[ok], ref[ok], rtol=0, atol=1e-12)
     op.close()
+
+
+def test_ld_prune_vs_reference_golden():
+    """pcaone_ld_prune against the keep masks of the unmodified ld_prune_big (LD.cpp:240-268)."""
+    g, pr, s = golden("ld_small"), golden("ld_prune_small"), golden("ssvd_small")
+    N = int(s["N"])
+    tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), "ld_golden_prune.residuals")
+    g["residuals_file"].tofile(tmp)
+    G = orc.read_residuals(tmp)
+    op = _ctx(s["packed"], N)
+    for tol in pr["tols"]:
+        assert np.array_equal(ld.ld_prune_big(op, G, g["ws"], g["we"], float(tol), pr["af"]), pr[f"keep_af_{tol}"])
+        assert np.array_equal(ld.ld_prune_big(op, G, g["ws"], g["we"], float(tol), None), pr[f"keep_noaf_{tol}"])
+    op.close()
+
+
+@pytest.mark.parametrize("N,M,bp,chunk,tol", [(301, 900, 2500, 0, 0.02), (600, 4000, 30000, 0, 0.05),
+                                              (257, 1500, 7000, 256, 0.03)])
+def test_ld_prune_vs_oracle(N, M, bp, chunk, tol, monkeypatch):
+    """Larger windows, several chromosomes, chunked leads with halos; with and without af.
+    Pairs whose r2 sits within 1e-12 of the threshold are excluded from the comparison."""
+    rng = np.random.default_rng(N + M)
+    packed = np.concatenate([synth.pack_codes(c) for _, c in synth.balding_nichols_codes(N, M, k_pop=4, seed=M)])
+    od = orc.OracleData(packed, N)
+    G = od.block(0, M - 1, False) + 0.01 * rng.standard_normal((N, M))
+    G -= G.mean(0, keepdims=True)
+    chrom, pos = _bim(M, nchr=3)
+    ws, we = ld.divide_pos_by_window(chrom, pos, bp)
+    assert np.abs(orc.ld_r2(G, ws, we) - tol).min() > 1e-10     # no knife-edge pair in this seed
+    if chunk:
+        monkeypatch.setenv("PCAONE_LD_CHUNK", str(chunk))
+    op = _ctx(packed, N)
+    for af in (od.F, None):
+        keep = ld.ld_prune_big(op, G, ws, we, tol, af)
+        ref = orc.ld_prune(G, ws, we, tol, af)
+        assert 0 < ref.sum() < M
+        assert np.array_equal(keep, ref)
+    # from the resident bed (G == NULL)
+    keep = ld.ld_prune_big(op, None, ws, we, tol, od.F)
+    assert np.array_equal(keep, orc.ld_prune(od.block(0, M - 1, False), ws, we, tol, od.F))
+    op.close()

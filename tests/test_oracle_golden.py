@@ -218,3 +218,14 @@ def test_perform_op_restatement_vs_reference():
     for std, key in ((True, "y_std"), (False, "y_raw")):
         y = orc.perform_op(od, a["x"], blocks, std)
         assert np.abs(y - a[key]).max() <= 1e-13 * np.abs(a[key]).max()
+
+
+def test_ld_prune_restatement_vs_reference(tmp_path):
+    """oracle.ld_prune against the keep masks recovered from ld_prune_big's own .ld.prune.in."""
+    ld, pr = golden("ld_small"), golden("ld_prune_small")
+    p = str(tmp_path / "r.residuals")
+    ld["residuals_file"].tofile(p)
+    G = orc.read_residuals(p)
+    for tol in pr["tols"]:
+        assert np.array_equal(orc.ld_prune(G, ld["ws"], ld["we"], float(tol), pr["af"]), pr[f"keep_af_{tol}"])
+        assert np.array_equal(orc.ld_prune(G, ld["ws"], ld["we"], float(tol), None), pr[f"keep_noaf_{tol}"])
