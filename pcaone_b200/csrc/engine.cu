@@ -855,8 +855,9 @@ bool orth_fused_ok(const pcaone_ctx* c) { return c->fused_orth && c->l <= kOrthM
 
 // One cooperative launch: Q = orth(A) (CholeskyQR2) [+ Householder signs] [+ flipOmg against Q2].
 void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Q2, double* Ttot, bool signs,
-                bool flip) {
+                bool flip, int phases = 7) {
   OrthArgs a{};
+  a.phases = phases;
   a.A = A;
   a.Q = Q;
   a.Q2 = Q2;
@@ -908,6 +909,23 @@ bool orth2(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Tto
            bool factors_only = false) {
   if (orth_fused_ok(c) && !(sharded_rows && c->cfg.world > 1)) {
     orth_fused(c, A, rows, factors_only ? nullptr : Q, nullptr, Ttot, false, false);
+    return !factors_only;
+  }
+  if (orth_fused_ok(c)) {
+    // rows sharded across ranks: the same kernel in three launches, the two l x l Gram matrices
+    // summed over the ranks in between (the allreduce hook cannot be called from inside a kernel)
+    auto reduce_W = [&]() {
+      if (!c->allreduce) throw std::runtime_error("world > 1 but no allreduce hook installed");
+      Timed t(c, 5);
+      if (c->allreduce(c->allreduce_user, c->d_W, (uint64_t)c->l * c->lp, c->stream))
+        throw std::runtime_error("allreduce hook failed");
+    };
+    double* Qo = factors_only ? nullptr : Q;
+    orth_fused(c, A, rows, Qo, nullptr, Ttot, false, false, 1);
+    reduce_W();
+    orth_fused(c, A, rows, Qo, nullptr, Ttot, false, false, 2);
+    reduce_W();
+    orth_fused(c, A, rows, Qo, nullptr, Ttot, false, false, 4);
     return !factors_only;
   }
   ts_gemm_tn(c, A, c->l, A, c->l, rows, c->d_W, sharded_rows);

@@ -46,6 +46,11 @@ struct OrthArgs {
   double* jscratch;  // [2*l*l + 2*l] global scratch of the eigen fallback
   int* status;       // out: number of factorizations that took the eigen (rank-deficient) route
   unsigned long long* prof;  // optional: globaltimer (ns) at the phase boundaries, CTA 0 (debug aid)
+  // Which part of the kernel this launch runs (bit mask, 0 = 7 = everything). Row-SHARDED inputs
+  // (multi-GPU G) need the two l x l Gram matrices summed across ranks between the parts, so the
+  // host runs three launches with an allreduce of Wg after each of the first two:
+  //   1: P1-P2 (Gram of A -> Wg)   2: P3-P5 (T1 from Wg, Gram of A T1 -> Wg)   4: P6-P8 (T2, Ttot, Q)
+  int phases;
 };
 
 __host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
@@ -383,10 +388,11 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     }
     ++prof_i;
   };
+  const int ph = a.phases ? a.phases : 7;
   stamp();
   zero_pad_cols();
   // ---------------- P1: partial Gram of A
-  {
+  if (ph & 1) {
     double acc[R][R];
 #pragma unroll
     for (int i = 0; i < R; ++i)
@@ -401,24 +407,29 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       gram_accumulate(As, acc);
     }
     store_part(acc);
+    stamp();
+    grid.sync();
+    stamp();
+    // ---------------- P2: W = sum of partials
+    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+    stamp();
+    if (ph & 6) grid.sync();
+    stamp();
   }
-  stamp();
-  grid.sync();
-  stamp();
-  // ---------------- P2: W = sum of partials
-  orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
-  stamp();
-  grid.sync();
-  stamp();
   // ---------------- P3: T1
-  if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
-  __threadfence();
-  stamp();
-  grid.sync();
-  stamp();
+  if (ph & 2) {
+    if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
+    __threadfence();
+    stamp();
+    grid.sync();
+    stamp();
+  }
   // ---------------- P4: partial Gram of Q1 = A T1
-  if (blockIdx.x != 0) load_T(a.T1g, T1s);
-  {
+  if ((ph & 2) ? blockIdx.x != 0 : (ph & 4) != 0) {  // T1 is in CTA 0's shared memory only if P3 ran in this launch
+    load_T(a.T1g, T1s);
+    __syncthreads();
+  }
+  if (ph & 2) {
     double acc[R][R];
 #pragma unroll
     for (int i = 0; i < R; ++i)
@@ -437,14 +448,15 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       gram_accumulate(Qs, acc);
     }
     store_part(acc);
+    stamp();
+    grid.sync();
+    stamp();
+    // ---------------- P5
+    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+    if (ph & 4) grid.sync();
+    stamp();
   }
-  stamp();
-  grid.sync();
-  stamp();
-  // ---------------- P5
-  orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
-  grid.sync();
-  stamp();
+  if (!(ph & 4)) return;  // uniform across the grid
   // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
   if (blockIdx.x == 0) {
     orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
