@@ -167,6 +167,18 @@ int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t
  * pcaone_set_usv); a context with k = 1, oversamples = 0 makes it a GEMV-shaped pass. */
 int pcaone_perform_op(pcaone_ctx* ctx, const double* x_in, double* y_out);
 
+/* ---- downstream consumers of U, S, V: the two half products on their own ----------
+ * pcaone_xt_times: out (nsnps x ncols) = X^T A for A = nsamples x ncols, plus sqnorm[j] = sum_i x_ij^2
+ *   (NULL to skip) — `V.row(j) = U^T G.col(j); y_norm2(j) = G.col(j).squaredNorm()` of run_selection
+ *   (Selection.cpp:16-34); the statistics on top (galinsky / pcadapt) stay host code.
+ * pcaone_x_times:  out (nsamples x ncols) = X B for B = nsnps x ncols — `U = G * V` of
+ *   run_projection option 1 (Projection.cpp:236-241; the caller scales V by 1 / S, and installs the
+ *   reference panel's allele frequencies with pcaone_set_F as Data::prepare does for projection).
+ * Column-major host matrices, ncols <= k + oversamples, X decoded under the pcaone_set_flags state
+ * (FP64 kernels on every source). */
+int pcaone_xt_times(pcaone_ctx* ctx, const double* A, uint32_t ncols, double* out, double* sqnorm);
+int pcaone_x_times(pcaone_ctx* ctx, const double* B, uint32_t ncols, double* out);
+
 /* ---- BGEN-style dosages (FileBgen::read_all / read_block_initial, FileBgen.cpp:15-168) ----------
  * The host keeps the container parsing (`var.minor_allele_dosage`, FileBgen.cpp:26) and hands over
  * what that call yields: one row of nsamples floats per variant, NaN = missing, SNP-major

@@ -99,6 +99,48 @@ __global__ void k_allele_freq(const uint8_t* __restrict__ P, uint32_t pitch, uin
   }
 }
 
+// Squared norm of every decoded SNP column, sum_i x_ij^2 (Selection.cpp:21,31 `G.col(j).squaredNorm()`),
+// from the code counts: n00 v0^2 + n10 v2^2 + n11 v3^2 (missing entries are 0). One warp per SNP.
+__global__ void k_snp_sqnorm(const uint8_t* __restrict__ P, uint32_t pitch, uint32_t N, uint64_t nsnps,
+                             const double* __restrict__ F, LutParams lp, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t nvec = (N + 63) >> 6;
+  for (uint64_t j = warp; j < nsnps; j += nwarps) {
+    const uint4* row = reinterpret_cast<const uint4*>(P + j * pitch);
+    uint32_t c01 = 0, c10 = 0, c11 = 0;
+    for (uint32_t v = lane; v < nvec; v += 32) {
+      const uint4 q = __ldg(row + v);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int32_t nvalid = (int32_t)N - (int32_t)(v * 64 + i * 16);
+        uint32_t m = 0x55555555u;
+        if (nvalid <= 0)
+          m = 0u;
+        else if (nvalid < 16)
+          m &= (1u << (2 * nvalid)) - 1u;
+        const uint32_t lo = w[i] & m, hi = (w[i] >> 1) & m;
+        c01 += __popc(lo & ~hi);
+        c10 += __popc(hi & ~lo);
+        c11 += __popc(lo & hi);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c01 += __shfl_xor_sync(0xffffffffu, c01, o);
+      c10 += __shfl_xor_sync(0xffffffffu, c10, o);
+      c11 += __shfl_xor_sync(0xffffffffu, c11, o);
+    }
+    if (lane == 0) {
+      const SnpLut t = make_lut(F[j], lp);
+      const double c00 = (double)(N - c01 - c10 - c11);
+      out[j] = c00 * t.v[0] * t.v[0] + (double)c10 * t.v[2] * t.v[2] + (double)c11 * t.v[3] * t.v[3];
+    }
+  }
+}
+
 __global__ void k_lookup_scale(const double* __restrict__ F, uint64_t nsnps, LutParams p,
                                double* __restrict__ lut4, double* __restrict__ scale) {
   for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nsnps; j += (uint64_t)gridDim.x * blockDim.x) {

@@ -410,6 +410,25 @@ k_dos_h(const float* __restrict__ D, uint32_t ldd, uint32_t nrows, uint32_t ncol
   }
 }
 
+// sum_i x_ij^2 of every dosage row (Selection.cpp:21,31), one warp per variant
+__global__ void __launch_bounds__(256) k_dosage_sqnorm(const float* __restrict__ D, uint32_t ldd, uint32_t N, uint64_t rows,
+                                                        const double* __restrict__ F, LutParams lp,
+                                                        double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t j = warp; j < rows; j += nwarps) {
+    const double f = F[j], sc = snp_scale(f, lp);
+    double s = 0.0;
+    for (uint32_t i = lane; i < N; i += 32) {
+      const double x = dosage_value(D[j * ldd + i], f, sc);
+      s += x * x;
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
+  }
+}
+
 // dense decode of dosage rows [start, start + nrows) -> col-major N x nrows doubles (Eigen layout
 // of data->G), for read_block parity checks (FileBgen.cpp:96-110)
 __global__ void k_dosage_decode(const float* __restrict__ D, uint32_t ldd, uint32_t N, uint64_t nrows,

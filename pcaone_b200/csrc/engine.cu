@@ -118,6 +118,7 @@ struct pcaone_ctx {
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
   std::vector<uint64_t> nmiss_prefix;
   uint64_t tc_ranges = 0, fp64_ranges = 0, tc_miss_ranges = 0;
+  int half = 3;                                        // which products a range runs: 1 = G rows only, 2 = H only, 3 = both
   bool g_is_q = false;                                 // d_G holds Q = G T after small_stage (else raw G)
   double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
   int fused_orth = 1;                                  // PCAONE_FUSED_ORTH=0 selects the multi-kernel path
@@ -282,12 +283,13 @@ void range_gemms_fp64(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t 
   const double* F = c->d_F + snp0;
   double* G = c->d_G + snp0 * c->lp;
   const double* Vrows = c->d_V + snp0 * c->lp;
-  {
+  if (c->half & 1) {
     Timed t(c, 0);
     NT_DISPATCH(gemm_g_nt, c, P, nrows, F, G, Vrows);
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
   }
+  if (!(c->half & 2)) return;
   const uint32_t tiles = ceil_div(c->N, kTileRows);
   uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
   splits = std::min<uint32_t>(splits, c->max_splits);
@@ -588,12 +590,13 @@ void dense_h_nt(pcaone_ctx* c, const double* D, uint32_t nrows, const double* G,
 void range_gemms_dense(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc, bool accumulate) {
   const double* D = c->d_dense + r0 * c->ldd;
   double* G = c->d_G + r0 * c->lp;
-  {
+  if (c->half & 1) {
     Timed t(c, 0);
     NT_DISPATCH(dense_g_nt, c, D, nrows, G);
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
   }
+  if (!(c->half & 2)) return;
   const uint32_t tiles = ceil_div(c->N, kDenseRows);
   uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
   splits = std::min<uint32_t>(splits, c->max_splits);
@@ -646,12 +649,13 @@ void range_gemms_dosage(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc
   const float* D = c->d_dos + r0 * c->ldf;
   const double* F = c->d_F + r0;
   double* G = c->d_G + r0 * c->lp;
-  {
+  if (c->half & 1) {
     Timed t(c, 0);
     NT_DISPATCH(dos_g_nt, c, D, nrows, F, G);
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
   }
+  if (!(c->half & 2)) return;
   const uint32_t tiles = ceil_div(c->N, kDenseRows);
   uint32_t splits = std::max<uint32_t>(1, (2u * c->sms + tiles - 1) / tiles);
   splits = std::min<uint32_t>(splits, c->max_splits);
@@ -685,7 +689,7 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
     return;
   }
   // EMU update passes fill every missing entry with its own FP64 value: FP64 kernels
-  const bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu);
+  const bool use_tc = c->slices > 0 && !(c->update && c->cfg.emu) && c->half == 3;  // half passes: FP64 kernels
   bool has_miss = false;
   if (use_tc) {
     uint64_t miss = tc_missing_in(c, snp0, nrows);
@@ -1303,21 +1307,11 @@ void compute_usv(pcaone_ctx* c, int p, double tol) {
   PCA_CUDA(cudaStreamSynchronize(c->stream));
 }
 
-// ArnoldiOpData::perform_op (Arnoldi.cpp:18-46): y = sum over blocks G_b (G_b^T x), the operator the
-// IRAM solver (Spectra) iterates. One decode + GEMM pass with x in column 0 of Omega; the current
-// update / standardize flags apply exactly as in computeGandH.
-void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
-  if (c->source < 0) throw std::runtime_error("no genotype source set");
+// One pass over every SNP of the source in plan order with the CURRENT Omega / d_G: G rows of each
+// range from Omega, d_H = sum over ranges (the sSVD pass of compute_gandh without the Omega update).
+void walk_ranges(pcaone_ctx* c) {
   const bool ooc = c->source == PCAONE_SRC_HOST || c->source == PCAONE_SRC_FILE;
-  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("perform_op(update) without U,S,V");
-  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
   const uint64_t HN = c->N * c->lp;
-  ensure_stage(c, c->N);
-  PCA_CUDA(cudaMemcpyAsync(c->d_stage, x_in, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  zero_async(c, c->d_Omg, HN);
-  PCA_CUDA(cudaMemcpy2DAsync(c->d_Omg, (size_t)c->lp * sizeof(double), c->d_stage, sizeof(double), sizeof(double), c->N,
-                             cudaMemcpyDeviceToDevice, c->stream));
-  c->omega_img_valid = false;
   if (!ooc) {
     if (!c->af_done && c->source != PCAONE_SRC_DENSE) throw std::runtime_error("call pcaone_allele_freq first");
     if (c->blk_start.empty()) {
@@ -1342,6 +1336,23 @@ void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
     }
     c->af_done = true;
   }
+}
+
+// ArnoldiOpData::perform_op (Arnoldi.cpp:18-46): y = sum over blocks G_b (G_b^T x), the operator the
+// IRAM solver (Spectra) iterates. One decode + GEMM pass with x in column 0 of Omega; the current
+// update / standardize flags apply exactly as in computeGandH.
+void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
+  if (c->source < 0) throw std::runtime_error("no genotype source set");
+  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("perform_op(update) without U,S,V");
+  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
+  const uint64_t HN = c->N * c->lp;
+  ensure_stage(c, c->N);
+  PCA_CUDA(cudaMemcpyAsync(c->d_stage, x_in, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  zero_async(c, c->d_Omg, HN);
+  PCA_CUDA(cudaMemcpy2DAsync(c->d_Omg, (size_t)c->lp * sizeof(double), c->d_stage, sizeof(double), sizeof(double), c->N,
+                             cudaMemcpyDeviceToDevice, c->stream));
+  c->omega_img_valid = false;
+  walk_ranges(c);
   allreduce_H(c, c->d_H);
   PCA_CUDA(cudaMemcpy2DAsync(c->d_stage, sizeof(double), c->d_H, (size_t)c->lp * sizeof(double), sizeof(double), c->N,
                              cudaMemcpyDeviceToDevice, c->stream));
@@ -1349,6 +1360,65 @@ void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
   PCA_CUDA(cudaStreamSynchronize(c->stream));
   c->tm.h2d_bytes += c->N * sizeof(double);
   c->tm.d2h_bytes += c->N * sizeof(double);
+}
+
+// V = X^T A per SNP (+ the squared norm of every decoded SNP column): the device part of
+// run_selection (Selection.cpp:16-34, `V.row(j) = U^T G.col(j); y_norm2(j) = G.col(j).squaredNorm()`).
+// A: N x ncols (column-major, host), out: M x ncols (column-major), sqnorm: M or NULL.
+void xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, double* sqnorm) {
+  if (c->source < 0) throw std::runtime_error("no genotype source set");
+  if (ncols == 0 || (int)ncols > c->l) throw std::runtime_error("xt_times: ncols must be in [1, k + oversamples]");
+  if (c->cfg.world > 1) throw std::runtime_error("xt_times: single-GPU only");
+  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("xt_times(update) without U,S,V");
+  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
+  zero_async(c, c->d_Omg, c->N * c->lp);
+  upload_colmajor(c, A, c->N, (int)ncols, c->d_Omg);
+  c->omega_img_valid = false;
+  c->half = 1;
+  try {
+    walk_ranges(c);
+  } catch (...) {
+    c->half = 3;
+    throw;
+  }
+  c->half = 3;
+  download_colmajor(c, c->d_G, c->M, (int)ncols, out);
+  if (sqnorm) {
+    ensure_stage(c, c->M);
+    if (c->source == PCAONE_SRC_RESIDENT) {
+      k_snp_sqnorm<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_packed, c->pitch, (uint32_t)c->N, c->M,
+                                                                           c->d_F, c->lut, c->d_stage);
+    } else if (c->source == PCAONE_SRC_DOSAGE) {
+      k_dosage_sqnorm<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_dos, c->ldf, (uint32_t)c->N, c->M,
+                                                                              c->d_F, c->lut, c->d_stage);
+    } else {
+      throw std::runtime_error("xt_times: squared norms need a resident genotype or dosage source");
+    }
+    PCA_CHECK_LAUNCH();
+    PCA_CUDA(cudaMemcpyAsync(sqnorm, c->d_stage, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+  }
+}
+
+// U = X B: the device part of run_projection option 1 (Projection.cpp:236-241, `U = G * V` with
+// V already scaled by 1 / S on the host side of the call). B: M x ncols, out: N x ncols (column-major).
+void x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out) {
+  if (c->source < 0) throw std::runtime_error("no genotype source set");
+  if (ncols == 0 || (int)ncols > c->l) throw std::runtime_error("x_times: ncols must be in [1, k + oversamples]");
+  if (c->cfg.world > 1) throw std::runtime_error("x_times: single-GPU only");
+  if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("x_times(update) without U,S,V");
+  c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
+  zero_async(c, c->d_G, c->M * c->lp);
+  upload_colmajor(c, B, c->M, (int)ncols, c->d_G);
+  c->half = 2;
+  try {
+    walk_ranges(c);
+  } catch (...) {
+    c->half = 3;
+    throw;
+  }
+  c->half = 3;
+  download_colmajor(c, c->d_H, c->N, (int)ncols, out);
 }
 
 // RsvdOpOnePass::computeGandH (RSVD.hpp:137-166 plain, :168-252 windows) followed by
@@ -2204,6 +2274,11 @@ int pcaone_ld_prune(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_
     ld_r2(c, G, nsnps, ws, we, nwin, nullptr, af, r2_tol, keep_out);
   });
 }
+
+int pcaone_xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, double* sqnorm) {
+  CTX_GUARD(c, xt_times(c, A, ncols, out, sqnorm));
+}
+int pcaone_x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out) { CTX_GUARD(c, x_times(c, B, ncols, out)); }
 
 int pcaone_perform_op(pcaone_ctx* c, const double* x_in, double* y_out) { CTX_GUARD(c, perform_op(c, x_in, y_out)); }
 

@@ -396,6 +396,27 @@ class RsvdOpData:
         self._chk(self.L.pcaone_decode_block(self.h, int(start), int(stop), int(standardize), int(update), _vp(out)))
         return out
 
+    def setF(self, F):
+        """External allele frequencies (projection: the reference panel's .mbim column 7,
+        Data::prepare for --project)."""
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        self._chk(self.L.pcaone_set_F(self.h, _vp(F)))
+
+    def xtTimes(self, A, want_sqnorm=False):
+        """X^T A (M x c) [+ per-SNP squared norms]: Selection.cpp:16-34."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        out = _f((self.rows(), A.shape[1]))
+        nrm = np.zeros(self.rows()) if want_sqnorm else None
+        self._chk(self.L.pcaone_xt_times(self.h, _vp(A), A.shape[1], _vp(out), _vp(nrm)))
+        return (out, nrm) if want_sqnorm else out
+
+    def xTimes(self, B):
+        """X B (N x c): Projection.cpp:236-241."""
+        B = np.asfortranarray(B, dtype=np.float64)
+        out = _f((self.cols(), B.shape[1]))
+        self._chk(self.L.pcaone_x_times(self.h, _vp(B), B.shape[1], _vp(out)))
+        return out
+
     def setUSV(self, U, S, V):
         U = np.asfortranarray(U, dtype=np.float64)
         V = np.asfortranarray(V, dtype=np.float64)

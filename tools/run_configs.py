@@ -125,6 +125,35 @@ def c2(args, out):
     _emit(out, rec)
 
 
+def c2m(args, out):
+    """configs[1] with 1 % missing calls everywhere: every range takes the (count, mask) product pair
+    on the int8 kernels; the FP64 DMMA route (LUT decode of code 01) is the checker."""
+    N, M, k = 10_000, int(1_000_000 * args.scale), 20
+    packed = synth.torch_packed(N, M, k_pop=k + 4, seed=1, miss=0.01, device="cuda:0", chunk=16384)
+    rec = {"config": "C2m", "workload": f"winSVD in-memory N={N} M={M} k={k} 64 windows, 1% missing calls",
+           "bytes_per_pass": M * packed.shape[1]}
+    res = {}
+    for name, prec in (("int8x3", 3), ("fp64", 0)):
+        p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, precision=prec)
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+        op.setFlags(False, True)
+        secs, ep = _run(op, p)
+        secs2, _ = _run(op, p)
+        pt = _pass_time(op, [6, 7, 8])
+        tm = op.timers(reset=True)
+        res[name] = (op.U.copy(), op.S.copy())
+        rec[name] = {"time_to_pcs_s": secs2, "first_run_s": secs, "epochs": ep, "late_pass_ms": 1e3 * pt,
+                     "gbs_per_late_pass": rec["bytes_per_pass"] / pt / 1e9, "tc_ranges": int(tm.tc_ranges),
+                     "tc_miss_ranges": int(tm.tc_miss_ranges), "fp64_ranges": int(tm.fp64_ranges)}
+        if prec == 3:
+            rec["missing_fraction"] = op.missing_count() / (N * M)
+        op.close()
+    rec["int8x3_vs_fp64"] = {"eig_rel": float(np.max(np.abs(res["int8x3"][1] ** 2 - res["fp64"][1] ** 2) / res["fp64"][1] ** 2)),
+                             "min_abs_corr": float(_corr_cols(res["int8x3"][0], res["fp64"][0]).min())}
+    _emit(out, rec)
+
+
 def _host_avail_gb():
     for ln in open("/proc/meminfo"):
         if ln.startswith("MemAvailable"):
@@ -216,6 +245,104 @@ def c5(args, out):
     _emit(out, rec)
 
 
+def f_bgen(args, out):
+    """§8 f-1: BGEN-style float dosages (4 B per genotype resident in HBM), sSVD, FP64 DMMA with the
+    decode fused into the operand load."""
+    N, M, k = 10_000, int(200_000 * args.scale), 20
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(3)
+    dos = torch.empty((M, N), dtype=torch.float32, device="cuda:0")
+    for s0 in range(0, M, 8192):
+        m = min(8192, M - s0)
+        pfreq = torch.rand(m, 1, generator=g, device="cuda:0") * 0.9 + 0.05
+        blk = (torch.rand(m, N, generator=g, device="cuda:0") < pfreq).float() + (torch.rand(m, N, generator=g, device="cuda:0") < pfreq).float()
+        blk = (blk + 0.05 * torch.randn(m, N, generator=g, device="cuda:0")).clamp_(0, 2)
+        blk[torch.rand(m, N, generator=g, device="cuda:0") < 0.01] = float("nan")
+        dos[s0:s0 + m] = blk
+    p = halko.Param(k=k, svd=1, maxp=20, tol=1e-4, precision=_lib.PREC_FP64)
+    d = halko.FileBgen(p, dos)      # selection skipped for the synthetic matrix (no all-zero variant)
+    op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+    op.setFlags(False, True)
+    secs, ep = _run(op, p)
+    secs2, _ = _run(op, p)
+    pt = _pass_time(op, [1, 2, 3])
+    l = op.size()
+    rec = {"config": "F1-bgen", "workload": f"sSVD on float32 dosages N={N} M={M} k={k}, 1% NaN, FP64 DMMA fused decode",
+           "dosage_bytes": 4 * N * M, "time_to_pcs_s": secs2, "first_run_s": secs, "epochs": ep, "pass_ms": 1e3 * pt,
+           "dosage_gbs_per_pass": 2 * 4.0 * N * M / pt / 1e9, "fp64_tflops": 4.0 * N * M * l / pt / 1e12,
+           "note": "each pass reads the dosage matrix twice (G product, H product); FP64 tensor nominal ~37 TFLOP/s"}
+    op.close()
+    _emit(out, rec)
+
+
+def f_prune(args, out):
+    """§8 f-2: greedy LD pruning on the device at config-5 size (r2 tiles never leave HBM)."""
+    N, M = 20_000, int(200_000 * args.scale)
+    packed = synth.torch_packed(N, M, k_pop=6, seed=5, device="cuda:0", chunk=8192)
+    p = halko.Param(k=2, svd=1, ld=True)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+    per = -(-M // 22)
+    chrom = np.minimum(np.arange(M) // per, 21)
+    pos = (np.arange(M) % per + 1) * 100
+    ws, we = ld.divide_pos_by_window(chrom, pos, 100_000)
+    af = op.F()
+    op.sync()
+    res = {}
+    for tol in (0.2, 0.02):
+        t0 = time.perf_counter()
+        keep = ld.ld_prune_big(op, None, ws, we, tol, af)
+        res[str(tol)] = {"seconds": time.perf_counter() - t0, "kept": int(keep.sum())}
+    pairs = int((we.astype(np.int64) - 1).sum())
+    rec = {"config": "F2-ldprune", "workload": f"LD pruning from the resident bed N={N} M={M}, --ld-bp 100000, MAF rule",
+           "pairs": pairs, "by_r2_tol": res, "pairs_per_s": pairs / res["0.2"]["seconds"]}
+    op.close()
+    _emit(out, rec)
+
+
+def f_iram(args, out):
+    """§8 f-3: one ArnoldiOpData::perform_op at config-2 size (GEMV-shaped pass, l = 1)."""
+    N, M = 10_000, int(1_000_000 * args.scale)
+    packed = synth.torch_packed(N, M, k_pop=24, seed=1, device="cuda:0", chunk=16384)
+    rec = {"config": "F3-iram-op", "workload": f"y = X X^T x, N={N} M={M}, resident bed", "bytes_per_op": M * packed.shape[1]}
+    x = np.random.default_rng(0).standard_normal(N)
+    ys = {}
+    for name, prec in (("int8x4", 4), ("fp64", 0)):
+        p = halko.Param(k=20, svd=1, precision=prec)
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        op = halko.ArnoldiOpData(d)
+        op.setFlags(False, True)
+        ys[name] = op.perform_op(x)
+        op.sync()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            op.perform_op(x)
+        dt = (time.perf_counter() - t0) / 5
+        rec[name] = {"ms_per_op": 1e3 * dt, "packed_gbs": rec["bytes_per_op"] / dt / 1e9}
+        op.close()
+    rec["int8x4_vs_fp64_rel"] = float(np.abs(ys["int8x4"] - ys["fp64"]).max() / np.abs(ys["fp64"]).max())
+    rec["note"] = "HBM-bound shape: the packed matrix is read twice per op (G product, H product)"
+    _emit(out, rec)
+
+
+def f_dense(args, out):
+    """§8 a15: RsvdOne on a dense FP64 matrix (PCAoneR's entry point)."""
+    from pcaone_b200.rsvd import RsvdOne
+    rows, cols, k = int(100_000 * args.scale), 2_000, 20
+    rng = np.random.default_rng(1)
+    A = (rng.standard_normal((rows, 30)) * np.linspace(50, 5, 30)) @ rng.standard_normal((30, cols)) \
+        + 0.1 * rng.standard_normal((rows, cols))
+    rec = {"config": "A15-dense", "workload": f"RsvdOne {rows} x {cols} doubles, k={k}, os=20", "bytes": 8 * rows * cols}
+    s = np.sqrt(np.linalg.eigvalsh(A.T @ A)[::-1][:k])     # exact singular values (checker)
+    for name, (pp, w) in (("plain_p7", (7, 0)), ("windows64_p7", (7, 64))):
+        r = RsvdOne(A, k, 20, 1)
+        t0 = time.perf_counter()
+        r.compute(pp, w)
+        rec[name] = {"seconds_incl_upload": time.perf_counter() - t0}
+        rec[name]["sv_rel_err_vs_lapack"] = float(np.max(np.abs(r.singularValues() - s) / s))
+    _emit(out, rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
@@ -225,7 +352,8 @@ def main():
     ap.add_argument("--c4-prec", type=int, default=0)
     args = ap.parse_args()
     _lib.load()
-    fns = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+    fns = {"c1": c1, "c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "bgen": f_bgen, "prune": f_prune,
+           "iram": f_iram, "dense": f_dense}
     for w in args.which:
         t0 = time.perf_counter()
         try:
