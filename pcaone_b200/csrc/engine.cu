@@ -115,6 +115,10 @@ struct pcaone_ctx {
   unsigned long long* d_tcs = nullptr;                 // [5][lp]: Omega colmax, Omega Csum, W colmax, W Csum, Fw
   double* d_Fpart = nullptr;
   bool omega_img_valid = false;
+  bool omega_colmax_valid = false;                     // d_tcs colmax of Omega was produced by the orth kernel
+  const double* sum_other = nullptr;                   // winSVD: the next finish_h also writes sum_out = Hacc + sum_other
+  double* sum_out = nullptr;
+  bool sum_done = false;
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
   std::vector<uint64_t> nmiss_prefix;
   uint64_t tc_ranges = 0, fp64_ranges = 0, tc_miss_ranges = 0;
@@ -481,10 +485,13 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
   {
     Timed t(c, 0);
     if (!c->omega_img_valid) {
-      PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
-      tc::k_tc_colmax<<<grid_for(c->N * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, 0, c->N, o_colmax);
-      PCA_CHECK_LAUNCH();
-      c->tm.kernel_launches++;
+      if (!c->omega_colmax_valid) {
+        PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
+        tc::k_tc_colmax<<<grid_for(c->N * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_Omg, c->lp, c->l, 0, c->N, o_colmax);
+        PCA_CHECK_LAUNCH();
+        c->tm.kernel_launches++;
+      }
+      c->omega_colmax_valid = false;
       tc_slice(c, c->d_Omg, 0, c->N, o_colmax, nullptr, 0, c->d_BimgO, o_csum, nullptr, nullptr);
       c->omega_img_valid = true;
     }
@@ -546,15 +553,23 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       }
     }
     double* Fw = reinterpret_cast<double*>(c->d_tcs + 4 * c->lp);
-    tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
-    PCA_CHECK_LAUNCH();
+    // (folding this sum into every finish block was tried: the serial chain of a window's ~250
+    // partials per block cost ~30 us per launch, 6x the separate reduction kernel)
+    const bool fold_fw = false;
+    if (!fold_fw) {
+      tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
+      PCA_CHECK_LAUNCH();
+      c->tm.kernel_launches++;
+    }
+    const bool fuse_sum = c->sum_out != nullptr && c->sum_other != nullptr;
     tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
-        c->d_Racc, miss ? c->d_Racc2 : nullptr, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw, Hacc,
-        accumulate ? 1 : 0);
+        c->d_Racc, miss ? c->d_Racc2 : nullptr, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw,
+        fold_fw ? c->d_Fpart : nullptr, nkb_w, Hacc, accumulate ? 1 : 0, fuse_sum ? c->sum_other : nullptr,
+        fuse_sum ? c->sum_out : nullptr);
     PCA_CHECK_LAUNCH();
+    if (fuse_sum) c->sum_done = true;
     c->tm.kernel_launches++;
     c->tm.gemm_h_launches++;
-    c->tm.kernel_launches++;
   }
   c->tc_ranges++;
   if (miss) c->tc_miss_ranges++;
@@ -859,9 +874,10 @@ bool orth_fused_ok(const pcaone_ctx* c) { return c->fused_orth && c->l <= kOrthM
 
 // One cooperative launch: Q = orth(A) (CholeskyQR2) [+ Householder signs] [+ flipOmg against Q2].
 void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double* Q2, double* Ttot, bool signs,
-                bool flip, int phases = 7) {
+                bool flip, int phases = 7, unsigned long long* colmax_out = nullptr) {
   OrthArgs a{};
   a.phases = phases;
+  a.colmax_out = colmax_out;
   a.A = A;
   a.Q = Q;
   a.Q2 = Q2;
@@ -968,9 +984,15 @@ void allreduce_H(pcaone_ctx* c, double* H) {
 void update_omega(pcaone_ctx* c, const double* H, bool flip) {
   Timed t(c, 2);
   if (orth_fused_ok(c)) {
-    orth_fused(c, H, c->N, c->d_Omg, flip ? c->d_Omg2 : nullptr, nullptr, true, flip);
+    unsigned long long* cm = nullptr;
+    if (c->slices > 0 && c->d_tcs) {  // int8 route: the kernel also leaves max |Omega| per column for the slicing
+      PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
+      cm = c->d_tcs;
+    }
+    orth_fused(c, H, c->N, c->d_Omg, flip ? c->d_Omg2 : nullptr, nullptr, true, flip, 7, cm);
     c->tm.omega_updates++;
     c->omega_img_valid = false;
+    c->omega_colmax_valid = cm != nullptr;
     return;
   }
   orth2(c, H, c->N, c->d_Omg, nullptr, false);
@@ -992,7 +1014,7 @@ void update_omega(pcaone_ctx* c, const double* H, bool flip) {
     c->tm.kernel_launches++;
   }
   c->tm.omega_updates++;
-  c->omega_img_valid = false;
+  c->omega_img_valid = c->omega_colmax_valid = false;
 }
 
 // ---------------------------------------------------------------- host <-> device matrices
@@ -1140,7 +1162,7 @@ void compute_gandh(pcaone_ctx* c, int pi) {
     if (!c->have_omg0) throw std::runtime_error("call pcaone_set_omega before the first pass");
     PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    c->omega_img_valid = false;
+    c->omega_img_valid = c->omega_colmax_valid = false;
   }
   if (ooc) {
     if (c->blk_start.empty()) throw std::runtime_error("out-of-core source needs pcaone_set_blocks");
@@ -1206,6 +1228,12 @@ void compute_gandh(pcaone_ctx* c, int pi) {
         ++e;
     }
     double* Hacc = steps[b].target == 1 ? c->d_H1 : c->d_H2;
+    const WinStep& last = steps[e];
+    if (last.update) {  // the range's H finish may also form H = H1 + H2 for the update (int8 route)
+      c->sum_other = steps[b].target == 1 ? c->d_H2 : c->d_H1;
+      c->sum_out = c->d_H;
+    }
+    c->sum_done = false;
     if (steps[b].stop >= steps[b].start) {
       const uint64_t s0 = steps[b].start, nrows = steps[e].stop - s0 + 1;
       if (!ooc) {
@@ -1218,11 +1246,14 @@ void compute_gandh(pcaone_ctx* c, int pi) {
         PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
       }
     }
-    const WinStep& last = steps[e];
+    c->sum_other = nullptr;
+    c->sum_out = nullptr;
     if (last.update) {
-      k_add2<<<grid_for(HN, 256, c->sms), 256, 0, c->stream>>>(c->d_H1, c->d_H2, c->d_H, HN);
-      PCA_CHECK_LAUNCH();
-      c->tm.kernel_launches++;
+      if (!c->sum_done) {
+        k_add2<<<grid_for(HN, 256, c->sms), 256, 0, c->stream>>>(c->d_H1, c->d_H2, c->d_H, HN);
+        PCA_CHECK_LAUNCH();
+        c->tm.kernel_launches++;
+      }
       allreduce_H(c, c->d_H);
       update_omega(c, c->d_H, true);
       zero_async(c, last.zero_h1 ? c->d_H1 : c->d_H2, HN);
@@ -1351,7 +1382,7 @@ void perform_op(pcaone_ctx* c, const double* x_in, double* y_out) {
   zero_async(c, c->d_Omg, HN);
   PCA_CUDA(cudaMemcpy2DAsync(c->d_Omg, (size_t)c->lp * sizeof(double), c->d_stage, sizeof(double), sizeof(double), c->N,
                              cudaMemcpyDeviceToDevice, c->stream));
-  c->omega_img_valid = false;
+  c->omega_img_valid = c->omega_colmax_valid = false;
   walk_ranges(c);
   allreduce_H(c, c->d_H);
   PCA_CUDA(cudaMemcpy2DAsync(c->d_stage, sizeof(double), c->d_H, (size_t)c->lp * sizeof(double), sizeof(double), c->N,
@@ -1373,7 +1404,7 @@ void xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, doubl
   c->lut.standardize = (c->standardize && c->cfg.scale == -9) ? 1 : 0;
   zero_async(c, c->d_Omg, c->N * c->lp);
   upload_colmajor(c, A, c->N, (int)ncols, c->d_Omg);
-  c->omega_img_valid = false;
+  c->omega_img_valid = c->omega_colmax_valid = false;
   c->half = 1;
   try {
     walk_ranges(c);
@@ -1433,7 +1464,7 @@ void dense_onepass(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder) {
   const uint64_t HN = c->N * c->lp;
   PCA_CUDA(cudaMemcpyAsync(c->d_Omg, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   PCA_CUDA(cudaMemcpyAsync(c->d_Omg2, c->d_Omg0, HN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  c->omega_img_valid = false;
+  c->omega_img_valid = c->omega_colmax_valid = false;
   auto full_pass = [&]() { range_gemms(c, nullptr, (uint32_t)c->M, 0, c->d_H, false, -1); };
   full_pass();
   if (windows == 0) {

@@ -51,6 +51,9 @@ struct OrthArgs {
   // host runs three launches with an allreduce of Wg after each of the first two:
   //   1: P1-P2 (Gram of A -> Wg)   2: P3-P5 (T1 from Wg, Gram of A T1 -> Wg)   4: P6-P8 (T2, Ttot, Q)
   int phases;
+  // optional: per-column max |Q| as IEEE bit patterns (atomicMax; zeroed by the caller) — what the
+  // int8 route's slicing of the new Omega needs, saving its own column-max kernel
+  unsigned long long* colmax_out;
 };
 
 __host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
@@ -562,9 +565,9 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   double hs[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? a.hsign[tx + 16 * j] : 0.0;
-  double dsum[R], ssum[R];
+  double dsum[R], ssum[R], amax[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = 0.0;
+  for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = amax[j] = 0.0;
   zero_pad_cols();
   prefetch(r0);
   stamp();
@@ -604,6 +607,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
           const int c = tx + 16 * j;
           if (c < lp) {
             const double qv = c < l ? q[i][j] * hs[j] : 0.0;
+            amax[j] = fmax(amax[j], fabs(qv));
             if (a.want_flip && c < l) {
               dsum[j] += fabs(o2[i][j] - qv);
               ssum[j] += fabs(o2[i][j] + qv);
@@ -612,6 +616,17 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
           }
         }
       }
+    }
+  }
+  if (a.colmax_out) {  // the 16 row-lanes of a column -> one atomicMax per column and CTA
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < R; ++j) As[ty * (LC + 1) + tx + 16 * j] = amax[j];
+    __syncthreads();
+    for (int c = tid; c < l; c += kOrthThreads) {
+      double m = 0.0;
+      for (int y = 0; y < 16; ++y) m = fmax(m, As[y * (LC + 1) + c]);
+      if (m > 0.0) atomicMax(a.colmax_out + c, (unsigned long long)__double_as_longlong(m));
     }
   }
   if (!a.want_flip) {

@@ -665,16 +665,28 @@ __global__ void __launch_bounds__(256) k_tc_reduce_fpart(const double* __restric
   if (lane == 0) Fw[c] = v;
 }
 
-// H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c. R is re-zeroed.
+// H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c. R is re-zeroed. Optionally
+// also Hsum = Hacc + Hother (the H = H1 + H2 of a winSVD Omega update) in the same sweep.
 // Ranges with missing calls add + 2^(e_c-p) * K[i][c], K = R2 = mask product with the image of
 // D~ = round((f_j - 1) W~_j): removes (1 - f_j) W~_j for the SNPs j missing in sample i.
 __global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__ R2, uint64_t nrows, int l, int lp, int S,
                               const long long* __restrict__ Csum, const unsigned long long* __restrict__ colmax,
-                              const double* __restrict__ Fw, double* __restrict__ Hacc, int accumulate) {
+                              const double* __restrict__ Fw, const double* __restrict__ Fpart, uint32_t nparts,
+                              double* __restrict__ Hacc, int accumulate, const double* __restrict__ Hother,
+                              double* __restrict__ Hsum) {
   __shared__ double sFw[kMaxNP], sScale[kMaxNP], sC[kMaxNP];
   const int p = 8 * S - 1;
   for (int c = threadIdx.x; c < l; c += blockDim.x) {
-    sFw[c] = Fw[c];
+    double fw;
+    if (Fpart) {
+      // Fw[c] = sum of the slice kernel's per-block partials, redone by every block in the same
+      // fixed order (few partials: a window) instead of a separate reduction launch
+      fw = 0.0;
+      for (uint32_t b = 0; b < nparts; ++b) fw += Fpart[(size_t)b * lp + c];
+    } else {
+      fw = Fw[c];
+    }
+    sFw[c] = fw;
     sScale[c] = scalbn(1.0, tc_exponent(colmax[c]) - p);
     sC[c] = (double)Csum[c];
   }
@@ -683,6 +695,7 @@ __global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % lp);
+    double out = 0.0;
     if (c < l) {
       const long long T = R[idx];
       R[idx] = 0;
@@ -691,10 +704,14 @@ __global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__
         h += sScale[c] * (double)R2[idx];
         R2[idx] = 0;
       }
-      Hacc[idx] = accumulate ? Hacc[idx] + h : h;
+      out = accumulate ? Hacc[idx] + h : h;
+      Hacc[idx] = out;
     } else if (!accumulate) {
       Hacc[idx] = 0.0;
+    } else {
+      out = Hacc[idx];
     }
+    if (Hsum) Hsum[idx] = out + Hother[idx];  // H = H1 + H2 for the Omega update that follows (Halko.cpp:209)
   }
 }
 
