@@ -216,18 +216,36 @@ class FileBgen:
 
     def prepare(self):
         """Variant selection of FileBgen.cpp:42-45: a variant is kept iff af > params.maf (so even
-        with the default --maf 0 an all-zero variant is dropped). Only the SELECTION happens here;
-        the allele frequencies the path uses are computed on the device (pcaone_allele_freq)."""
-        d = self.dosages.cpu().numpy() if _is_torch(self.dosages) else self.dosages
-        with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
-            __import__("warnings").simplefilter("ignore")
-            af = np.nanmean(d.astype(np.float64) / 2.0, axis=1)
-        keep = np.flatnonzero(np.nan_to_num(af) > self.params.maf)
+        with the default --maf 0 an all-zero variant is dropped). The allele frequencies come from
+        the device (k_dosage_af through a throw-away context); only the index selection is host
+        logic."""
+        L = _lib.load()
+        p = self.params
+        cfg = _lib.Config(nsamples=self.nsamples, nsnps=self.nsnps, nsnps_total=self.nsnps, k=1, oversamples=0, svd=1,
+                          bands=p.bands, maxp=1, tol=0.0, ploidy=p.ploidy, scale=p.scale, emu=0, out_of_core=0,
+                          precision=_lib.PREC_FP64, device=p.device, rank=0, world=1, maxiter=0, tolem=0.0)
+        h = C.c_void_p()
+        if L.pcaone_create(C.byref(cfg), C.byref(h)):
+            raise RuntimeError(L.pcaone_last_error(None).decode())
+        try:
+            on_dev = _is_torch(self.dosages) and self.dosages.is_cuda
+            af = np.zeros(self.nsnps)
+            for call in (lambda: L.pcaone_upload_dosage(h, _vp(self.dosages), self.nsnps, int(on_dev)),
+                         lambda: L.pcaone_allele_freq(h), lambda: L.pcaone_get_F(h, _vp(af))):
+                if call():
+                    raise RuntimeError(L.pcaone_last_error(h).decode())
+        finally:
+            L.pcaone_destroy(h)
+        keep = np.flatnonzero(af > p.maf)
         if len(keep) == 0:
             raise RuntimeError("the number of SNPs after filtering is 0!")
         if len(keep) != self.nsnps:
             self.keep = keep
-            self.dosages = np.ascontiguousarray(d[keep])
+            if _is_torch(self.dosages):
+                import torch
+                self.dosages = self.dosages[torch.as_tensor(keep, device=self.dosages.device)].contiguous()
+            else:
+                self.dosages = np.ascontiguousarray(self.dosages[keep])
             self.nsnps = len(keep)
 
 
