@@ -37,7 +37,7 @@ enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cm
  * missing genotypes run each product as a (non-missing count, missing mask) pair on the same
  * kernels (mean imputation); EMU update passes still run on the FP64 kernels. */
 enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_INT8X2 = 2, PCAONE_PREC_INT8X3 = 3, PCAONE_PREC_INT8X4 = 4 };
-enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3, PCAONE_SRC_DOSAGE = 4 };
+enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3, PCAONE_SRC_DOSAGE = 4, PCAONE_SRC_GL = 5 };
 
 /* Mirrors the fields of `Param` (Cmd.hpp:16-98) that the hot path reads. */
 typedef struct pcaone_config {
@@ -189,6 +189,19 @@ int pcaone_x_times(pcaone_ctx* ctx, const double* B, uint32_t ncols, double* out
  * context behaves like a resident genotype shard (sSVD / winSVD, pcaone_permute_resident,
  * pcaone_set_blocks). precision must be PCAONE_PREC_FP64; --emu is rejected for this source. */
 int pcaone_upload_dosage(pcaone_ctx* ctx, const float* dosage, uint64_t nsnps, int device_ptr);
+
+/* ---- Beagle genotype likelihoods, PCAngsd (FileBeagle::read_all FileBeagle.cpp:14-68, emMAF_with_GL
+ * Utils.cpp:745-775, Data::fit_with_pi Data.cpp:296-316, EM loop Halko.cpp:290-311) -------------------
+ * The host keeps the gz text parsing (parse_beagle_file) and hands over the reference's own matrix
+ * P: 2*nsamples x nsnps doubles, column-major, P(2i, j) / P(2i+1, j) = likelihoods of genotypes 0 / 1.
+ * pcaone_gl_em_maf runs the allele-frequency EM from F = 0.25 (iters_out: EM steps taken).
+ * The expected genotypes E = (p1 + 2 p2) / (p0 + p1 + p2) - 2 F are rebuilt on the device at pi == 0 of
+ * every computeUSV — from F, or on update passes from the individual allele frequencies of the current
+ * U, S, V — and feed the dense FP64 products; pcaone_run_em (with emu = 0) is the PCAngsd EM loop,
+ * pcaone_decode_block returns E blocks. precision = PCAONE_PREC_FP64, single GPU. The GRM step after
+ * the loop (pcangsd_standardize_E + the N x N covariance, Halko.cpp:320-334) is not built. */
+int pcaone_upload_gl(pcaone_ctx* ctx, const double* P, uint64_t nsnps, int device_ptr);
+int pcaone_gl_em_maf(pcaone_ctx* ctx, uint32_t maxiter, double tolmaf, int* iters_out);
 
 /* ---- generic dense matrix: RsvdOpOnePass / RsvdOnePass / RsvdOne (RSVD.hpp:92-362) ----------
  * The same passes on a dense FP64 matrix A (rows x cols, column-major, as Eigen hands it over)

@@ -35,6 +35,7 @@ def lib():
         L.ref_perm_size.restype = C.c_longlong
         L.ref_missing_count.restype = C.c_longlong
         L.ref_ld_r2.restype = C.c_longlong
+        L.ref_get_P.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -192,6 +193,13 @@ class Ref:
         self._chk(lib().ref_ld_prune(self.h, filebim.encode(), int(ld_bp), C.c_double(r2_tol), fileout.encode(),
                                      _p(keep), C.c_longlong(int(self.M))))
         return keep.astype(bool)
+
+    def P(self):
+        """Beagle input: the 2N x M likelihood matrix parse_beagle_file filled."""
+        n = lib().ref_get_P(self.h, None)
+        out = _f((2 * self.N, n // (2 * self.N)))
+        lib().ref_get_P(self.h, _p(out))
+        return out
 
     def perform_op(self, x, update=False, standardize=True):
         """ArnoldiOpData(data).perform_op(x) on this (out-of-core) run -> y (N)."""

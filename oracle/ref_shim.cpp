@@ -18,6 +18,7 @@
 //   calc_sds / divide_pos_by_window (src/LD.cpp:48,154)
 //   PCAone::RsvdOne  (src/RSVD.hpp:327-362, the dense-matrix front-end PCAoneR binds)
 //   ArnoldiOpData::perform_op (src/Arnoldi.cpp:18-46, the IRAM operator)
+//   FileBeagle       (src/FileBeagle.cpp:14-68; PCAngsd EM through the same ref_run_em)
 #define _DECLARE_TOOLBOX_HERE
 #include <omp.h>
 
@@ -31,6 +32,7 @@
 #include "Cmd.hpp"
 #include "Common.hpp"
 #include "Data.hpp"
+#include "FileBeagle.hpp"
 #include "FileBinary.hpp"
 #include "FilePlink.hpp"
 #include "Arnoldi.hpp"
@@ -106,8 +108,10 @@ void* ref_open(const char* cmdline) {
       } else {
         c->data = new FileBed(params);
       }
+    } else if (params.file_t == FileType::BEAGLE) {
+      c->data = new FileBeagle(params);   // genotype likelihoods; read_all runs emMAF_with_GL and builds E
     } else {
-      throw std::runtime_error("ref_shim: only --bfile / --binary inputs are driven by the oracle");
+      throw std::runtime_error("ref_shim: only --bfile / --binary / --beagle inputs are driven by the oracle");
     }
     c->data->prepare();
   });
@@ -452,6 +456,13 @@ int ref_ld_prune(void* h, const char* filebim, int ld_bp, double r2_tol, const c
     }
     if (have) throw std::runtime_error("ref_ld_prune: kept list does not align with the bim");
   });
+}
+
+// Beagle input: the parsed likelihood matrix P (2N x M, column-major) as FileBeagle::read_all left it.
+long long ref_get_P(void* h, double* out) {
+  RefCtx* c = (RefCtx*)h;
+  if (out) std::memcpy(out, c->data->P.data(), sizeof(double) * c->data->P.size());
+  return (long long)c->data->P.size();
 }
 
 // Data::write_residuals (Data.cpp:242-291) via the reference writer.

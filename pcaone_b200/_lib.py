@@ -49,6 +49,7 @@ SYMBOLS = [
     "pcaone_orth_omega", "pcaone_mev", "pcaone_init_omega", "pcaone_shuffle_indices", "pcaone_ld_r2",
     "pcaone_get_timers", "pcaone_enable_timing", "pcaone_alloc_pinned", "pcaone_free_pinned", "pcaone_device_count",
     "pcaone_upload_dense", "pcaone_dense_rsvd", "pcaone_upload_dosage", "pcaone_perform_op", "pcaone_ld_prune", "pcaone_xt_times", "pcaone_x_times",
+    "pcaone_upload_gl", "pcaone_gl_em_maf",
 ]
 
 _lib = None
@@ -88,6 +89,7 @@ def load():
         "pcaone_get_timers": [vp, C.POINTER(Timers), i32], "pcaone_enable_timing": [vp, i32],
         "pcaone_upload_dense": [vp, vp, u64, u64], "pcaone_dense_rsvd": [vp, u32, u32, i32],
         "pcaone_upload_dosage": [vp, vp, u64, i32], "pcaone_perform_op": [vp, vp, vp], "pcaone_xt_times": [vp, vp, u32, vp, vp], "pcaone_x_times": [vp, vp, u32, vp],
+        "pcaone_upload_gl": [vp, vp, u64, i32], "pcaone_gl_em_maf": [vp, u32, dbl, vp],
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

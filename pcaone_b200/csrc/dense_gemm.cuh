@@ -443,6 +443,88 @@ __global__ void k_dosage_decode(const float* __restrict__ D, uint32_t ldd, uint3
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Beagle genotype likelihoods (PCAngsd): FileBeagle.cpp:14-68, Utils.cpp:745-775, Data.cpp:296-316
+// P: [rows][2N] doubles, (P0, P1) of sample i at 2i, 2i+1 — the columns of the reference's 2N x M
+// matrix P. The expected genotypes E = G are MATERIALISED as the dense source ([rows][ldd] doubles),
+// like the reference does in core: E changes once per EM iteration, not per pass, so evaluating the
+// k-term individual allele frequency inside every GEMM operand load would repeat that work
+// (2 products x epochs) times.
+// ------------------------------------------------------------------------------------------
+
+// one EM step of emMAF_with_GL (Utils.cpp:753-765) for every variant: one warp per variant.
+// Fnew[j] = sum_i (p1 + 2 p2) / (p0 + p1 + p2) / (2N); sq[j] = (Fnew - F)^2
+__global__ void __launch_bounds__(256) k_gl_maf_step(const double* __restrict__ P, uint32_t N, uint64_t rows,
+                                                      const double* __restrict__ F, double* __restrict__ Fnew,
+                                                      double* __restrict__ sq) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const double scale = 1.0 / (2.0 * (double)N);
+  for (uint64_t j = warp; j < rows; j += nwarps) {
+    const double2* row = reinterpret_cast<const double2*>(P + j * 2ull * N);
+    const double f = F[j], omf = 1.0 - f;
+    double pt = 0.0;
+    for (uint32_t i = lane; i < N; i += 32) {
+      const double2 g = row[i];
+      const double p0 = __dmul_rn(__dmul_rn(g.x, omf), omf);
+      const double p1 = __dmul_rn(__dmul_rn(__dmul_rn(g.y, 2.0), f), omf);
+      const double p2 = __dmul_rn(__dmul_rn(__dsub_rn(__dsub_rn(1.0, g.x), g.y), f), f);
+      pt += __ddiv_rn(__dadd_rn(p1, __dmul_rn(2.0, p2)), __dadd_rn(__dadd_rn(p0, p1), p2));
+    }
+    pt = warp_sum(pt);
+    if (lane == 0) {
+      const double fn = pt * scale;
+      Fnew[j] = fn;
+      sq[j] = (fn - f) * (fn - f);
+    }
+  }
+}
+
+// out[0] = sum of v[0..n) in a fixed order (one CTA)
+__global__ void __launch_bounds__(1024) k_sum_fixed(const double* __restrict__ v, uint64_t n, double* __restrict__ out) {
+  __shared__ double s[1024];
+  double a = 0.0;
+  for (uint64_t i = threadIdx.x; i < n; i += 1024) a += v[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+// E[j][i] = (p1 + 2 p2) / (p0 + p1 + p2) - 2 F_j with pt = F_j (initial E, FileBeagle.cpp:57-66) or the
+// individual allele frequency pt = clamp((U_i . (S o V_j) + 2 F_j) / 2, 1e-4, 1 - 1e-4) (fit_with_pi,
+// Data.cpp:296-316). U: [N][ldu], V: [rows][ldv] row-major device layouts; U == nullptr -> initial.
+__global__ void k_gl_expected(const double* __restrict__ P, uint32_t N, uint64_t rows, const double* __restrict__ F,
+                              const double* __restrict__ U, int ldu, const double* __restrict__ S,
+                              const double* __restrict__ V, int ldv, int k, double* __restrict__ E, uint32_t ldd) {
+  const uint64_t total = rows * N;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = idx / N;
+    const uint32_t i = (uint32_t)(idx - j * N);
+    const double f = F[j];
+    double pt = f;
+    if (U) {
+      pt = 0.0;
+      for (int r = 0; r < k; ++r) pt = __dadd_rn(pt, __dmul_rn(__dmul_rn(U[(uint64_t)i * ldu + r], S[r]), V[j * ldv + r]));
+      pt = __ddiv_rn(__dadd_rn(pt, __dmul_rn(2.0, f)), 2.0);
+      pt = fmin(fmax(pt, 1e-4), 1.0 - 1e-4);
+    }
+    const double2 g = reinterpret_cast<const double2*>(P + j * 2ull * N)[i];
+    const double omp = __dsub_rn(1.0, pt);
+    const double p0 = __dmul_rn(__dmul_rn(g.x, omp), omp);
+    const double p1 = __dmul_rn(__dmul_rn(__dmul_rn(g.y, 2.0), pt), omp);
+    const double p2 = __dmul_rn(__dmul_rn(__dsub_rn(__dsub_rn(1.0, g.x), g.y), pt), pt);
+    E[j * ldd + i] = __dsub_rn(__ddiv_rn(__dadd_rn(p1, __dmul_rn(2.0, p2)), __dadd_rn(__dadd_rn(p0, p1), p2)),
+                               __dmul_rn(2.0, f));
+  }
+}
+
 // col-major (rows x cols, ld = rows) -> row-major [rows][ldd], 32 x 32 tiles through shared memory
 __global__ void __launch_bounds__(256) k_dense_transpose_in(const double* __restrict__ src, uint64_t rows, uint64_t cols,
                                                              double* __restrict__ dst, uint32_t ldd) {

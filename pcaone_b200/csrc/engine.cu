@@ -55,6 +55,7 @@ struct pcaone_ctx {
   int source = -1;
   double* d_dense = nullptr;  // PCAONE_SRC_DENSE: tall orientation of a generic matrix, row-major [M][ldd]
   uint32_t ldd = 0;
+  double* d_P = nullptr;      // PCAONE_SRC_GL: genotype likelihoods [M][2N]; the expected genotypes E live in d_dense
   float* d_dos = nullptr;     // PCAONE_SRC_DOSAGE: float dosages, row-major [M][ldf], NaN = missing
   uint32_t ldf = 0;
   uint8_t* d_packed = nullptr;  // resident, M x pitch
@@ -695,7 +696,7 @@ void range_gemms_dosage(pcaone_ctx* c, uint64_t r0, uint32_t nrows, double* Hacc
 void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0, double* Hacc, bool accumulate,
                  int buf) {
   if (nrows == 0) return;
-  if (c->source == PCAONE_SRC_DENSE) {
+  if (c->source == PCAONE_SRC_DENSE || c->source == PCAONE_SRC_GL) {
     range_gemms_dense(c, snp0, nrows, Hacc, accumulate);
     return;
   }
@@ -1151,6 +1152,19 @@ void incore_windows(pcaone_ctx* c, std::vector<uint64_t>& ws, std::vector<uint64
 
 void zero_async(pcaone_ctx* c, double* p, uint64_t n) { PCA_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), c->stream)); }
 
+// Beagle / PCAngsd: (re)build the expected genotypes E from the likelihoods — with pt = F
+// (FileBeagle.cpp:57-66) or, on update passes, the individual allele frequencies of the current
+// U, S, V (Data::fit_with_pi, Data.cpp:296-316, called at pi == 0 by Halko.cpp:108-118).
+void gl_refresh(pcaone_ctx* c, uint64_t r0, uint64_t nrows, bool update, double* E, uint32_t ldd) {
+  if (!c->af_done) throw std::runtime_error("GL source: call pcaone_gl_em_maf (or pcaone_set_F) first");
+  if (update && !c->have_usv) throw std::runtime_error("GL update pass without U,S,V");
+  k_gl_expected<<<grid_for(nrows * c->N, 256, c->sms), 256, 0, c->stream>>>(
+      c->d_P + r0 * 2ull * c->N, (uint32_t)c->N, nrows, c->d_F + r0, update ? c->d_U : nullptr, c->lp, c->d_S,
+      c->d_V + r0 * c->lp, c->lp, c->k, E, ldd);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
 void compute_gandh(pcaone_ctx* c, int pi) {
   if (c->source < 0) throw std::runtime_error("no genotype source set");
   if (c->update && c->cfg.emu && !c->have_usv) throw std::runtime_error("EMU update pass without U,S,V");
@@ -1169,6 +1183,10 @@ void compute_gandh(pcaone_ctx* c, int pi) {
     alloc_stream_buffers(c);
   } else if (!c->af_done && c->source != PCAONE_SRC_DENSE) {
     throw std::runtime_error("call pcaone_allele_freq before the first pass");
+  }
+  if (c->source == PCAONE_SRC_GL && pi == 0) {
+    Timed t(c, 6);
+    gl_refresh(c, 0, c->M, c->update != 0, c->d_dense, c->ldd);
   }
 
   if (!win) {
@@ -1566,6 +1584,7 @@ void run_em(pcaone_ctx* c, int* iters_out) {
   flip_uv(c);
   int iters = 0;
   const uint64_t vbytes = c->M * c->lp * sizeof(double);
+  if (!c->d_Vpre) dmalloc(&c->d_Vpre, c->M * c->lp);  // PCAngsd EM on a context created with emu = 0
   for (uint32_t i = 0; i < c->cfg.maxiter; ++i) {
     c->update = 1;
     c->standardize = 0;
@@ -1893,7 +1912,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_status, (void*)c->d_part, (void*)c->d_pidx, (void*)c->d_stage, (void*)c->d_raw[0],
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
-                  (void*)c->d_dense, (void*)c->d_dos, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
+                  (void*)c->d_dense, (void*)c->d_P, (void*)c->d_dos, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -2013,10 +2032,11 @@ int pcaone_set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop
 
 int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
   CTX_GUARD(c, {
-    if (c->source != PCAONE_SRC_RESIDENT && c->source != PCAONE_SRC_DOSAGE)
+    if (c->source != PCAONE_SRC_RESIDENT && c->source != PCAONE_SRC_DOSAGE && c->source != PCAONE_SRC_GL)
       throw std::runtime_error("permute_resident needs a resident shard");
-    const bool dos = c->source == PCAONE_SRC_DOSAGE;
-    const uint32_t row_bytes = dos ? c->ldf * (uint32_t)sizeof(float) : c->pitch;  // both multiples of 16
+    const bool gl = c->source == PCAONE_SRC_GL;
+    const bool dos = c->source == PCAONE_SRC_DOSAGE || gl;  // rows of d_dos / d_P instead of d_packed
+    const uint32_t row_bytes = gl ? (uint32_t)(16 * c->N) : dos ? c->ldf * (uint32_t)sizeof(float) : c->pitch;  // multiples of 16
     uint32_t* d_idx = nullptr;
     uint8_t* d_new = nullptr;
     double* d_Fn = nullptr;
@@ -2025,7 +2045,8 @@ int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
     dmalloc(&d_Fn, c->M);
     PCA_CUDA(cudaMemcpyAsync(d_idx, indices, c->M * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     k_gather_rows<<<grid_for(c->M * (row_bytes >> 4), 256, c->sms), 256, 0, c->stream>>>(
-        dos ? reinterpret_cast<const uint8_t*>(c->d_dos) : c->d_packed, d_new, d_idx, c->M, row_bytes);
+        gl ? reinterpret_cast<const uint8_t*>(c->d_P) : dos ? reinterpret_cast<const uint8_t*>(c->d_dos) : c->d_packed,
+        d_new, d_idx, c->M, row_bytes);
     k_gather_f64<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_F, d_Fn, d_idx, c->M);
     PCA_CHECK_LAUNCH();
     PCA_CUDA(cudaStreamSynchronize(c->stream));
@@ -2034,11 +2055,13 @@ int pcaone_permute_resident(pcaone_ctx* c, const uint32_t* indices) {
     k_gather_u32<<<grid_for(c->M, 256, c->sms), 256, 0, c->stream>>>(c->d_nmiss, d_nm, d_idx, c->M);
     PCA_CHECK_LAUNCH();
     PCA_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(dos ? (void*)c->d_dos : (void*)c->d_packed);
+    cudaFree(gl ? (void*)c->d_P : dos ? (void*)c->d_dos : (void*)c->d_packed);
     cudaFree(c->d_F);
     cudaFree(c->d_nmiss);
     cudaFree(d_idx);
-    if (dos)
+    if (gl)
+      c->d_P = reinterpret_cast<double*>(d_new);
+    else if (dos)
       c->d_dos = reinterpret_cast<float*>(d_new);
     else
       c->d_packed = d_new;
@@ -2064,6 +2087,8 @@ int pcaone_allele_freq(pcaone_ctx* c) {
                                                                           c->d_F, c->d_nmiss);
       PCA_CHECK_LAUNCH();
       c->tm.kernel_launches++;
+    } else if (c->source == PCAONE_SRC_GL) {
+      throw std::runtime_error("allele_freq: genotype likelihoods use pcaone_gl_em_maf");
     } else if (c->source == PCAONE_SRC_DENSE) {
       throw std::runtime_error("allele_freq: a dense matrix has no allele frequencies");
     } else if (c->source >= 0) {
@@ -2141,6 +2166,13 @@ int pcaone_decode_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int standa
                                                                              (uint32_t)c->N, B, c->d_F + start, p,
                                                                              c->d_stage);
       PCA_CHECK_LAUNCH();
+      PCA_CUDA(cudaMemcpyAsync(out, c->d_stage, c->N * B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    if (c->source == PCAONE_SRC_GL) {  // E block: initial (FileBeagle.cpp:57-66) or fit_with_pi (Data.cpp:296-316)
+      ensure_stage(c, c->N * B);
+      gl_refresh(c, start, B, update != 0, c->d_stage, (uint32_t)c->N);
       PCA_CUDA(cudaMemcpyAsync(out, c->d_stage, c->N * B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       PCA_CUDA(cudaStreamSynchronize(c->stream));
       return 0;
@@ -2328,6 +2360,55 @@ int pcaone_upload_dosage(pcaone_ctx* c, const float* dosage, uint64_t nsnps, int
     if (!device_ptr) c->tm.h2d_bytes += c->M * c->N * sizeof(float);
     c->source = PCAONE_SRC_DOSAGE;
     c->af_done = false;
+  });
+}
+
+int pcaone_upload_gl(pcaone_ctx* c, const double* P, uint64_t nsnps, int device_ptr) {
+  CTX_GUARD(c, {
+    if (nsnps != c->M) throw std::runtime_error("upload_gl: nsnps does not match the context");
+    if (c->cfg.precision != PCAONE_PREC_FP64) throw std::runtime_error("upload_gl: genotype likelihoods run in FP64");
+    if (c->cfg.emu) throw std::runtime_error("upload_gl: --emu does not apply to genotype likelihoods (PCAngsd EM is pcaone_run_em with emu = 0)");
+    if (c->cfg.world > 1) throw std::runtime_error("upload_gl: single-GPU only");
+    c->ldd = (uint32_t)round_up(c->N, 8);
+    if (!c->d_P) dmalloc(&c->d_P, c->M * 2 * c->N);
+    if (!c->d_dense) dmalloc(&c->d_dense, c->M * (size_t)c->ldd);
+    PCA_CUDA(cudaMemsetAsync(c->d_dense, 0, c->M * (size_t)c->ldd * sizeof(double), c->stream));
+    PCA_CUDA(cudaMemcpyAsync(c->d_P, P, c->M * 2 * c->N * sizeof(double),
+                             device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    if (!device_ptr) c->tm.h2d_bytes += c->M * 2 * c->N * sizeof(double);
+    c->source = PCAONE_SRC_GL;
+    c->af_done = false;
+  });
+}
+
+int pcaone_gl_em_maf(pcaone_ctx* c, uint32_t maxiter, double tolmaf, int* iters_out) {
+  CTX_GUARD(c, {
+    if (c->source != PCAONE_SRC_GL) throw std::runtime_error("gl_em_maf: call pcaone_upload_gl first");
+    // emMAF_with_GL (Utils.cpp:745-775): F = 0.25, EM steps until the RMS change over all variants < tolmaf
+    std::vector<double> f0(c->M, 0.25);
+    PCA_CUDA(cudaMemcpyAsync(c->d_F, f0.data(), c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ensure_stage(c, 2 * c->M + 8);
+    double* Fnew = c->d_stage;
+    double* sq = c->d_stage + c->M;
+    int it = 0;
+    for (; it < (int)maxiter; ++it) {
+      k_gl_maf_step<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_P, (uint32_t)c->N, c->M, c->d_F, Fnew, sq);
+      PCA_CHECK_LAUNCH();
+      k_sum_fixed<<<1, 1024, 0, c->stream>>>(sq, c->M, c->d_scal);
+      PCA_CHECK_LAUNCH();
+      PCA_CUDA(cudaMemcpyAsync(c->d_F, Fnew, c->M * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      PCA_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      PCA_CUDA(cudaStreamSynchronize(c->stream));
+      c->tm.kernel_launches += 2;
+      if (sqrt(c->h_scal[0] / (double)c->M) < tolmaf) {
+        ++it;
+        break;
+      }
+    }
+    if (iters_out) *iters_out = it;
+    PCA_CUDA(cudaMemsetAsync(c->d_nmiss, 0, c->M * sizeof(uint32_t), c->stream));
+    c->af_done = true;
   });
 }
 

@@ -249,6 +249,65 @@ class FileBgen:
             self.nsnps = len(keep)
 
 
+class FileBeagle:
+    """`Data` for Beagle genotype-likelihood input, in-core (src/FileBeagle.cpp:14-68). The gz text
+    parsing stays on the host side of the boundary: this class takes the matrix the reference's
+    parse_beagle_file fills, P (2 * nsamples x nsnps, P[2i, j] / P[2i+1, j] = likelihoods of genotypes
+    0 / 1). prepare() runs the allele-frequency EM on the device (emMAF_with_GL, Utils.cpp:745-775)
+    and applies the `--maf` filter of Data::filter_snps_resize_F (Data.cpp:88-105)."""
+
+    def __init__(self, params: Param, P, tolmaf: float = 1e-6):
+        self.params = params
+        if params.out_of_core:
+            raise RuntimeError("doesn't support out-of-core PCAngsd algorithm")     # FileBeagle.cpp:77
+        if params.precision != _lib.PREC_FP64:
+            raise RuntimeError("FileBeagle: genotype likelihoods run on the FP64 kernels (precision = PREC_FP64)")
+        self.P = np.asfortranarray(P, dtype=np.float64)
+        if self.P.shape[0] % 2:
+            raise RuntimeError("P must have two rows per sample")
+        self.nsamples, self.nsnps = self.P.shape[0] // 2, int(self.P.shape[1])
+        self.tolmaf = tolmaf
+        self.packed = None
+        self.perm = None
+        self.start = self.stop = None
+        self.nblocks, self.blocksize, self.bandFactor = 1, 0, 1
+        self.keep = None
+        self.F = None
+        self.maf_iters = 0
+
+    def prepare(self):
+        L = _lib.load()
+        p = self.params
+        cfg = _lib.Config(nsamples=self.nsamples, nsnps=self.nsnps, nsnps_total=self.nsnps, k=1, oversamples=0, svd=1,
+                          bands=p.bands, maxp=1, tol=0.0, ploidy=p.ploidy, scale=p.scale, emu=0, out_of_core=0,
+                          precision=_lib.PREC_FP64, device=p.device, rank=0, world=1, maxiter=0, tolem=0.0)
+        h = C.c_void_p()
+        if L.pcaone_create(C.byref(cfg), C.byref(h)):
+            raise RuntimeError(L.pcaone_last_error(None).decode())
+        try:
+            F = np.zeros(self.nsnps)
+            it = C.c_int(0)
+            for call in (lambda: L.pcaone_upload_gl(h, _vp(self.P), self.nsnps, 0),
+                         lambda: L.pcaone_gl_em_maf(h, int(p.maxiter), C.c_double(self.tolmaf), C.byref(it)),
+                         lambda: L.pcaone_get_F(h, _vp(F))):
+                if call():
+                    raise RuntimeError(L.pcaone_last_error(h).decode())
+        finally:
+            L.pcaone_destroy(h)
+        self.maf_iters = it.value
+        self.F = F
+        if p.maf > 0:   # Data::filter_snps_resize_F: keep MAF(F) > maf
+            if not 0 < p.maf <= 0.5:
+                raise RuntimeError("--maf has to be between (0, 0.5)")
+            keep = np.flatnonzero(np.minimum(F, 1 - F) > p.maf)
+            if len(keep) < 1:
+                raise RuntimeError("no SNPs left after filtering!")
+            self.keep = keep
+            self.P = np.asfortranarray(self.P[:, keep])
+            self.F = F[keep]
+            self.nsnps = len(keep)
+
+
 class RsvdOpData:
     """Abstract op (src/Halko.hpp:6-42). Subclasses pick the computeGandH variant."""
     svd = None
@@ -277,7 +336,12 @@ class RsvdOpData:
             cb = _lib.ALLREDUCE_FN(allreduce)
             self._keep.append(cb)
             self._chk(L.pcaone_set_allreduce(self.h, cb, None))
-        if getattr(data, "dosages", None) is not None:
+        if getattr(data, "P", None) is not None:
+            if data.F is None:
+                raise RuntimeError("FileBeagle: call prepare() first")
+            self._chk(L.pcaone_upload_gl(self.h, _vp(data.P), data.nsnps, 0))
+            self._chk(L.pcaone_set_F(self.h, _vp(np.ascontiguousarray(data.F))))
+        elif getattr(data, "dosages", None) is not None:
             on_dev = _is_torch(data.dosages) and data.dosages.is_cuda
             self._chk(L.pcaone_upload_dosage(self.h, _vp(data.dosages), data.nsnps, int(on_dev)))
             self._chk(L.pcaone_allele_freq(self.h))
@@ -494,7 +558,9 @@ def run_pca_with_halko(data: FileBed, params: Param, **kw):
         raise RuntimeError("--svd 0: only ArnoldiOpData.perform_op is on the GPU; the IRAM driver (Spectra) is host code")
     cls = FancyRsvdOpData if params.svd == 2 else NormalRsvdOpData
     rsvd = cls(data, params.k, params.oversamples, **kw)
-    if not params.emu:
+    if getattr(data, "P", None) is not None:      # Beagle input => PCAngsd EM (Cmd.cpp:227, Halko.cpp:290-311)
+        rsvd.em_iters = rsvd.runEM()
+    elif not params.emu:
         rsvd.setFlags(False, not params.ld)
         rsvd.computeUSV(params.maxp, params.tol)
     else:

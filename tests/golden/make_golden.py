@@ -159,6 +159,32 @@ def main():
     r.close()
     np.savez_compressed(os.path.join(OUT, "ld_prune_small.npz"), af=af, tols=np.array([0.02, 0.1]), **pr)
 
+    # ---- I: Beagle genotype likelihoods, PCAngsd EM (FileBeagle.cpp, Utils.cpp:745-775, Data.cpp:296-316,
+    # Halko.cpp:290-311) on a synthetic low-depth beagle.gz written here
+    import gzip
+    Nb, Mb = 61, 300
+    rngb = np.random.default_rng(8)
+    codes_b = np.concatenate([c for _, c in synth.balding_nichols_codes(Nb, Mb, k_pop=4, seed=21)])
+    gt = np.array([2, 0, 1, 0])[codes_b]
+    depth = rngb.poisson(2.0, size=gt.shape)
+    alt = rngb.binomial(depth, np.clip(gt / 2.0, 0.01, 0.99))
+    lik = [np.clip(q / 2.0, 0.01, 0.99) ** alt * (1 - np.clip(q / 2.0, 0.01, 0.99)) ** (depth - alt) for q in (0, 1, 2)]
+    Lb = np.stack(lik, axis=-1)
+    Lb = Lb / Lb.sum(-1, keepdims=True)
+    bgl = os.path.join(tmp, "g.beagle.gz")
+    with gzip.open(bgl, "wt") as f:
+        f.write("marker\tallele1\tallele2" + "".join(f"\tInd{i}\tInd{i}\tInd{i}" for i in range(Nb)) + "\n")
+        for j in range(Mb):
+            f.write(f"chr1_{j + 1}\t0\t1" + "".join("\t%.6f\t%.6f\t%.6f" % tuple(Lb[j, i]) for i in range(Nb)) + "\n")
+    r = ref.Ref(f"PCAone --beagle {bgl} -k {K} -d 1 -o {tmp}/b --maxp 3 --tol-rsvd 0 --maxiter 4 -n 1", threads=thr)
+    Pb, Fb, E0 = r.P(), r.F(), r.dataG()
+    r.new_op()
+    omega_b = ref.init_omega(r.N, r.l, 112, True)
+    Ub, Sb, Vb, itb = r.run_em()
+    r.close()
+    np.savez_compressed(os.path.join(OUT, "pcangsd_small.npz"), P=Pb, F=Fb, E0=E0, omega=omega_b, U=Ub, S=Sb, V=Vb,
+                        iters=itb, k=K, maxp=3, maxiter=4)
+
     # ---- H: IRAM operator ArnoldiOpData::perform_op (Arnoldi.cpp:18-46) on the out-of-core plan
     r = ref.Ref(f"PCAone -b {bed} -k {K} -d 0 -m 0.00012 -o {tmp}/h -n 1", threads=thr)
     s3, e3 = r.block_plan()

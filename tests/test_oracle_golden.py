@@ -229,3 +229,18 @@ def test_ld_prune_restatement_vs_reference(tmp_path):
     for tol in pr["tols"]:
         assert np.array_equal(orc.ld_prune(G, ld["ws"], ld["we"], float(tol), pr["af"]), pr[f"keep_af_{tol}"])
         assert np.array_equal(orc.ld_prune(G, ld["ws"], ld["we"], float(tol), None), pr[f"keep_noaf_{tol}"])
+
+
+def test_pcangsd_restatement_vs_reference():
+    """emMAF_with_GL, the initial E and the PCAngsd EM loop restated in numpy against the unmodified
+    reference driven on a synthetic beagle.gz (tests/golden/pcangsd_small.npz)."""
+    g = golden("pcangsd_small")
+    P, k = g["P"], int(g["k"])
+    F, it = orc.em_maf_with_gl(P, int(g["maxiter"]), 1e-6)       # --maxiter also bounds the MAF EM (FileBeagle.cpp:52)
+    assert np.abs(F - g["F"]).max() < 1e-13
+    assert np.abs(orc.gl_expected(P, g["F"]) - g["E0"]).max() < 1e-13
+    od = orc.OracleGLData(P, g["F"])
+    oo = orc.OracleRsvd(od, k, omega=g["omega"])
+    U, S, V, iters = orc.run_emu(oo, int(g["maxp"]), 0.0, maxiter=int(g["maxiter"]), tolem=1e-5, final_standardize=False)
+    assert iters == int(g["iters"])
+    assert_usv_close(U, S, V, g["U"], g["S"], g["V"], eig_rtol=1e-10, min_corr=1 - 1e-10)

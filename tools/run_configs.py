@@ -275,6 +275,39 @@ def f_bgen(args, out):
     _emit(out, rec)
 
 
+def f_beagle(args, out):
+    """§8 f-1: Beagle genotype likelihoods, PCAngsd EM (allele-frequency EM, expected genotypes from the
+    individual allele frequencies once per EM iteration, dense FP64 DMMA products)."""
+    N, M, k = 2_000, int(200_000 * args.scale), 4
+    rng = np.random.default_rng(5)
+    pop = rng.integers(0, 5, N)
+    P = np.zeros((2 * N, M), order="F")
+    for s0 in range(0, M, 20_000):
+        m = min(20_000, M - s0)
+        pf = np.clip(rng.uniform(0.1, 0.9, (m, 1)) + 0.12 * rng.standard_normal((m, 5)), 0.05, 0.95)[:, pop]
+        gt = rng.binomial(2, pf)
+        d = rng.poisson(2.0, gt.shape)
+        alt = rng.binomial(d, np.clip(gt / 2.0, 0.01, 0.99))
+        lik = [np.clip(q / 2.0, 0.01, 0.99) ** alt * (1 - np.clip(q / 2.0, 0.01, 0.99)) ** (d - alt) for q in (0, 1, 2)]
+        tot = lik[0] + lik[1] + lik[2]
+        P[0::2, s0:s0 + m] = (lik[0] / tot).T
+        P[1::2, s0:s0 + m] = (lik[1] / tot).T
+    p = halko.Param(k=k, svd=1, maxp=20, tol=1e-4, maxiter=100, precision=_lib.PREC_FP64)
+    d = halko.FileBeagle(p, P)
+    t0 = time.perf_counter()
+    d.prepare()
+    maf_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    op = halko.run_pca_with_halko(d, p)
+    op.sync()
+    em_s = time.perf_counter() - t0
+    rec = {"config": "F1-beagle", "workload": f"PCAngsd EM on genotype likelihoods N={N} M={M} k={k} (depth ~2x), sSVD, FP64",
+           "gl_bytes": 16 * N * M, "maf_em_s_incl_upload": maf_s, "maf_em_iterations": d.maf_iters,
+           "pcangsd_s_incl_upload": em_s, "em_iterations": op.em_iters, "eigvals": (op.S ** 2 / M).tolist()}
+    op.close()
+    _emit(out, rec)
+
+
 def f_prune(args, out):
     """§8 f-2: greedy LD pruning on the device at config-5 size (r2 tiles never leave HBM)."""
     N, M = 20_000, int(200_000 * args.scale)
@@ -352,7 +385,7 @@ def main():
     ap.add_argument("--c4-prec", type=int, default=0)
     args = ap.parse_args()
     _lib.load()
-    fns = {"c1": c1, "c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "bgen": f_bgen, "prune": f_prune,
+    fns = {"c1": c1, "c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "bgen": f_bgen, "beagle": f_beagle, "prune": f_prune,
            "iram": f_iram, "dense": f_dense}
     for w in args.which:
         t0 = time.perf_counter()
