@@ -114,8 +114,13 @@ Param::Param(int argc, char** argv) {
   off_path("B", "binary", true);
   off_path("c", "csv", true);
   off_path("g", "bgen", true);
-  off_path("G", "beagle", true);
-  off_path("", "pcangsd", false);
+  val("G", "beagle", "path of BEAGLE file compressed by gzip (genotype likelihoods, PCAngsd algorithm).",
+      [this](const std::string& v) {
+        filein = v;
+        file_t = FileType::BEAGLE;
+      });
+  sw("", "pcangsd", "use PCAngsd algorithm for genotype likelihood input.", &pcangsd);
+  val("", "tol-maf", "tolerance for MAF estimation by EM.", [this](const std::string& v) { tolmaf = std::stod(v); });
   off_path("", "hardcall", false);
   off_path("", "maf", true);
   off_path("", "project", true);
@@ -207,7 +212,8 @@ Param::Param(int argc, char** argv) {
       svd_t = SvdType::PCAoneAlg2;
     else
       throw std::invalid_argument("--svd 0 (IRAM) and 3 (full SVD) are outside the B200 randomized-SVD path; use --svd 1 or 2");
-    if (file_t != FileType::PLINK) throw std::invalid_argument("please give the PLINK prefix with -b/--bfile");
+    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE)
+      throw std::invalid_argument("please give the PLINK prefix with -b/--bfile or a BEAGLE file with -G/--beagle");
     genetic = true;
     if (!usvprefix.empty()) {
       fileU = usvprefix + ".eigvecs";
@@ -223,10 +229,18 @@ Param::Param(int argc, char** argv) {
     oversamples = oversamples > k ? oversamples : k;  // Cmd.cpp:216
     if (haploid && genetic) ploidy = 1;
     if (memory > 0) out_of_core = true;
-    if (emu)
+    if (dopca && file_t == FileType::BEAGLE) pcangsd = true;  // Cmd.cpp:227
+    if (emu || pcangsd)
       missme = true;
     else if (dopca)
       maxiter = 0;
+    if (file_t == FileType::BEAGLE) {
+      if (out_of_core) throw std::invalid_argument("not supporting -m option (out-of-core) for PCAngsd and BEAGLE input yet!");
+      if (emu) throw std::invalid_argument("--emu does not apply to BEAGLE input (PCAngsd is used)");
+      if (print_r2 || ld) throw std::invalid_argument("LD options need PLINK input on the B200 path");
+      if (gpus > 1) throw std::invalid_argument("--gpus > 1 is not available for BEAGLE input");
+      precision = "fp64";  // genotype likelihoods run on the FP64 kernels
+    }
     if (bands < 4 || bands % 2 != 0)
       throw std::invalid_argument("the -w/--batches must be a power of 2 and the minimun is 4.");
     if (svd_t == SvdType::PCAoneAlg2 && !noshuffle) perm = true;

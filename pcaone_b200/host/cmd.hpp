@@ -37,6 +37,7 @@ class Param {
   bool perm = false;
   uint maxiter = 100;
   double tolem = 1e-5;
+  double tolmaf = 1e-6;
   double maf = 0.0;
   uint oversamples = 10;
   double tol = 1e-4;

@@ -4,6 +4,7 @@
 // into libpcaone_b200.so. There is no CPU fallback: without a CUDA device the first call fails.
 #include <thread>
 
+#include "beagle.hpp"
 #include "halko.hpp"
 #include "ld.hpp"
 
@@ -34,6 +35,14 @@ int main(int argc, char* argv[]) {
       params.perm = false;
       FileBed data(params);
       run_ld_stuff(&data, params);
+      return bye();
+    }
+    if (params.file_t == FileType::BEAGLE) {  // Main.cpp:117-120 + Halko.cpp:290-311 (PCAngsd EM)
+      FileBeagle data(params);
+      data.tolmaf = params.tolmaf;
+      data.prepare();
+      run_pca_with_halko(&data, params);
+      cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
       return bye();
     }
     if (params.gpus > 1) {

@@ -27,7 +27,8 @@ def test_cli_binary_is_built_and_prints_reference_flags():
     assert os.path.exists(BIN), "run __graft_entry__.build()"
     out = _run(["--help"]).stdout
     for flag in ("--bfile", "--pc", "--svd", "--memory", "--batches", "--no-shuffle", "--emu", "--maxp", "--tol-rsvd",
-                 "--print-r2", "--ld-bp", "--printv", "--out", "--seed", "--oversamples", "--gpus", "--precision"):
+                 "--print-r2", "--ld-bp", "--printv", "--out", "--seed", "--oversamples", "--gpus", "--precision", "--beagle",
+                 "--pcangsd", "--tol-maf"):
         assert flag in out, flag
 
 
@@ -36,6 +37,7 @@ def test_cli_rejects_bad_options(tmp_path):
     assert _run(["-b", "x", "--svd", "0"], ok=False).returncode != 0          # IRAM is off the GPU path
     r = _run(["-b", "x", "--bgen", "y"], ok=False)
     assert r.returncode != 0 and "outside the B200" in r.stderr
+    assert _run(["--beagle", "x.gz", "--emu"], ok=False).returncode != 0
     assert _run(["-b", "x", "-k", "abc"], ok=False).returncode != 0
     assert _run(["--nope"], ok=False).returncode != 0
     # a missing / corrupt bed is an error, not a silent fallback
@@ -165,3 +167,38 @@ def test_cli_print_r2_vs_reference(tmp_path):
     r.close()
     assert r2.shape == want.shape
     assert np.abs(r2 - want).max() < 2e-6  # std::to_string keeps 6 decimals
+
+
+def _write_beagle(path, P):
+    """BEAGLE text (gz) from the 2N x M likelihood matrix: the columns parse_beagle_file reads."""
+    N, M = P.shape[0] // 2, P.shape[1]
+    with gzip.open(path, "wt") as f:
+        f.write("marker\tallele1\tallele2" + "".join(f"\tInd{i}\tInd{i}\tInd{i}" for i in range(N)) + "\n")
+        for j in range(M):
+            p0, p1 = P[0::2, j], P[1::2, j]
+            f.write(f"chr1_{j + 1}\t0\t1" + "".join("\t%.6f\t%.6f\t%.6f" % (a, b, max(1 - a - b, 0.0)) for a, b in zip(p0, p1)) + "\n")
+
+
+@pytest.mark.gpu
+def test_cli_beagle_pcangsd_vs_reference_golden(tmp_path):
+    """--beagle: gz parsing on the host, PCAngsd EM on the device; against U, S of the unmodified
+    reference on the same likelihoods (tests/golden/pcangsd_small.npz, six-decimal text round trip)."""
+    from conftest import golden
+    g = golden("pcangsd_small")
+    P, k = g["P"], int(g["k"])
+    N, M = P.shape[0] // 2, P.shape[1]
+    bgl = str(tmp_path / "g.beagle.gz")
+    _write_beagle(bgl, P)
+    out = str(tmp_path / "o")
+    r = _run(["--beagle", bgl, "-k", k, "-d", 1, "-o", out, "--maxp", int(g["maxp"]), "--tol-rsvd", 0, "--maxiter",
+              int(g["maxiter"]), "-V"])
+    U, S, V = _load(out, k, M)
+    assert U.shape[0] == N and V.shape == (M, k)
+    assert np.max(np.abs(S - g["S"]) / g["S"]) < 1e-5
+    assert col_cos(U, g["U"]).min() > 0.9999 and col_cos(V, g["V"]).min() > 0.9999
+    # winSVD with the in-core shuffle runs too and finds the same top PCs
+    out2 = str(tmp_path / "o2")
+    _run(["-G", bgl, "-k", k, "-d", 2, "-w", 8, "-o", out2, "--maxiter", 4, "-V"])
+    U2, S2, V2 = _load(out2, k, M)
+    assert col_cos(U2[:, :1], U[:, :1]).min() > 0.99 and V2.shape == (M, k)
+    assert _run(["--beagle", bgl, "-m", "0.001", "-o", out], ok=False).returncode != 0   # Cmd.cpp:233
