@@ -128,7 +128,7 @@ Param::Param(int argc, char** argv) {
   off_path("", "project-bootstrap-save", false);
   off_path("", "inbreed", true);
   off_path("", "selection", true);
-  off_path("", "ld-r2", true);
+  val("", "ld-r2", "r2 cutoff for LD-based pruning (usually 0.2).", [this](const std::string& v) { ld_r2 = std::stod(v); });
   off_path("", "clump", true);
   off_path("", "clump-names", true);
   off_path("", "clump-p1", true);
@@ -222,7 +222,7 @@ Param::Param(int argc, char** argv) {
       fileV = usvprefix + ".loadings";
       if (filebim.empty()) filebim = usvprefix + ".mbim";
     }
-    if (print_r2) {  // Cmd.cpp:181-184
+    if (print_r2 || ld_r2 > 0) {  // Cmd.cpp:181-184
       dopca = false;
       memory /= 2.0;
     }

@@ -30,6 +30,7 @@ void get_snp_pos_bim(SNPld& snp, const std::string& filebim) {
       snp.chr.push_back(t[0]);
     }
     prev = t[0];
+    if (t.size() == 7) snp.af.push_back(std::stod(t[6]));  // LD.cpp:90
     snp.pos.push_back(std::stoi(t[3]));
     ++i;
   }
@@ -77,7 +78,32 @@ void run_ld_stuff(Data* data, const Param& params) {
   get_snp_pos_bim(snp, filebim);
   if ((uint64)snp.pos.size() != data->nsnps) cao.error("the number of SNPs in " + filebim + " does not match the bed");
   divide_pos_by_window(snp, (int)params.ld_bp);
-  if (!params.print_r2) cao.error("LD pruning / clumping is outside the B200 path for now; use --print-r2");
+  if (!params.print_r2) {
+    // ld_prune_big (LD.cpp:240-268): greedy pruning on the device, then write_pruned_snp_ids (:170-190)
+    if (!(params.ld_r2 > 0)) cao.error("give --print-r2 or --ld-r2 <cutoff>");
+    const bool pick_random_one = snp.af.empty();
+    cao.print(tick.date(), "LD pruning, choose sites to be kept randomly or with high MAF? 1(random) : 0(high MAF). =>",
+              pick_random_one);
+    if (!snp.af.empty() && snp.af.size() != data->nsnps) cao.error("the 7th column (allele frequency) must be on every line");
+    std::vector<uint8_t> keep(data->nsnps, 1);
+    data->check(pcaone_ld_prune(data->ctx, nullptr, data->nsnps, snp.ws.data(), snp.we.data(), snp.ws.size(),
+                                snp.af.empty() ? nullptr : snp.af.data(), params.ld_r2, keep.data()));
+    uint64 nkeep = 0;
+    for (uint8_t k : keep) nkeep += k;
+    cao.print(tick.date(), nkeep, " sites will be kept");
+    std::ifstream fin(filebim);
+    std::ofstream ofs_out(params.fileout + ".ld.prune.out"), ofs_in(params.fileout + ".ld.prune.in");
+    std::string line;
+    uint64 i = 0;
+    while (std::getline(fin, line)) {
+      if (line.empty() || line[0] == '#') continue;
+      auto t = tokens_of(line);
+      std::ofstream& o = keep[i] ? ofs_in : ofs_out;
+      o << t[0] << "\t" << t[1] << "\t" << t[2] << "\t" << t[3] << "\t" << t[4] << "\t" << t[5] << std::endl;
+      ++i;
+    }
+    return;
+  }
   uint64 npairs = 0;
   for (int w : snp.we) npairs += (uint64)(w - 1);
   cao.print(tick.date(), "LD windows:", snp.ws.size(), ", pairs:", npairs);

@@ -30,7 +30,7 @@ int main(int argc, char* argv[]) {
   try {
     if (pcaone_device_count() == 0) cao.error("no CUDA device is visible: pcaone_b200 has no CPU fallback");
     // LD from a bed (Main.cpp:78-97): windows from the .bim, r2 on the device
-    if (params.print_r2) {
+    if (params.print_r2 || params.ld_r2 > 0) {
       params.memory = 0, params.out_of_core = false;  // Main.cpp:84
       params.perm = false;
       FileBed data(params);

@@ -169,6 +169,35 @@ def test_cli_print_r2_vs_reference(tmp_path):
     assert np.abs(r2 - want).max() < 2e-6  # std::to_string keeps 6 decimals
 
 
+@pytest.mark.gpu
+def test_cli_ld_prune_vs_reference(tmp_path):
+    """--ld-r2: .ld.prune.in / .ld.prune.out against the reference's ld_prune_big on the same bed
+    (centred genotypes read in core), without and with the allele-frequency column."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, tol = 300, 1500, 0.03
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=4, seed=35)
+    r = ref.Ref(f"PCAone -b {prefix} -k 2 -d 1 -o {tmp_path}/r -n 4", threads=4)
+    F = r.F()
+    mbim = str(tmp_path / "s.mbim")
+    with open(mbim, "w") as f:
+        for ln, af in zip(open(prefix + ".bim"), F):
+            f.write(ln.rstrip("\n") + "\t%.6g\n" % af)
+    for bim, tag in ((prefix + ".bim", "noaf"), (mbim, "af")):
+        want = r.ld_prune(bim, 3000, tol, str(tmp_path / ("ref_" + tag)))
+        out = str(tmp_path / ("o_" + tag))
+        _run(["-b", prefix, "--ld-r2", tol, "--ld-bp", 3000, "-F", bim, "-o", out])
+        kept = [l.split("\t")[1] for l in open(out + ".ld.prune.in")]
+        dropped = [l.split("\t")[1] for l in open(out + ".ld.prune.out")]
+        ids = [l.split()[1] for l in open(prefix + ".bim")]
+        assert len(kept) + len(dropped) == M and 0 < len(dropped) < M
+        got = np.isin(ids, kept)
+        assert np.array_equal(got, want), (tag, int((got != want).sum()))
+    r.close()
+
+
 def _write_beagle(path, P):
     """BEAGLE text (gz) from the 2N x M likelihood matrix: the columns parse_beagle_file reads."""
     N, M = P.shape[0] // 2, P.shape[1]
