@@ -1284,22 +1284,53 @@ void compute_gandh(pcaone_ctx* c, int pi) {
 // Halko.cpp:55-70 on the device. Leaves: G <- Q2, d_Ucur (N x k), d_sigma (l), d_Vr = U_B (l x l)
 void small_stage(pcaone_ctx* c) {
   Timed t(c, 3);
+  // optional per-step breakdown (debug aid): PCAONE_SMALL_PROF=n prints the first n calls
+  static int prof_left = getenv("PCAONE_SMALL_PROF") ? atoi(getenv("PCAONE_SMALL_PROF")) : 0;
+  cudaEvent_t ev[10];
+  int nev = 0;
+  const bool prof = prof_left > 0;
+  auto mark = [&]() {
+    if (!prof) return;
+    PCA_CUDA(cudaEventCreate(&ev[nev]));
+    PCA_CUDA(cudaEventRecord(ev[nev], c->stream));
+    ++nev;
+  };
+  mark();
   // G = Q R twice (CholeskyQR2); T = R^-1 so that Q = G T and B^T = H R^-1 = H T
   // Only T is needed per epoch; Q itself enters the result once, as V = Q U_B (Halko.cpp:89), which
   // finalize_usv forms as G (T U_B): the M x l matrix Q is never written.
   c->g_is_q = orth2(c, c->d_G, c->M, c->d_G, c->d_T, true, true);
+  mark();
   ts_rightmult(c, c->d_H, c->l, c->d_T, c->l, c->N, c->d_Bt);
   // SVD of B^T (N x l): Gram -> Cholesky -> one-sided Jacobi on the triangular factor
   ts_gemm_tn(c, c->d_Bt, c->l, c->d_Bt, c->l, c->N, c->d_W, false);
   launch_chol(c, c->d_W, c->d_R, c->d_Rinv);
-  if (read_status(c) == 0)
+  mark();
+  const int st = read_status(c);
+  mark();
+  if (st == 0)
     jacobi(c, c->d_R, 0, c->d_sigma, c->d_Vr);
   else
     jacobi(c, c->d_W, 1, c->d_sigma, c->d_Vr);
+  mark();
   k_scale_v_by_inv_sigma<<<1, 1024, 0, c->stream>>>(c->d_Vr, c->d_sigma, c->l, c->k, c->lp, c->d_Z);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
   ts_rightmult(c, c->d_Bt, c->l, c->d_Z, c->k, c->N, c->d_Ucur);
+  mark();
+  if (prof) {
+    --prof_left;
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    fprintf(stderr, "small_stage (ms): orth(G)");
+    const char* names[] = {"", " Bt+Gram+chol", " status-sync", " jacobi", " scale+Ucur"};
+    for (int i = 1; i < nev; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, "%s %.3f", names[i - 1], ms);
+    }
+    fprintf(stderr, "\n");
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  }
 }
 
 double device_mev(pcaone_ctx* c, const double* X, const double* Y, uint64_t rows, bool sharded) {

@@ -56,9 +56,11 @@ struct OrthArgs {
   unsigned long long* colmax_out;
 };
 
+// shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
+// (= 4 mod 16), which makes every DMMA fragment load below bank-conflict free
 __host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
-  const int LC = 16 * R;
-  return ((size_t)2 * l * LC + (size_t)2 * orth_tile_rows(R) * (LC + 1) + (size_t)l * l) * sizeof(double);
+  const int LD = 16 * R + 4;
+  return ((size_t)2 * l * LD + (size_t)2 * orth_tile_rows(R) * LD + (size_t)l * l) * sizeof(double);
 }
 
 // W (l x l, row-major ld, global) -> T (l x l row-major ld, global) with (A T) orthonormal:
@@ -282,15 +284,25 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   cg::grid_group grid = cg::this_grid();
   constexpr int LC = 16 * R;
   constexpr int TR = orth_tile_rows(R);  // rows per tile
-  constexpr int RI = TR / 16;            // rows per thread
+  constexpr int RI = TR / 16;            // rows per thread in the 16 x 16 epilogue layout
   constexpr int NLD = TR * R / 16;       // register-prefetched doubles per thread (>= TR*lp/256)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* T1s = reinterpret_cast<double*>(smem_raw);  // [l][LC]
-  double* T2s = T1s + (size_t)a.l * LC;               // [l][LC]
-  double* As = T2s + (size_t)a.l * LC;                // [TR][LC+1]
-  double* Qs = As + TR * (LC + 1);                    // [TR][LC+1]
-  double* Ws = Qs + TR * (LC + 1);                    // [l][l]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+  constexpr int LD = LC + 4;                          // smem row stride of tiles and factors
+  constexpr int NT = LC / 8;                          // 8-column MMA tiles per row
+  constexpr int MT = TR / 8;                          // 8-row MMA tiles per staged tile (8 or 4)
+  constexpr int NSPLIT = 8 / MT;                      // warps sharing one row tile (1 or 2)
+  constexpr int NPW = NT / NSPLIT;                    // column tiles per warp in a tile x factor product
+  constexpr int NTT = NT * (NT + 1) / 2;              // upper-triangle tiles of the Gram
+  constexpr int GPW = (NTT + 7) / 8;                  // Gram tiles per warp
+  double* T1s = reinterpret_cast<double*>(smem_raw);  // [l][LD]
+  double* T2s = T1s + (size_t)a.l * LD;               // [l][LD]
+  double* As = T2s + (size_t)a.l * LD;                // [TR][LD]
+  double* Qs = As + TR * LD;                          // [TR][LD]
+  double* Ws = Qs + TR * LD;                          // [l][l]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int fg = lane >> 2, ft = lane & 3;            // DMMA fragment coordinates (common.cuh dmma884)
+  const int m0 = (warp % MT) * 8;                     // this warp's row tile in tile x factor products
+  const int nbase = (warp / MT) * NPW;                // ... and its first column tile
   const int l = a.l, lp = a.lp;
   const int gwarp = (blockIdx.x * kOrthThreads + tid) >> 5, nwarps = (gridDim.x * kOrthThreads) >> 5;
   const uint64_t rpc = ((a.rows + gridDim.x - 1) / gridDim.x + TR - 1) / TR * TR;
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       const int e = tid + kOrthThreads * i;
       if (e < tile_elems) {
         const int rr = e / lp, c = e - rr * lp;
-        if (c < LC) As[rr * (LC + 1) + c] = c < l ? pre[i] : 0.0;
+        if (c < LC) As[rr * LD + c] = c < l ? pre[i] : 0.0;
       }
     }
   };
@@ -324,63 +336,82 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     if (lp < LC)
       for (int idx = tid; idx < TR * (LC - lp); idx += kOrthThreads) {
         const int rr = idx / (LC - lp), c = lp + idx - rr * (LC - lp);
-        As[rr * (LC + 1) + c] = 0.0;
+        As[rr * LD + c] = 0.0;
       }
   };
   auto load_T = [&](const double* Tg, double* Ts) {
     for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
       const int r = idx / LC, c = idx - r * LC;
-      Ts[idx] = c < l ? Tg[r * lp + c] : 0.0;
+      Ts[r * LD + c] = c < l ? Tg[r * lp + c] : 0.0;
     }
   };
-  // acc[i][j] = sum_k src[ty+16i][k] * Ts[k][tx+16j]
-  auto tile_times_T = [&](const double* src, const double* Ts, double (&acc)[RI][R]) {
+  // The three tall products run on the FP64 tensor cores (DMMA m8n8k4). The scalar version (each
+  // thread an RI x R register tile fed by 7 shared-memory loads per 12 FMAs) reached ~45 % of the FP64
+  // rate and made QR(G) on 1M rows 1.2 ms of a 1.85 ms dense stage.
+  //
+  // tile x factor: acc[n][0..1] = (src[TR][0..l) * Ts[0..l)[LC]) at rows m0 + fg, columns 8 (nbase + n) + 2 ft (+1)
+  auto tile_times_T = [&](const double* src, const double* Ts, double (&acc)[NPW][2]) {
 #pragma unroll
-    for (int i = 0; i < RI; ++i)
-#pragma unroll
-      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    for (int n = 0; n < NPW; ++n) acc[n][0] = acc[n][1] = 0.0;
+    const double* ap = src + (m0 + fg) * LD + ft;
+    const double* bp = Ts + ft * LD + 8 * nbase + fg;
+    const int l4 = (l + 3) & ~3;
 #pragma unroll 2
-    for (int k = 0; k < l; ++k) {
-      double av[RI], tv[R];
+    for (int k = 0; k < l4; k += 4) {
+      const double av = ap[k];                       // columns >= l of the staged tile are zero
+      const bool kin = k + ft < l;                   // rows >= l of Ts do not exist
 #pragma unroll
-      for (int i = 0; i < RI; ++i) av[i] = src[(ty + 16 * i) * (LC + 1) + k];
-#pragma unroll
-      for (int j = 0; j < R; ++j) tv[j] = Ts[k * LC + tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < RI; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[i][j] += av[i] * tv[j];
-    }
-  };
-  auto store_tile = [&](double* dst, const double (&acc)[RI][R]) {
-#pragma unroll
-    for (int i = 0; i < RI; ++i)
-#pragma unroll
-      for (int j = 0; j < R; ++j) dst[(ty + 16 * i) * (LC + 1) + tx + 16 * j] = acc[i][j];
-  };
-  auto gram_accumulate = [&](const double* src, double (&acc)[R][R]) {
-#pragma unroll 4
-    for (int rr = 0; rr < TR; ++rr) {
-      double av[R], bv[R];
-#pragma unroll
-      for (int i = 0; i < R; ++i) av[i] = src[rr * (LC + 1) + ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < R; ++j) bv[j] = src[rr * (LC + 1) + tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[i][j] += av[i] * bv[j];
-    }
-  };
-  auto store_part = [&](double (&acc)[R][R]) {
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const int r = ty + 16 * i, c = tx + 16 * j;
-        if (r < l && c < lp) mypart[r * lp + c] = c < l ? acc[i][j] : 0.0;
+      for (int n = 0; n < NPW; ++n) {
+        const double bv = kin ? bp[k * LD + 8 * n] : 0.0;
+        dmma884(acc[n][0], acc[n][1], av, bv);
       }
+    }
   };
+  auto store_tile = [&](double* dst, const double (&acc)[NPW][2]) {
+#pragma unroll
+    for (int n = 0; n < NPW; ++n)
+      *reinterpret_cast<double2*>(dst + (m0 + fg) * LD + 8 * (nbase + n) + 2 * ft) = make_double2(acc[n][0], acc[n][1]);
+  };
+  // Gram: upper-triangle 8 x 8 tiles (ti <= tj) of src^T src, tile q of this warp = list entry warp + 8 q
+  int g_ti[GPW], g_tj[GPW];
+#pragma unroll
+  for (int q = 0; q < GPW; ++q) {
+    int idx = warp + 8 * q, ti = 0;
+    if (idx >= NTT) {
+      g_ti[q] = g_tj[q] = -1;
+    } else {
+      while (idx >= NT - ti) {
+        idx -= NT - ti;
+        ++ti;
+      }
+      g_ti[q] = ti;
+      g_tj[q] = ti + idx;
+    }
+  }
+  auto gram_accumulate = [&](const double* src, double (&acc)[GPW][2]) {
+#pragma unroll 4
+    for (int rr = 0; rr < TR; rr += 4) {
+      const double* row = src + (rr + ft) * LD + fg;  // A[i = fg][k = ft] = src[k][8 ti + fg], B[k = ft][j = fg] = src[k][8 tj + fg]
+#pragma unroll
+      for (int q = 0; q < GPW; ++q)
+        if (g_ti[q] >= 0) dmma884(acc[q][0], acc[q][1], row[8 * g_ti[q]], row[8 * g_tj[q]]);
+    }
+  };
+  auto store_part = [&](double (&acc)[GPW][2]) {
+#pragma unroll
+    for (int q = 0; q < GPW; ++q) {
+      if (g_ti[q] < 0) continue;
+      const int r = 8 * g_ti[q] + fg;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 8 * g_tj[q] + 2 * ft + h;
+        const double v = (r < l && c < l) ? acc[q][h] : 0.0;
+        if (r < l && c < lp) mypart[r * lp + c] = v;
+        if (g_ti[q] != g_tj[q] && c < l && r < lp) mypart[c * lp + r] = v;  // mirror
+      }
+    }
+  };
+  // pad entries of the partial Gram that no tile writes (rows < l, columns in [LC, lp) never exist: lp <= LC)
 
   int prof_i = 0;
   auto stamp = [&]() {
@@ -396,11 +427,9 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   zero_pad_cols();
   // ---------------- P1: partial Gram of A
   if (ph & 1) {
-    double acc[R][R];
+    double acc[GPW][2];
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    for (int q = 0; q < GPW; ++q) acc[q][0] = acc[q][1] = 0.0;
     prefetch(r0);
     for (uint64_t r = r0; r < r1; r += TR) {
       __syncthreads();
@@ -421,7 +450,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   // ---------------- P3: T1
   if (ph & 2) {
-    if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LC, a.jscratch, a.status);
+    if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LD, a.jscratch, a.status);
     __threadfence();
     stamp();
     grid.sync();
@@ -433,18 +462,16 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     __syncthreads();
   }
   if (ph & 2) {
-    double acc[R][R];
+    double acc[GPW][2];
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+    for (int q = 0; q < GPW; ++q) acc[q][0] = acc[q][1] = 0.0;
     prefetch(r0);
     for (uint64_t r = r0; r < r1; r += TR) {
       __syncthreads();
       commit_tile();
       prefetch(r + TR);
       __syncthreads();
-      double q1[RI][R];
+      double q1[NPW][2];
       tile_times_T(As, T1s, q1);
       store_tile(Qs, q1);
       __syncthreads();
@@ -462,14 +489,14 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   if (!(ph & 4)) return;  // uniform across the grid
   // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
   if (blockIdx.x == 0) {
-    orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LC, a.jscratch, a.status);
+    orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
     stamp();
     if (a.Ttot) {
       for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
         const int r = idx / lp, c = idx - r * lp;
         double s = 0.0;
         if (c < l)
-          for (int k = 0; k < l; ++k) s += T1s[r * LC + k] * T2s[k * LC + c];
+          for (int k = 0; k < l; ++k) s += T1s[r * LD + k] * T2s[k * LD + c];
         a.Ttot[idx] = s;
       }
     }
@@ -480,21 +507,21 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         __syncthreads();
         for (int idx = tid; idx < TR * LC; idx += kOrthThreads) {
           const int rr = idx / LC, c = idx - rr * LC;
-          As[rr * (LC + 1) + c] =
+          As[rr * LD + c] =
               ((uint64_t)(rb + rr) < a.rows && rb + rr < l && c < l) ? a.A[(uint64_t)(rb + rr) * lp + c] : 0.0;
         }
         __syncthreads();
-        double q[RI][R];
+        double q[NPW][2];
         tile_times_T(As, T1s, q);
         store_tile(Qs, q);
         __syncthreads();
         tile_times_T(Qs, T2s, q);
 #pragma unroll
-        for (int i = 0; i < RI; ++i)
+        for (int n = 0; n < NPW; ++n)
 #pragma unroll
-          for (int j = 0; j < R; ++j) {
-            const int rr = rb + ty + 16 * i, c = tx + 16 * j;
-            if (rr < l && c < l) Ws[rr * l + c] = q[i][j];
+          for (int h = 0; h < 2; ++h) {
+            const int rr = rb + m0 + fg, c = 8 * (nbase + n) + 2 * ft + h;
+            if (rr < l && c < l) Ws[rr * l + c] = q[n][h];
           }
       }
       (void)r1_save;
@@ -562,6 +589,9 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   // ---------------- P7: Q = (A T1) T2 o hsign ; partial flip sums
   if (blockIdx.x != 0) load_T(a.T2g, T2s);
+  // the epilogue keeps the 16 x 16 thread layout (thread = RI rows x R columns: 3 x R running
+  // column statistics per thread instead of 3 x 2 NPW in the MMA fragment layout); the second
+  // product goes through shared memory once more (As is free after the first product)
   double hs[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? a.hsign[tx + 16 * j] : 0.0;
@@ -591,13 +621,17 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         }
       }
     }
-    double q[RI][R];
-    tile_times_T(As, T1s, q);
-    store_tile(Qs, q);
-    __syncthreads();
-    stamp();
-    tile_times_T(Qs, T2s, q);
-    stamp();
+    {
+      double q[NPW][2];
+      tile_times_T(As, T1s, q);
+      store_tile(Qs, q);
+      __syncthreads();
+      stamp();
+      tile_times_T(Qs, T2s, q);
+      store_tile(As, q);  // every warp finished reading As before the barrier above
+      __syncthreads();
+      stamp();
+    }
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
       const uint64_t row = r + ty + 16 * i;
@@ -606,7 +640,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         for (int j = 0; j < R; ++j) {
           const int c = tx + 16 * j;
           if (c < lp) {
-            const double qv = c < l ? q[i][j] * hs[j] : 0.0;
+            const double qv = c < l ? As[(ty + 16 * i) * LD + c] * hs[j] : 0.0;
             amax[j] = fmax(amax[j], fabs(qv));
             if (a.want_flip && c < l) {
               dsum[j] += fabs(o2[i][j] - qv);
@@ -621,11 +655,11 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   if (a.colmax_out) {  // the 16 row-lanes of a column -> one atomicMax per column and CTA
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < R; ++j) As[ty * (LC + 1) + tx + 16 * j] = amax[j];
+    for (int j = 0; j < R; ++j) As[ty * LD + tx + 16 * j] = amax[j];
     __syncthreads();
     for (int c = tid; c < l; c += kOrthThreads) {
       double m = 0.0;
-      for (int y = 0; y < 16; ++y) m = fmax(m, As[y * (LC + 1) + c]);
+      for (int y = 0; y < 16; ++y) m = fmax(m, As[y * LD + c]);
       if (m > 0.0) atomicMax(a.colmax_out + c, (unsigned long long)__double_as_longlong(m));
     }
   }
@@ -635,18 +669,18 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     return;  // uniform across the grid: no further grid.sync
   }
   __syncthreads();
-  // reduce the 16 row-lanes (ty) per column in fixed order: reuse As/Qs as [16][LC+1]
+  // reduce the 16 row-lanes (ty) per column in fixed order: reuse As/Qs as [16][LD]
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    As[ty * (LC + 1) + tx + 16 * j] = dsum[j];
-    Qs[ty * (LC + 1) + tx + 16 * j] = ssum[j];
+    As[ty * LD + tx + 16 * j] = dsum[j];
+    Qs[ty * LD + tx + 16 * j] = ssum[j];
   }
   __syncthreads();
   for (int c = tid; c < l; c += kOrthThreads) {
     double d = 0.0, s = 0.0;
     for (int y = 0; y < 16; ++y) {
-      d += As[y * (LC + 1) + c];
-      s += Qs[y * (LC + 1) + c];
+      d += As[y * LD + c];
+      s += Qs[y * LD + c];
     }
     mypart[c] = d;
     mypart[l + c] = s;
