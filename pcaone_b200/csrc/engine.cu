@@ -828,7 +828,15 @@ void jacobi(pcaone_ctx* c, const double* A, int sym, double* sigma, double* V) {
     PCA_CUDA(cudaFuncSetAttribute(k_jacobi_svd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  k_jacobi_svd<<<1, kSmallThreads, smem, c->stream>>>(A, c->l, c->lp, sym, sigma, V, nullptr);
+  static int sw_left = getenv("PCAONE_SMALL_PROF") ? atoi(getenv("PCAONE_SMALL_PROF")) : 0;
+  k_jacobi_svd<<<1, kSmallThreads, smem, c->stream>>>(A, c->l, c->lp, sym, sigma, V, sw_left > 0 ? c->d_status + 2 : nullptr);
+  if (sw_left > 0) {
+    --sw_left;
+    int sw = 0;
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    PCA_CUDA(cudaMemcpy(&sw, c->d_status + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "jacobi sweeps: %d\n", sw);
+  }
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
 }

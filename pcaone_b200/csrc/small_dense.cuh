@@ -140,11 +140,14 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
         alpha = warp_sum(alpha);
         beta = warp_sum(beta);
         gamma = warp_sum(gamma);
-        if (fabs(gamma) > eps * sqrt(alpha * beta) && gamma != 0.0) {
+        // the rotation parameters are a serial chain every lane waits for: reciprocal / rsqrt
+        // forms instead of three divisions and three square roots (same test, squared)
+        if (gamma * gamma > (eps * eps) * (alpha * beta) && gamma != 0.0) {
           if (lane == 0) s_rot = 1;
-          const double zeta = (beta - alpha) / (2.0 * gamma);
-          const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+          const double zeta = (beta - alpha) * __drcp_rn(2.0 * gamma);
+          const double z2 = 1.0 + zeta * zeta;
+          const double tt = copysign(1.0, zeta) * __drcp_rn(fabs(zeta) + z2 * rsqrt(z2));
+          const double c = rsqrt(1.0 + tt * tt), s = c * tt;
           double* vp = V + p * l;
           double* vq = V + q * l;
           for (int r = lane; r < l; r += 32) {
