@@ -98,6 +98,37 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
   if (tid == 0) s_fail = 0;
   for (int i = tid; i < l * lc; i += nt) Ts[i] = 0.0;
   __syncthreads();
+  // Second pass of CholeskyQR2: W = Q1^T Q1 = I + E with |E| ~ eps * cond(A)^2. For |E_ij| <= 1e-11
+  // the factor is its own first-order expansion to below one ulp (the dropped terms are
+  // <= (l * 1e-11)^2 < 1e-18): R = I + U, U = strict_upper(E) + diag(E) / 2, T = R^-1 = I - U.
+  // That replaces the l-step serial loop below (24 us of a 130 us Omega update at l = 40) by one
+  // parallel pass; anything larger (first pass, ill-conditioned inputs, NaN) takes the loop.
+  {
+    bool big = false;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (r < l && c < l) big |= !(fabs(a[i][j] - (r == c ? 1.0 : 0.0)) <= 1e-11);
+      }
+    if (!__syncthreads_or(big)) {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = ty + 16 * i, c = tx + 16 * j;
+          if (r < l && c < l && r <= c) Ts[r * lc + c] = (r == c) ? 1.0 - 0.5 * (a[i][j] - 1.0) : -a[i][j];
+        }
+      __syncthreads();
+      for (int i = tid; i < l * ld; i += nt) {
+        const int r = i / ld, c = i - r * ld;
+        T[i] = c < l ? Ts[r * lc + c] : 0.0;
+      }
+      __syncthreads();
+      return;
+    }
+  }
   double maxd = 0.0;
   for (int i = 0; i < l; ++i) maxd = fmax(maxd, s_row[0][i]);
   __syncthreads();
