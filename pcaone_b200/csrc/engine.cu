@@ -113,7 +113,7 @@ struct pcaone_ctx {
   int8_t* d_BimgD = nullptr;                           // B image of D = (f - 1) o W (mask operand of the H pass)
   size_t R2_rows = 0, bimgD_kb = 0;
   size_t R_rows = 0;
-  unsigned long long* d_tcs = nullptr;                 // [5][lp]: Omega colmax, Omega Csum, W colmax, W Csum, Fw
+  unsigned long long* d_tcs = nullptr;                 // [5][lp] + 1: Omega colmax, Omega Csum, W colmax, W Csum, Fw, block counter
   double* d_Fpart = nullptr;
   bool omega_img_valid = false;
   bool omega_colmax_valid = false;                     // d_tcs colmax of Omega was produced by the orth kernel
@@ -337,8 +337,8 @@ void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG,
 
 void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows, bool miss) {
   if (!c->d_tcs) {
-    dmalloc(&c->d_tcs, (size_t)5 * c->lp);
-    PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)5 * c->lp * sizeof(unsigned long long), c->stream));
+    dmalloc(&c->d_tcs, (size_t)5 * c->lp + 1);  // + the block counter of the slice kernel's Fw reduction
+    PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, ((size_t)5 * c->lp + 1) * sizeof(unsigned long long), c->stream));
     dmalloc(&c->d_BimgO, (size_t)(tc_nkb_samples(c) + 1) * tc::kKB * c->NP);
   }
   const size_t need_rows = std::max<uint64_t>(tc_nrt_samples(c) * tc::kRowTile, max_range_rows + 2 * tc::kRowTile);
@@ -444,6 +444,8 @@ void tc_launch(pcaone_ctx* c, tc::TcGemmArgs a, int mode, long long* R) {
   throw std::runtime_error("tc_gemm: unsupported slice count");
 }
 
+constexpr uint32_t kFoldFwMaxParts = 512;
+
 void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned long long* colmax, const double* F,
               int writeback, int8_t* Bimg, long long* Csum, double* Fpart, uint32_t* nkb_out, int dmode = 0) {
   tc::TcSliceArgs a{};
@@ -465,6 +467,11 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
   a.Fpart = Fpart;
   // an even number of k-block images: a pipeline stage of k_tc_gemm is two k-blocks (the pad image is zero)
   const uint32_t nkb = ((uint32_t)((r1 - 1) / tc::kKB) - a.kb0 + 2) & ~1u;
+  // window-sized launches fold the Fw reduction into their last block; with thousands of partials
+  // (merged ranges of the late epochs) the single block would be a long tail: separate kernel
+  const bool fold_fw = Fpart && nkb <= kFoldFwMaxParts;
+  a.Fw = fold_fw ? reinterpret_cast<double*>(c->d_tcs + 4 * c->lp) : nullptr;
+  a.done = reinterpret_cast<unsigned int*>(c->d_tcs + 5 * c->lp);
   const size_t smem = (size_t)tc::kKB * c->NP;
   tc::k_tc_slice<<<nkb, tc::tc_flat_threads(c->lp), smem, c->stream>>>(a);
   PCA_CHECK_LAUNCH();
@@ -554,16 +561,17 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       }
     }
     double* Fw = reinterpret_cast<double*>(c->d_tcs + 4 * c->lp);
-    // (folding this sum into every finish block was tried: the serial chain of a window's ~250
-    // partials per block cost ~30 us per launch, 6x the separate reduction kernel)
+    // Fw: reduced by the last block of the slice kernel for window-sized launches, by its own
+    // kernel otherwise (folding the sum into every finish block was tried: the serial chain of a
+    // window's ~250 partials per block cost ~30 us per launch)
     const bool fold_fw = false;
-    if (!fold_fw) {
+    if (nkb_w > kFoldFwMaxParts) {
       tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
       PCA_CHECK_LAUNCH();
       c->tm.kernel_launches++;
     }
     const bool fuse_sum = c->sum_out != nullptr && c->sum_other != nullptr;
-    tc::k_tc_finish_h<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(
+    tc::k_tc_finish_h<<<grid_for((c->N * c->lp + 3) / 4, 256, c->sms), 256, 0, c->stream>>>(  // 4 elements per thread
         c->d_Racc, miss ? c->d_Racc2 : nullptr, c->N, c->l, c->lp, c->slices, w_csum, w_colmax, Fw,
         fold_fw ? c->d_Fpart : nullptr, nkb_w, Hacc, accumulate ? 1 : 0, fuse_sum ? c->sum_other : nullptr,
         fuse_sum ? c->sum_out : nullptr);

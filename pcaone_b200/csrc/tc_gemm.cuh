@@ -478,6 +478,8 @@ struct TcSliceArgs {
   int8_t* Bimg;                       // out: [nkb][64*NP]
   long long* Csum;                    // out (atomic): sum_rows I[row][c]
   double* Fpart;                      // out: [gridDim.x][lp] partial sums of f_row * X~[row][c], or nullptr
+  double* Fw;                         // out: [lp] sum of Fpart over the blocks in a fixed order (last block done), or nullptr
+  unsigned int* done;                 // block counter of the Fw reduction: zero on entry, left zero
 };
 
 // Threads per block of the slice / finish kernels: a multiple of lp, so that with the flat index
@@ -497,6 +499,24 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
   const int tid = threadIdx.x, B = blockDim.x;
   const int p = 8 * a.S - 1;
   const uint64_t row0 = (uint64_t)kb * kKB;
+  // The X loads of a batch are issued before their first use, the first batch before anything
+  // else: with the write-back to the same array inside the loop the compiler kept every load
+  // behind the previous store, a chain of 64 / rpp dependent memory round trips per thread
+  // (11 of the 13.5 us of a window-sized launch, ncu source page).
+  constexpr int UB = 8;
+  const int rpp = B / a.lp;  // rows per pass
+  const int g0 = tid / a.lp, c = tid - g0 * a.lp;
+  double* Xb = a.X + row0 * a.lp;
+  double xv[UB];
+  auto load_batch = [&](int gb) {
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int g = gb + u * rpp;
+      const uint64_t row = row0 + g;
+      xv[u] = (g < kKB && row >= a.r0 && row < a.r1) ? Xb[g * a.lp + c] : 0.0;
+    }
+  };
+  if (c < a.l) load_batch(g0);
   for (int i = tid; i < kKB * a.NP / 16; i += B) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
   if (tid < kKB) {
     const uint64_t row = row0 + tid;
@@ -508,8 +528,6 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     s_scale[tid] = s;
     s_f[tid] = f;
   }
-  const int rpp = B / a.lp;  // rows per pass
-  const int g0 = tid / a.lp, c = tid - g0 * a.lp;
   double up = 0.0, dn = 0.0;
   if (c < a.l) {
     const int e = tc_exponent(a.colmax[c]);
@@ -517,16 +535,18 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     dn = scalbn(1.0, e - p);
   }
   __syncthreads();
-  double* Xb = a.X + row0 * a.lp;
   long long csum = 0;
   double fsum = 0.0;
   if (c < a.l) {
-#pragma unroll 4
-    for (int g = g0; g < kKB; g += rpp) {
-      const uint64_t row = row0 + g;
-      if (row >= a.r0 && row < a.r1) {
+    for (int gb = g0; gb < kKB; gb += rpp * UB) {
+      if (gb != g0) load_batch(gb);
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int g = gb + u * rpp;
+        const uint64_t row = row0 + g;
+        if (!(g < kKB && row >= a.r0 && row < a.r1)) continue;
         const double sj = s_scale[g];
-        double x = Xb[g * a.lp + c] * sj;
+        double x = xv[u] * sj;
         if (a.dmode) x *= s_f[g] - 1.0;
         const long long I = llrint(x * up);
         const double xt = (double)I * dn;
@@ -560,6 +580,29 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     }
     if (tc_) atomicAdd(reinterpret_cast<unsigned long long*>(a.Csum + c), (unsigned long long)tc_);
     if (a.Fpart) a.Fpart[(size_t)blockIdx.x * a.lp + c] = tf;
+  }
+  // Fw[c] = sum of the per-block partials, by whichever block finishes last, always in the same
+  // order: one warp per column, lane q sums parts q, q + 32, ... then the 32 lane sums are folded
+  // (was a separate 5-block launch, ~6 us of pure latency per window).
+  if (a.Fpart && a.Fw) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int lane = tid & 31, w = tid >> 5, nw = B >> 5;  // full warps only
+      if (w < nw) {
+        for (int cw = w; cw < a.l; cw += nw) {
+          double v = 0.0;
+          for (uint32_t b = lane; b < gridDim.x; b += 32) v += __ldcg(a.Fpart + (size_t)b * a.lp + cw);
+          v = warp_sum(v);
+          if (lane == 0) a.Fw[cw] = v;
+        }
+      }
+      if (tid == 0) *a.done = 0;
+    }
   }
 }
 
@@ -647,9 +690,21 @@ k_tc_finish_g(long long* __restrict__ R, long long* __restrict__ R2, uint64_t nr
       load_batch();
     }
   }
+  // the rows-per-pass lanes of a column pair fold in shared memory first: one atomicMax per column
+  // and block. (Every thread issuing its own pair was 245 blocks x 240 threads x 2 atomics on three
+  // cache lines, serialised in L2: most of the 27 us of a window-sized launch.)
+  __shared__ double s_m[256][2];
+  s_m[tid][0] = m[0];
+  s_m[tid][1] = m[1];
+  __syncthreads();
+  if (g0 == 0) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
-    if (c + h < l && m[h] > 0.0) atomicMax(&colmax_out[c + h], (unsigned long long)__double_as_longlong(m[h]));
+    for (int h = 0; h < 2; ++h) {
+      double v = 0.0;
+      for (int q = 0; q < rpp; ++q) v = fmax(v, s_m[q * hp + (c >> 1)][h]);
+      if (c + h < l && v > 0.0) atomicMax(&colmax_out[c + h], (unsigned long long)__double_as_longlong(v));
+    }
+  }
 }
 
 // Fw[c] = sum over the slice kernel's per-block partials, in block order with a fixed tree:
@@ -676,6 +731,33 @@ __global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__
                               double* __restrict__ Hsum) {
   __shared__ double sFw[kMaxNP], sScale[kMaxNP], sC[kMaxNP];
   const int p = 8 * S - 1;
+  // Batches of U elements per thread with every load of a batch issued before the first use, and
+  // the first batch before the per-column constants are formed: with one element per thread and
+  // the loads interleaved with the stores (R, Hacc, Hother came back one after the other) a
+  // window-sized launch was three dependent memory round trips per block behind the preamble,
+  // 23 us for 19 MB of traffic (ncu source page: 66 % of the samples on the Hacc add).
+  constexpr int U = 4;
+  const uint64_t total = nrows * (uint64_t)lp;
+  const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t iters = (total + nth * U - 1) / (nth * U);
+  long long T[U], K[U];
+  double ha[U], ho[U];
+  int cc[U];
+  auto load_batch = [&](uint64_t it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t idx = first + (it * U + u) * nth;
+      const bool in = idx < total;
+      cc[u] = in ? (int)(idx % lp) : lp;
+      const bool live = in && cc[u] < l;
+      T[u] = live ? R[idx] : 0;
+      K[u] = (live && R2) ? R2[idx] : 0;
+      ha[u] = (in && accumulate) ? Hacc[idx] : 0.0;
+      ho[u] = (in && Hsum) ? Hother[idx] : 0.0;
+    }
+  };
+  load_batch(0);
   for (int c = threadIdx.x; c < l; c += blockDim.x) {
     double fw;
     if (Fpart) {
@@ -691,27 +773,30 @@ __global__ void k_tc_finish_h(long long* __restrict__ R, long long* __restrict__
     sC[c] = (double)Csum[c];
   }
   __syncthreads();
-  const uint64_t total = nrows * (uint64_t)lp;
-  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (uint64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % lp);
-    double out = 0.0;
-    if (c < l) {
-      const long long T = R[idx];
-      R[idx] = 0;
-      double h = sScale[c] * (sC[c] - 0.5 * (double)T) - sFw[c];
-      if (R2) {
-        h += sScale[c] * (double)R2[idx];
-        R2[idx] = 0;
+  for (uint64_t it = 0; it < iters; ++it) {
+    if (it) load_batch(it);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t idx = first + (it * U + u) * nth;
+      if (idx >= total) continue;
+      const int c = cc[u];
+      double out = 0.0;
+      if (c < l) {
+        R[idx] = 0;
+        double h = sScale[c] * (sC[c] - 0.5 * (double)T[u]) - sFw[c];
+        if (R2) {
+          h += sScale[c] * (double)K[u];
+          R2[idx] = 0;
+        }
+        out = accumulate ? ha[u] + h : h;
+        Hacc[idx] = out;
+      } else if (!accumulate) {
+        Hacc[idx] = 0.0;
+      } else {
+        out = ha[u];
       }
-      out = accumulate ? Hacc[idx] + h : h;
-      Hacc[idx] = out;
-    } else if (!accumulate) {
-      Hacc[idx] = 0.0;
-    } else {
-      out = Hacc[idx];
+      if (Hsum) Hsum[idx] = out + ho[u];  // H = H1 + H2 for the Omega update that follows (Halko.cpp:209)
     }
-    if (Hsum) Hsum[idx] = out + Hother[idx];  // H = H1 + H2 for the Omega update that follows (Halko.cpp:209)
   }
 }
 
