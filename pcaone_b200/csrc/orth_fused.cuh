@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   const int l = a.l, lp = a.lp;
   const int gwarp = (blockIdx.x * kOrthThreads + tid) >> 5, nwarps = (gridDim.x * kOrthThreads) >> 5;
   const uint64_t rpc = ((a.rows + gridDim.x - 1) / gridDim.x + TR - 1) / TR * TR;
-  const uint64_t r0 = min(a.rows, (uint64_t)blockIdx.x * rpc), r1 = min(a.rows, r0 + rpc);
+  uint64_t r0 = min(a.rows, (uint64_t)blockIdx.x * rpc), r1 = min(a.rows, r0 + rpc);  // (re-split for P7/P8 below)
   const size_t pstride = (size_t)l * lp;
   double* mypart = a.part + (size_t)blockIdx.x * pstride;
   const int tile_elems = TR * lp;  // a tile is TR contiguous rows of lp doubles
@@ -519,9 +519,18 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   if (!(ph & 4)) return;  // uniform across the grid
   // ---------------- P6: T2, Ttot, Householder signs (CTA 0)
-  if (blockIdx.x == 0) {
+  // Omega updates (signs AND flipOmg): the sign replay is a serial l-step loop on one CTA (~20 us at
+  // l = 40) that only P8 needs — P7 can write Q unsigned and sum |Omega2 -+ Q| for both signs. So the
+  // grid barrier moves up to right after the T2 factor, CTA 0 replays the signs (stage 1) WHILE the
+  // other CTAs run P7 on all rows, and P8 applies hsign * flip in its one sweep (same bits as
+  // before: |o2 - h q| and |o2 + h q| swap roles when h = -1).
+  const bool overlap = a.want_signs && a.want_flip && a.Q != nullptr && a.Q != a.A && gridDim.x > 1;  // (in place: CTA 0 still reads the top rows of A)
+  for (int stage = 0; stage < 2; ++stage) {
+  if (stage == 0 && blockIdx.x == 0) {
     orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
     stamp();
+  }
+  if (blockIdx.x == 0 && stage == (overlap ? 1 : 0)) {
     if (a.Ttot) {
       for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
         const int r = idx / lp, c = idx - r * lp;
@@ -609,15 +618,24 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       for (int c = tid; c < l; c += kOrthThreads) a.hsign[c] = 1.0;
     }
   }
-  __threadfence();
-  stamp();
-  grid.sync();
-  stamp();
-  if (!a.Q) {  // factors only (uniform across the grid)
-    if (blockIdx.x == 0)
-      for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
-    return;
+  if (stage == 0) {
+    __threadfence();
+    stamp();
+    grid.sync();
+    stamp();
+    if (!a.Q) {  // factors only (uniform across the grid)
+      if (blockIdx.x == 0)
+        for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
+      return;
+    }
+    if (overlap) {  // the rows of P7 / P8 go to CTAs 1.., CTA 0 has none
+      const uint64_t rpc7 = ((a.rows + gridDim.x - 2) / (gridDim.x - 1) + TR - 1) / TR * TR;
+      r0 = blockIdx.x == 0 ? a.rows : min(a.rows, (uint64_t)(blockIdx.x - 1) * rpc7);
+      r1 = min(a.rows, r0 + rpc7);
+    }
   }
+  }  // stage
+  if (overlap && blockIdx.x == 0) __threadfence();  // hsign, Ttot: visible to the grid after the next barrier
   // ---------------- P7: Q = (A T1) T2 o hsign ; partial flip sums
   if (blockIdx.x != 0) load_T(a.T2g, T2s);
   // the epilogue keeps the 16 x 16 thread layout (thread = RI rows x R columns: 3 x R running
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   // product goes through shared memory once more (As is free after the first product)
   double hs[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? a.hsign[tx + 16 * j] : 0.0;
+  for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? (overlap ? 1.0 : a.hsign[tx + 16 * j]) : 0.0;
   double dsum[R], ssum[R], amax[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = amax[j] = 0.0;
@@ -734,9 +752,12 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   __syncthreads();
   for (int c = tid; c < l; c += kOrthThreads) {
-    const double f = (Qs[c] > 2 * Qs[l + c]) ? -1.0 : 1.0;
-    As[c] = f;
-    if (blockIdx.x == 0) a.fsign[c] = f * a.hsign[c];
+    // overlap mode: the sums were taken on the unsigned Q; with hsign = -1 they swap roles
+    const double hsg = overlap ? __ldcg(a.hsign + c) : 1.0;
+    const double dsm = hsg < 0.0 ? Qs[l + c] : Qs[c], ssm = hsg < 0.0 ? Qs[c] : Qs[l + c];
+    const double f = (dsm > 2 * ssm) ? -1.0 : 1.0;
+    As[c] = f * hsg;
+    if (blockIdx.x == 0) a.fsign[c] = f * __ldcg(a.hsign + c);
   }
   __syncthreads();
   const uint64_t total = (r1 - r0) * (uint64_t)lp;

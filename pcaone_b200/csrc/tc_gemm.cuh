@@ -582,8 +582,7 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     if (a.Fpart) a.Fpart[(size_t)blockIdx.x * a.lp + c] = tf;
   }
   // Fw[c] = sum of the per-block partials, by whichever block finishes last, always in the same
-  // order: one warp per column, lane q sums parts q, q + 32, ... then the 32 lane sums are folded
-  // (was a separate 5-block launch, ~6 us of pure latency per window).
+  // order (was a separate 5-block launch, ~6 us of pure latency per window).
   if (a.Fpart && a.Fw) {
     __shared__ int s_last;
     __threadfence();
@@ -592,14 +591,28 @@ __global__ void __launch_bounds__(256) k_tc_slice(const TcSliceArgs a) {
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const int lane = tid & 31, w = tid >> 5, nw = B >> 5;  // full warps only
-      if (w < nw) {
-        for (int cw = w; cw < a.l; cw += nw) {
-          double v = 0.0;
-          for (uint32_t b = lane; b < gridDim.x; b += 32) v += __ldcg(a.Fpart + (size_t)b * a.lp + cw);
-          v = warp_sum(v);
-          if (lane == 0) a.Fw[cw] = v;
+      // thread (g0, c) sums parts g0, g0 + rpp, ... of column c (loads in batches, adds in order),
+      // then the rpp partial sums of a column are folded in order
+      double v = 0.0;
+      if (c < a.l) {
+        constexpr int UF = 16;
+        for (uint32_t b0 = g0; b0 < gridDim.x; b0 += rpp * UF) {
+          double t[UF];
+#pragma unroll
+          for (int u = 0; u < UF; ++u) {
+            const uint32_t b = b0 + u * rpp;
+            t[u] = b < gridDim.x ? __ldcg(a.Fpart + (size_t)b * a.lp + c) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < UF; ++u) v += t[u];
         }
+      }
+      s_pf[g0 * a.lp + c] = v;
+      __syncthreads();
+      if (g0 == 0 && c < a.l) {
+        double tf = 0.0;
+        for (int q = 0; q < rpp; ++q) tf += s_pf[q * a.lp + c];
+        a.Fw[c] = tf;
       }
       if (tid == 0) *a.done = 0;
     }

@@ -22,3 +22,18 @@ for rep in range(2):
         t2 = time.perf_counter()
         tm = op.timers(reset=True)
         print(f"rep {rep} epoch {i}: gandh {1e3*(t1-t0):7.2f} ms  small {1e3*(t2-t1):6.2f} ms | g {tm.gemm_g_ms:6.2f} (tc {tm.tc_g_ms:6.2f}) h {tm.gemm_h_ms:6.2f} (tc {tm.tc_h_ms:6.2f}) orth {tm.orth_ms:6.2f} small {tm.small_ms:6.2f} launches {tm.kernel_launches} omega_updates {tm.omega_updates}")
+
+# cost of the per-scope CUDA events themselves: the same 7 epochs with the library's timers on / off
+for timing in (True, False, True, False):
+    op.enable_timing(timing)
+    op.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.ExternalStream(op.L.pcaone_stream(op.h))
+    e0.record(st)
+    for i in range(7):
+        op._chk(op.L.pcaone_compute_gandh(op.h, i))
+        op._chk(op.L.pcaone_small_stage(op.h))
+    e1.record(st)
+    op.sync()
+    torch.cuda.synchronize()
+    print(f"7 epochs, library timers {'on ' if timing else 'off'}: {e0.elapsed_time(e1):7.2f} ms")
