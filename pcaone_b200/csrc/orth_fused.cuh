@@ -54,6 +54,9 @@ struct OrthArgs {
   // optional: per-column max |Q| as IEEE bit patterns (atomicMax; zeroed by the caller) — what the
   // int8 route's slicing of the new Omega needs, saving its own column-max kernel
   unsigned long long* colmax_out;
+  // optional (single-launch, factors-only calls): device flag through which CTA 0 tells the grid
+  // that one Cholesky pass is enough (see P3); nullptr = always CholeskyQR2
+  int* skip2;
 };
 
 // shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
@@ -481,18 +484,47 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   }
   // ---------------- P3: T1
   if (ph & 2) {
-    if (blockIdx.x == 0) orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LD, a.jscratch, a.status);
+    if (blockIdx.x == 0) {
+      orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LD, a.jscratch, a.status);
+      if (a.skip2) {
+        // One Cholesky pass leaves |Q1^T Q1 - I| ~ eps * cond_2(A)^2; cond_F(A)^2 = trace(W) * |T1|_F^2
+        // bounds cond_2(A)^2 from above (by up to a factor l^2; ~l for a flat spectrum: 1.4e4 against
+        // 35 on the bench matrix) and costs one block reduction. Up to 1e5 the second pass (a full
+        // re-read of A and two thirds of the flops) would change the factor by < 1e-11 in the worst
+        // case, ~1e-13 typically — five orders under the 1e-6 the eigenvalues are held to: skip it, T2 = I.
+        __shared__ double s_red[2][kOrthThreads / 32];
+        double tr = 0.0, tf = 0.0;
+        for (int i = tid; i < l; i += kOrthThreads) tr += a.Wg[i * lp + i];
+        for (int i = tid; i < l * LD; i += kOrthThreads) tf += T1s[i] * T1s[i];
+        tr = warp_sum(tr);
+        tf = warp_sum(tf);
+        if (lane == 0) {
+          s_red[0][warp] = tr;
+          s_red[1][warp] = tf;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          tr = tf = 0.0;
+          for (int w = 0; w < kOrthThreads / 32; ++w) {
+            tr += s_red[0][w];
+            tf += s_red[1][w];
+          }
+          *a.skip2 = (tr * tf <= 1e5) ? 1 : 0;  // NaN -> 0
+        }
+      }
+    }
     __threadfence();
     stamp();
     grid.sync();
     stamp();
   }
+  const bool skip = a.skip2 != nullptr && (ph & 2) && __ldcg(a.skip2) != 0;  // uniform across the grid
   // ---------------- P4: partial Gram of Q1 = A T1
   if ((ph & 2) ? blockIdx.x != 0 : (ph & 4) != 0) {  // T1 is in CTA 0's shared memory only if P3 ran in this launch
     load_T(a.T1g, T1s);
     __syncthreads();
   }
-  if (ph & 2) {
+  if ((ph & 2) && !skip) {
     double acc[GPW][2];
 #pragma unroll
     for (int q = 0; q < GPW; ++q) acc[q][0] = acc[q][1] = 0.0;
@@ -527,7 +559,13 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   const bool overlap = a.want_signs && a.want_flip && a.Q != nullptr && a.Q != a.A && gridDim.x > 1;  // (in place: CTA 0 still reads the top rows of A)
   for (int stage = 0; stage < 2; ++stage) {
   if (stage == 0 && blockIdx.x == 0) {
-    orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
+    if (skip) {  // single pass: T2 = I
+      for (int i = tid; i < l * LD; i += kOrthThreads) T2s[i] = (i / LD == i % LD) ? 1.0 : 0.0;
+      for (int i = tid; i < l * lp; i += kOrthThreads) a.T2g[i] = (i / lp == i % lp) ? 1.0 : 0.0;
+      __syncthreads();
+    } else {
+      orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
+    }
     stamp();
   }
   if (blockIdx.x == 0 && stage == (overlap ? 1 : 0)) {

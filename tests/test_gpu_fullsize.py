@@ -25,7 +25,7 @@ def _run(packed, N, cls, **kw):
     return out
 
 
-def _orthonormal(Q, tol=1e-12):
+def _orthonormal(Q, tol=1e-10):
     return np.abs(Q.T @ Q - np.eye(Q.shape[1])).max() <= tol
 
 
