@@ -912,10 +912,11 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
   a.fsign = c->d_sign;
   a.jscratch = c->d_jscratch;
   a.status = c->d_status + 1;
-  // QR(G) of the dense stage (factors only, whole matrix on this rank): the second Cholesky pass is
+  // QR(G) of the dense stage (factors only; single launch or the row-sharded three-launch form): the second Cholesky pass is
   // dropped when the first one shows cond_F(G)^2 <= 1e5 (PCAONE_QR2_ALWAYS=1 keeps it)
   static const bool qr2_always = getenv("PCAONE_QR2_ALWAYS") && atoi(getenv("PCAONE_QR2_ALWAYS")) != 0;
-  a.skip2 = (!Q && phases == 7 && !qr2_always) ? c->d_status + 3 : nullptr;
+  a.skip2 = (!Q && (phases == 7 || phases == 2) && !qr2_always) ? c->d_status + 3 : nullptr;
+  a.skip_diag = c->cfg.rank == 0 ? 1.0 : 0.0;
   static unsigned long long* d_prof = nullptr;
   static int prof_left = getenv("PCAONE_ORTH_PROF") ? atoi(getenv("PCAONE_ORTH_PROF")) : 0;
   if (prof_left > 0) {

@@ -54,9 +54,10 @@ struct OrthArgs {
   // optional: per-column max |Q| as IEEE bit patterns (atomicMax; zeroed by the caller) — what the
   // int8 route's slicing of the new Omega needs, saving its own column-max kernel
   unsigned long long* colmax_out;
-  // optional (single-launch, factors-only calls): device flag through which CTA 0 tells the grid
+  // optional (factors-only calls): device flag through which CTA 0 tells the grid
   // that one Cholesky pass is enough (see P3); nullptr = always CholeskyQR2
   int* skip2;
+  double skip_diag;  // phase-split launches: this rank's share of the identity (1 on rank 0, else 0)
 };
 
 // shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
@@ -519,6 +520,14 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     stamp();
   }
   const bool skip = a.skip2 != nullptr && (ph & 2) && __ldcg(a.skip2) != 0;  // uniform across the grid
+  if (skip && !(ph & 4)) {
+    // phase-split launch (rows sharded over ranks; every rank took the same decision from the same
+    // allreduced Gram): hand the host's second allreduce matrices that sum to I, so that the last
+    // launch finds T2 = I
+    if (blockIdx.x == 0)
+      for (int i = tid; i < l * lp; i += kOrthThreads) a.Wg[i] = (i / lp == i % lp) ? a.skip_diag : 0.0;
+    return;
+  }
   // ---------------- P4: partial Gram of Q1 = A T1
   if ((ph & 2) ? blockIdx.x != 0 : (ph & 4) != 0) {  // T1 is in CTA 0's shared memory only if P3 ran in this launch
     load_T(a.T1g, T1s);

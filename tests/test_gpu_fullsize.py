@@ -89,3 +89,34 @@ def test_configs0_full_size_vs_compiled_reference(tmp_path):
         a = _run(packed, N, halko.NormalRsvdOpData, k=k, svd=1, maxp=20, tol=1e-4, precision=prec)
         assert np.array_equal(a["F"], Fr)
         assert_usv_close(a["U"], a["S"], a["V"], Ur, Sr, Vr)
+
+
+def test_single_pass_qr_of_g_matches_cholesky_qr2(tmp_path):
+    """QR(G) of the dense stage drops its second Cholesky pass when cond_F(G)^2 <= 1e5
+    (orth_fused.cuh, P3); PCAONE_QR2_ALWAYS=1 keeps CholeskyQR2. Same input, both settings (the
+    switch is read once per process, hence the subprocesses): identical up to rounding."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from pcaone_b200 import halko, synth\n"
+        "N, M, k = 3000, 60000, 10\n"
+        "packed = synth.torch_packed(N, M, k_pop=k + 4, seed=11, device='cuda:0', chunk=16384)\n"
+        "p = halko.Param(k=k, svd=2, bands=16, maxp=8, tol=0.0, no_shuffle=True, precision=3)\n"
+        "d = halko.FileBed(p, packed=packed, nsamples=N); d.prepare()\n"
+        "op = halko.FancyRsvdOpData(d, p.k, p.oversamples); op.setFlags(False, True)\n"
+        "op.computeUSV(p.maxp, p.tol)\n"
+        "np.savez(sys.argv[1], U=op.U, S=op.S, V=op.V)\n" % root)
+    outs = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / f"r{flag}.npz")
+        env = dict(os.environ, PCAONE_QR2_ALWAYS=flag)
+        r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs.append(np.load(out))
+    a, b = outs
+    assert np.max(np.abs(a["S"] ** 2 - b["S"] ** 2) / b["S"] ** 2) <= 1e-11
+    assert col_cos(a["U"], b["U"]).min() >= 1 - 1e-10 and col_cos(a["V"], b["V"]).min() >= 1 - 1e-10
+    assert _orthonormal(a["V"], 1e-11) and _orthonormal(b["V"], 1e-11)
