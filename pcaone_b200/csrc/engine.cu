@@ -566,7 +566,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     // window's ~250 partials per block cost ~30 us per launch)
     const bool fold_fw = false;
     if (nkb_w > kFoldFwMaxParts) {
-      tc::k_tc_reduce_fpart<<<(c->l + 7) / 8, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
+      tc::k_tc_reduce_fpart<<<c->l, 256, 0, c->stream>>>(c->d_Fpart, nkb_w, c->l, c->lp, Fw);
       PCA_CHECK_LAUNCH();
       c->tm.kernel_launches++;
     }

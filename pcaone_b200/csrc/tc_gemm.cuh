@@ -720,17 +720,33 @@ k_tc_finish_g(long long* __restrict__ R, long long* __restrict__ R2, uint64_t nr
   }
 }
 
-// Fw[c] = sum over the slice kernel's per-block partials, in block order with a fixed tree:
-// one warp per column, lane q sums parts q, q+32, ... then the 32 lane sums are folded.
+// Fw[c] = sum over the slice kernel's per-block partials (merged ranges: thousands of them), in a
+// fixed order: one block per column, thread t sums parts t, t + 256, ... (8 loads in flight), then a
+// shared-memory tree. (One warp per column on 5 blocks was 63 us per half-shard launch.)
 __global__ void __launch_bounds__(256) k_tc_reduce_fpart(const double* __restrict__ Fpart, uint32_t nparts, int l, int lp,
                                                           double* __restrict__ Fw) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ double s[256];
+  const int c = blockIdx.x, t = threadIdx.x;
   if (c >= l) return;
+  constexpr int UF = 8;
   double v = 0.0;
-  for (uint32_t b = lane; b < nparts; b += 32) v += Fpart[(size_t)b * lp + c];
-  v = warp_sum(v);
-  if (lane == 0) Fw[c] = v;
+  for (uint32_t b0 = t; b0 < nparts; b0 += 256 * UF) {
+    double x[UF];
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      const uint32_t b = b0 + 256 * u;
+      x[u] = b < nparts ? Fpart[(size_t)b * lp + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UF; ++u) v += x[u];
+  }
+  s[t] = v;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) s[t] += s[t + w];
+    __syncthreads();
+  }
+  if (t == 0) Fw[c] = s[0];
 }
 
 // H pass finish: Hacc[i][c] (+)= 2^(e_c-p) * (Cw_c - T[i][c] / 2) - Fw_c. R is re-zeroed. Optionally
