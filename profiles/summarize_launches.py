@@ -1,12 +1,14 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel.
-usage: python profiles/summarize_launches.py launches.csv [last_n_launches]"""
+usage: python profiles/summarize_launches.py launches.csv [last_n_launches]
+       python profiles/summarize_launches.py launches.csv start count     (a window of the list)"""
 import collections
 import csv
 import re
 import sys
 
 path = sys.argv[1]
-last = int(sys.argv[2]) if len(sys.argv) > 2 else None
+last = int(sys.argv[2]) if len(sys.argv) == 3 else None
+window = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else None
 import gzip
 op = gzip.open if path.endswith(".gz") else open
 with op(path, "rt") as f:
@@ -25,6 +27,9 @@ print(f"{len(rows)} launches in file")
 if last:
     rows = rows[-last:]
     print(f"summarising the last {last} launches (the timed region)")
+if window:
+    rows = rows[window[0]:window[0] + window[1]]
+    print(f"summarising launches [{window[0]}, {window[0] + window[1]}) (the timed region)")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for k, v in rows:
     agg[k][0] += 1
