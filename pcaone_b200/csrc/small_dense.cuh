@@ -96,7 +96,7 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* A = reinterpret_cast<double*>(smem_raw);  // column-major l x l: column j at A + j*l
   double* V = A + (size_t)l * l;                    // column-major l x l
-  __shared__ int s_rot;
+  __shared__ int s_rot, s_big;
   __shared__ double s_norm[kMaxL];
   __shared__ int s_ord[kMaxL];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -110,7 +110,7 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
   const double eps = 1e-15;
   int sweep = 0;
   for (; sweep < 60; ++sweep) {
-    if (tid == 0) s_rot = 0;
+    if (tid == 0) s_rot = s_big = 0;
     __syncthreads();
     for (int round = 0; round < n - 1; ++round) {
       for (int pi = warp; pi < n / 2; pi += nw) {
@@ -143,7 +143,10 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
         // the rotation parameters are a serial chain every lane waits for: reciprocal / rsqrt
         // forms instead of three divisions and three square roots (same test, squared)
         if (gamma * gamma > (eps * eps) * (alpha * beta) && gamma != 0.0) {
-          if (lane == 0) s_rot = 1;
+          if (lane == 0) {
+            s_rot = 1;
+            if (gamma * gamma > 1e-16 * (alpha * beta)) s_big = 1;
+          }
           const double zeta = (beta - alpha) * __drcp_rn(2.0 * gamma);
           const double z2 = 1.0 + zeta * zeta;
           const double tt = copysign(1.0, zeta) * __drcp_rn(fabs(zeta) + z2 * rsqrt(z2));
@@ -162,9 +165,12 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
       }
       __syncthreads();
     }
-    const int rot = s_rot;
+    const int rot = s_rot, big = s_big;
     __syncthreads();
-    if (!rot) break;
+    // Cyclic Jacobi converges quadratically: a sweep that met no pair with |cos| > 1e-8 (and rotated
+    // the ones above eps) leaves every pair below ~1e-16 — the sweep that would only confirm
+    // "no rotations" is not run.
+    if (!rot || !big) break;
   }
   // column norms -> singular values
   for (int j = warp; j < l; j += nw) {
