@@ -503,8 +503,9 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
       tc_slice(c, c->d_Omg, 0, c->N, o_colmax, nullptr, 0, c->d_BimgO, o_csum, nullptr, nullptr);
       c->omega_img_valid = true;
     }
-    PCA_CUDA(cudaMemsetAsync(w_colmax, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
     tc::TcGemmArgs a{};
+    a.zero_ptr = w_colmax;  // W column maxima + column sums of this range (finish_g / slice accumulate into them)
+    a.zero_n = 2 * (uint32_t)c->lp;
     a.PA = PG;
     a.stride_rt = (uint64_t)nkb_s * tc::kChunkBytes;
     a.stride_kb = tc::kChunkBytes;
@@ -520,6 +521,7 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     {
       Timed tk(c, 7);
       tc_launch(c, a, mode, c->d_Racc);
+      a.zero_ptr = nullptr;
       if (miss) tc_launch(c, a, tc::kMask, c->d_Racc2);
     }
     const uint64_t roff = (loc0 - (uint64_t)a.row_r0) * c->lp;
@@ -1008,8 +1010,7 @@ void update_omega(pcaone_ctx* c, const double* H, bool flip) {
   if (orth_fused_ok(c)) {
     unsigned long long* cm = nullptr;
     if (c->slices > 0 && c->d_tcs) {  // int8 route: the kernel also leaves max |Omega| per column for the slicing
-      PCA_CUDA(cudaMemsetAsync(c->d_tcs, 0, (size_t)2 * c->lp * sizeof(unsigned long long), c->stream));
-      cm = c->d_tcs;
+      cm = c->d_tcs;  // [0, 2 lp): column maxima + column sums of Omega, cleared by the kernel itself
     }
     orth_fused(c, H, c->N, c->d_Omg, flip ? c->d_Omg2 : nullptr, nullptr, true, flip, 7, cm);
     c->tm.omega_updates++;

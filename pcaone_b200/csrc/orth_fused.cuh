@@ -51,8 +51,10 @@ struct OrthArgs {
   // host runs three launches with an allreduce of Wg after each of the first two:
   //   1: P1-P2 (Gram of A -> Wg)   2: P3-P5 (T1 from Wg, Gram of A T1 -> Wg)   4: P6-P8 (T2, Ttot, Q)
   int phases;
-  // optional: per-column max |Q| as IEEE bit patterns (atomicMax; zeroed by the caller) — what the
-  // int8 route's slicing of the new Omega needs, saving its own column-max kernel
+  // optional: per-column max |Q| as IEEE bit patterns (atomicMax) — what the int8 route's slicing of
+  // the new Omega needs, saving its own column-max kernel. Single-launch calls clear
+  // colmax_out[0, 2 lp) themselves (the maxima and the slice kernel's column sums behind them):
+  // CTA 0 in P1, barriers before the atomics of P7
   unsigned long long* colmax_out;
   // optional (factors-only calls): device flag through which CTA 0 tells the grid
   // that one Cholesky pass is enough (see P3); nullptr = always CholeskyQR2
@@ -459,6 +461,8 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   };
   const int ph = a.phases ? a.phases : 7;
   stamp();
+  if (a.colmax_out && ph == 7 && blockIdx.x == 0)
+    for (int i = tid; i < 2 * lp; i += kOrthThreads) a.colmax_out[i] = 0ull;
   zero_pad_cols();
   // ---------------- P1: partial Gram of A
   if (ph & 1) {

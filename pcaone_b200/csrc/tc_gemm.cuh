@@ -107,6 +107,11 @@ struct TcGemmArgs {
   long long row_begin, row_end;   // absolute rows that receive output
   long long row_r0;               // absolute row stored at R[0]
   long long* R;                   // [rows][lp] int64 accumulators (zero on entry, added to)
+  // optional: zero_n words that the kernels AFTER this launch accumulate into with atomics and that
+  // nothing reads during it (the W column maxima / column sums of the range): cleared by CTA 0
+  // instead of a cudaMemsetAsync node per range
+  unsigned long long* zero_ptr;
+  uint32_t zero_n;
 };
 
 // Four UMMAs (K = 4 x 32) of one row tile for one stage: D[d_tmem] (+)= A[a_tmem .. +32 cols] * B.
@@ -165,6 +170,8 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
   long long* scratch = reinterpret_cast<long long*>(smem + (size_t)kNS * stage_bytes);
 
   if (warp == 2) tmem_alloc<512>(&tmem_slot);
+  if (blockIdx.x == 0 && a.zero_ptr)
+    for (uint32_t i = threadIdx.x; i < a.zero_n; i += blockDim.x) a.zero_ptr[i] = 0ull;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNS; ++i) {
       mbar_init(&full[i], 4 * RT + 1);
