@@ -11,6 +11,10 @@
 //   P6  CTA 0: T2, Ttot = T1 T2, Householder signs from the top l x l block of Q
 //   P7  Q = (A T1) T2 o signs written out; partial flipOmg column sums
 //   P8  flip decision, Omega *= flip sign, Omega2 = Omega
+// Shortcuts taken from the data (each bounded below 1e-11, see the code): T2 from its first-order
+// expansion when Q1^T Q1 is within 1e-11 of I; P4/P5 skipped (T2 = I) for factors-only calls whose
+// first pass shows cond_F(A)^2 <= 1e5; for Omega updates the sign replay of P6 runs on CTA 0
+// WHILE the other CTAs do P7 on the unsigned Q, and P8 applies hsign * flip.
 // winSVD calls this up to 63 times per epoch on an N x l matrix that is a few MB: the multi-kernel
 // version (2 Gram + 2 reduce + 2 Cholesky + 2 host status reads + 2 right-multiplies + signs + 3
 // flip kernels) is launch/latency bound at ~0.3 ms per update; this kernel is one launch and no
@@ -569,122 +573,123 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   // grid barrier moves up to right after the T2 factor, CTA 0 replays the signs (stage 1) WHILE the
   // other CTAs run P7 on all rows, and P8 applies hsign * flip in its one sweep (same bits as
   // before: |o2 - h q| and |o2 + h q| swap roles when h = -1).
-  const bool overlap = a.want_signs && a.want_flip && a.Q != nullptr && a.Q != a.A && gridDim.x > 1;  // (in place: CTA 0 still reads the top rows of A)
+  // (not for in-place calls: CTA 0 still reads the top rows of A while the others write Q)
+  const bool overlap = a.want_signs && a.want_flip && a.Q != nullptr && a.Q != a.A && gridDim.x > 1;
   for (int stage = 0; stage < 2; ++stage) {
-  if (stage == 0 && blockIdx.x == 0) {
-    if (skip) {  // single pass: T2 = I
-      for (int i = tid; i < l * LD; i += kOrthThreads) T2s[i] = (i / LD == i % LD) ? 1.0 : 0.0;
-      for (int i = tid; i < l * lp; i += kOrthThreads) a.T2g[i] = (i / lp == i % lp) ? 1.0 : 0.0;
-      __syncthreads();
-    } else {
-      orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
-    }
-    stamp();
-  }
-  if (blockIdx.x == 0 && stage == (overlap ? 1 : 0)) {
-    if (a.Ttot) {
-      for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
-        const int r = idx / lp, c = idx - r * lp;
-        double s = 0.0;
-        if (c < l)
-          for (int k = 0; k < l; ++k) s += T1s[r * LD + k] * T2s[k * LD + c];
-        a.Ttot[idx] = s;
+    if (stage == 0 && blockIdx.x == 0) {
+      if (skip) {  // single pass: T2 = I
+        for (int i = tid; i < l * LD; i += kOrthThreads) T2s[i] = (i / LD == i % LD) ? 1.0 : 0.0;
+        for (int i = tid; i < l * lp; i += kOrthThreads) a.T2g[i] = (i / lp == i % lp) ? 1.0 : 0.0;
+        __syncthreads();
+      } else {
+        orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
       }
-    }
-    if (a.want_signs) {
-      // top l x l block of Q = (A T1) T2 -> Ws (row-major l x l)
-      const uint64_t r1_save = r1;
-      for (int rb = 0; rb < l; rb += TR) {
-        __syncthreads();
-        for (int idx = tid; idx < TR * LC; idx += kOrthThreads) {
-          const int rr = idx / LC, c = idx - rr * LC;
-          As[rr * LD + c] =
-              ((uint64_t)(rb + rr) < a.rows && rb + rr < l && c < l) ? a.A[(uint64_t)(rb + rr) * lp + c] : 0.0;
-        }
-        __syncthreads();
-        double q[NPW][2];
-        tile_times_T(As, T1s, q);
-        store_tile(Qs, q);
-        __syncthreads();
-        tile_times_T(Qs, T2s, q);
-#pragma unroll
-        for (int n = 0; n < NPW; ++n)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = rb + m0 + fg, c = 8 * (nbase + n) + 2 * ft + h;
-            if (rr < l && c < l) Ws[rr * l + c] = q[n][h];
-          }
-      }
-      (void)r1_save;
-      __syncthreads();
       stamp();
-      // sign-modified LU replay of the Householder sign decisions (see k_householder_signs), with
-      // the l x l block in registers: per step the owners publish row i and column i, one barrier
-      __shared__ double s_lr[2][16 * R], s_lc[2][16 * R];
-      double w[R][R];
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int r = ty + 16 * i, c = tx + 16 * j;
-          w[i][j] = (r < l && c < l) ? Ws[r * l + c] : 0.0;
+    }
+    if (blockIdx.x == 0 && stage == (overlap ? 1 : 0)) {
+      if (a.Ttot) {
+        for (int idx = tid; idx < l * lp; idx += kOrthThreads) {
+          const int r = idx / lp, c = idx - r * lp;
+          double s = 0.0;
+          if (c < l)
+            for (int k = 0; k < l; ++k) s += T1s[r * LD + k] * T2s[k * LD + c];
+          a.Ttot[idx] = s;
         }
-      for (int i0 = 0; i0 < l; ++i0) {
-        const int b = i0 & 1, it = i0 >> 4;
-        if (ty == (i0 & 15)) {
+      }
+      if (a.want_signs) {
+        // top l x l block of Q = (A T1) T2 -> Ws (row-major l x l)
+        const uint64_t r1_save = r1;
+        for (int rb = 0; rb < l; rb += TR) {
+          __syncthreads();
+          for (int idx = tid; idx < TR * LC; idx += kOrthThreads) {
+            const int rr = idx / LC, c = idx - rr * LC;
+            As[rr * LD + c] =
+                ((uint64_t)(rb + rr) < a.rows && rb + rr < l && c < l) ? a.A[(uint64_t)(rb + rr) * lp + c] : 0.0;
+          }
+          __syncthreads();
+          double q[NPW][2];
+          tile_times_T(As, T1s, q);
+          store_tile(Qs, q);
+          __syncthreads();
+          tile_times_T(Qs, T2s, q);
 #pragma unroll
-          for (int i = 0; i < R; ++i)
-            if (i == it) {
+          for (int n = 0; n < NPW; ++n)
 #pragma unroll
-              for (int j = 0; j < R; ++j) s_lr[b][tx + 16 * j] = w[i][j];
+            for (int h = 0; h < 2; ++h) {
+              const int rr = rb + m0 + fg, c = 8 * (nbase + n) + 2 * ft + h;
+              if (rr < l && c < l) Ws[rr * l + c] = q[n][h];
             }
         }
-        if (tx == (i0 & 15)) {
-#pragma unroll
-          for (int j = 0; j < R; ++j)
-            if (j == it) {
-#pragma unroll
-              for (int i = 0; i < R; ++i) s_lc[b][ty + 16 * i] = w[i][j];
-            }
-        }
+        (void)r1_save;
         __syncthreads();
-        const double c0 = s_lr[b][i0];
-        const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
-        if (tid == 0) a.hsign[i0] = beta;
-        const double inv = __drcp_rn(c0 - beta);  // == 1.0 / (c0 - beta), correctly rounded
-        double cr[R], rc[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) cr[i] = s_lc[b][ty + 16 * i] * inv;
-#pragma unroll
-        for (int j = 0; j < R; ++j) rc[j] = s_lr[b][tx + 16 * j];
+        stamp();
+        // sign-modified LU replay of the Householder sign decisions (see k_householder_signs), with
+        // the l x l block in registers: per step the owners publish row i and column i, one barrier
+        __shared__ double s_lr[2][16 * R], s_lc[2][16 * R];
+        double w[R][R];
 #pragma unroll
         for (int i = 0; i < R; ++i)
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int r = ty + 16 * i, c = tx + 16 * j;
-            if (r > i0 && c > i0) w[i][j] -= cr[i] * rc[j];
+            w[i][j] = (r < l && c < l) ? Ws[r * l + c] : 0.0;
           }
+        for (int i0 = 0; i0 < l; ++i0) {
+          const int b = i0 & 1, it = i0 >> 4;
+          if (ty == (i0 & 15)) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+              if (i == it) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) s_lr[b][tx + 16 * j] = w[i][j];
+              }
+          }
+          if (tx == (i0 & 15)) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+              if (j == it) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) s_lc[b][ty + 16 * i] = w[i][j];
+              }
+          }
+          __syncthreads();
+          const double c0 = s_lr[b][i0];
+          const double beta = (c0 >= 0.0) ? -1.0 : 1.0;
+          if (tid == 0) a.hsign[i0] = beta;
+          const double inv = __drcp_rn(c0 - beta);  // == 1.0 / (c0 - beta), correctly rounded
+          double cr[R], rc[R];
+#pragma unroll
+          for (int i = 0; i < R; ++i) cr[i] = s_lc[b][ty + 16 * i] * inv;
+#pragma unroll
+          for (int j = 0; j < R; ++j) rc[j] = s_lr[b][tx + 16 * j];
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const int r = ty + 16 * i, c = tx + 16 * j;
+              if (r > i0 && c > i0) w[i][j] -= cr[i] * rc[j];
+            }
+        }
+      } else {
+        for (int c = tid; c < l; c += kOrthThreads) a.hsign[c] = 1.0;
       }
-    } else {
-      for (int c = tid; c < l; c += kOrthThreads) a.hsign[c] = 1.0;
     }
-  }
-  if (stage == 0) {
-    __threadfence();
-    stamp();
-    grid.sync();
-    stamp();
-    if (!a.Q) {  // factors only (uniform across the grid)
-      if (blockIdx.x == 0)
-        for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
-      return;
+    if (stage == 0) {
+      __threadfence();
+      stamp();
+      grid.sync();
+      stamp();
+      if (!a.Q) {  // factors only (uniform across the grid)
+        if (blockIdx.x == 0)
+          for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
+        return;
+      }
+      if (overlap) {  // the rows of P7 / P8 go to CTAs 1.., CTA 0 has none
+        const uint64_t rpc7 = ((a.rows + gridDim.x - 2) / (gridDim.x - 1) + TR - 1) / TR * TR;
+        r0 = blockIdx.x == 0 ? a.rows : min(a.rows, (uint64_t)(blockIdx.x - 1) * rpc7);
+        r1 = min(a.rows, r0 + rpc7);
+      }
     }
-    if (overlap) {  // the rows of P7 / P8 go to CTAs 1.., CTA 0 has none
-      const uint64_t rpc7 = ((a.rows + gridDim.x - 2) / (gridDim.x - 1) + TR - 1) / TR * TR;
-      r0 = blockIdx.x == 0 ? a.rows : min(a.rows, (uint64_t)(blockIdx.x - 1) * rpc7);
-      r1 = min(a.rows, r0 + rpc7);
-    }
-  }
   }  // stage
   if (overlap && blockIdx.x == 0) __threadfence();  // hsign, Ttot: visible to the grid after the next barrier
   // ---------------- P7: Q = (A T1) T2 o hsign ; partial flip sums
