@@ -56,9 +56,20 @@ typedef struct pcaone_config {
   int32_t  out_of_core;  /* -m > 0: walk start[]/stop[] blocks, no flipOmg in sSVD   */
   int32_t  precision;    /* PCAONE_PREC_*                                            */
   int32_t  device;       /* CUDA ordinal                                             */
-  int32_t  rank, world;  /* SNP-sharded multi-GPU job: this context's rank / #ranks  */
+  int32_t  rank, world;  /* sharded multi-GPU job: this context's rank / #ranks      */
   uint32_t maxiter;      /* --maxiter 100 (EM)                                       */
   double   tolem;        /* --tol-em 1e-5                                            */
+  /* How the matrix is split over the ranks of a multi-GPU job. 0: by SNPs — every rank
+   * owns nsnps of the nsnps_total SNPs and all nsamples samples; the N x l partial H is summed over
+   * the ranks before each Omega update. 1: by samples — every rank owns nsamples of the
+   * nsamples_total samples (a byte-column range of every bed row, sample_offset % 4 == 0) and ALL
+   * SNPs; the exact int64 partial sums of G_b = X_b^T Omega (window x l) are summed instead, H and
+   * Omega stay row-sharded, and the orthonormalisation exchanges only l x l Gram matrices. The
+   * exchange per Omega update is N x l doubles in mode 0, (window SNPs) x l in mode 1: hosts pick
+   * mode 1 when the windows are shorter than N (configs[2]: 7.8k-SNP windows, N = 500k). */
+  int32_t  shard_samples;
+  uint64_t nsamples_total; /* N of the whole job (0 = nsamples)                        */
+  uint64_t sample_offset;  /* first sample of this rank (shard_samples)                */
 } pcaone_config;
 
 /* Collective hook for SNP-sharded jobs: sum `count` doubles at device pointer `buf`
@@ -79,6 +90,14 @@ int  pcaone_abi_version(void);
 void* pcaone_stream(pcaone_ctx* ctx);                  /* the cudaStream_t all work runs on */
 int  pcaone_sync(pcaone_ctx* ctx);
 int  pcaone_set_allreduce(pcaone_ctx* ctx, pcaone_allreduce_fn fn, void* user);
+/* In-library collectives (NCCL over NVLink, enqueued on the context's stream with no host
+ * round trip): rank 0 calls pcaone_comm_unique_id, the host hands the 128 bytes to every rank
+ * (one process per GPU), each calls pcaone_comm_init. A host that drives several GPUs from one
+ * process creates the communicators itself (ncclCommInitAll) and attaches them. With a
+ * communicator attached the allreduce hook above is not used. */
+int  pcaone_comm_unique_id(uint8_t* out128);
+int  pcaone_comm_init(pcaone_ctx* ctx, const uint8_t* id128, int rank, int world);
+int  pcaone_comm_attach(pcaone_ctx* ctx, void* nccl_comm);
 /* Page-locked host buffers for the packed bed (FileBed::inbed, FilePlink.hpp:43-46): a host that
  * reads the .bed into one of these gets full-rate cudaMemcpyAsync in upload / streaming. */
 int  pcaone_alloc_pinned(void** out, size_t bytes);
@@ -92,6 +111,14 @@ int pcaone_upload_bed(pcaone_ctx* ctx, const uint8_t* packed, uint64_t nsnps, in
 /* Out-of-core from host memory: `packed` (nsnps x bpr, ideally pinned) stays on the host
  * and is streamed block by block through double-buffered cudaMemcpyAsync every pass. */
 int pcaone_set_host_source(pcaone_ctx* ctx, const uint8_t* packed, uint64_t nsnps);
+/* Same with rows `row_stride` bytes apart: `packed` points at this context's first byte of SNP 0
+ * inside a wider bed (a sample shard reads bytes [sample_offset/4, +ceil(nsamples/4)) of every row).
+ * Either call also tells the context that the data behind the plan is new: the HBM tile cache
+ * (below) is refilled on the next pass.
+ * Streamed blocks on the int8 route keep their re-tiled operands in HBM after the first pass when
+ * they fit (2 x the packed bytes), so an out-of-core job whose bed fits a 180 GB B200 twice reads
+ * the host link once; blocks that do not fit keep streaming every pass. */
+int pcaone_set_host_source2(pcaone_ctx* ctx, const uint8_t* packed, uint64_t nsnps, uint64_t row_stride);
 /* Out-of-core through a reader callback (file-backed FileBed). */
 int pcaone_set_reader_source(pcaone_ctx* ctx, pcaone_read_block_fn fn, void* user);
 /* Out-of-core straight from a .bed file (checks the magic 6c 1b 01, FilePlink.hpp:24-27);
@@ -234,6 +261,7 @@ typedef struct pcaone_timers {
   double ld_ms;                    /* k_ld_tiles (pcaone_ld_r2) */
   uint64_t ld_tiles, ld_pairs;     /* 128 x 128 Gram tiles computed / r2 values produced */
   uint64_t tc_miss_ranges;         /* of tc_ranges: ranges with missing calls (count + mask GEMM pairs) */
+  uint64_t cache_hits;             /* streamed blocks served from the HBM tile cache instead of the host */
 } pcaone_timers;
 int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
 int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */

@@ -20,6 +20,7 @@ class Config(C.Structure):
         ("maxp", C.c_uint32), ("tol", C.c_double), ("ploidy", C.c_int32), ("scale", C.c_int32),
         ("emu", C.c_int32), ("out_of_core", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32), ("maxiter", C.c_uint32), ("tolem", C.c_double),
+        ("shard_samples", C.c_int32), ("nsamples_total", C.c_uint64), ("sample_offset", C.c_uint64),
     ]
 
 
@@ -31,7 +32,7 @@ class Timers(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("omega_updates", C.c_uint64),
         ("tc_ranges", C.c_uint64), ("fp64_ranges", C.c_uint64), ("tc_g_ms", C.c_double), ("tc_h_ms", C.c_double),
         ("ld_ms", C.c_double), ("ld_tiles", C.c_uint64), ("ld_pairs", C.c_uint64),
-        ("tc_miss_ranges", C.c_uint64),
+        ("tc_miss_ranges", C.c_uint64), ("cache_hits", C.c_uint64),
     ]
 
 
@@ -50,6 +51,7 @@ SYMBOLS = [
     "pcaone_get_timers", "pcaone_enable_timing", "pcaone_alloc_pinned", "pcaone_free_pinned", "pcaone_device_count",
     "pcaone_upload_dense", "pcaone_dense_rsvd", "pcaone_upload_dosage", "pcaone_perform_op", "pcaone_ld_prune", "pcaone_xt_times", "pcaone_x_times",
     "pcaone_upload_gl", "pcaone_gl_em_maf",
+    "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2",
 ]
 
 _lib = None
@@ -91,6 +93,8 @@ def load():
         "pcaone_upload_dosage": [vp, vp, u64, i32], "pcaone_perform_op": [vp, vp, vp], "pcaone_xt_times": [vp, vp, u32, vp, vp], "pcaone_x_times": [vp, vp, u32, vp],
         "pcaone_upload_gl": [vp, vp, u64, i32], "pcaone_gl_em_maf": [vp, u32, dbl, vp],
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
+        "pcaone_comm_unique_id": [vp], "pcaone_comm_init": [vp, vp, i32, i32], "pcaone_comm_attach": [vp, vp],
+        "pcaone_set_host_source2": [vp, vp, u64, u64],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.pcaone_alloc_pinned.restype = C.c_int

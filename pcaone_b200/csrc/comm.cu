@@ -1,0 +1,155 @@
+// pcaone_b200 — collectives between the ranks of a sharded job.
+//
+// One context per GPU; the exchange steps of the path are sums of small or tall partial products
+// (N x l partial H, range x l int64 partial G accumulators, l x l Gram matrices, per-SNP genotype
+// counts). They run on the context's stream through an NCCL communicator owned by the library:
+//   pcaone_comm_unique_id + pcaone_comm_init   one process per GPU (torchrun): rank 0 makes the id,
+//                                             the host broadcasts the 128 bytes, every rank joins
+//   pcaone_comm_attach                         one process, several GPUs: the host made the
+//                                             communicators itself (ncclCommInitAll)
+// libnccl is resolved at run time (dlopen), so the library loads on a box without it and a
+// Python host that already imported torch shares torch's copy. The older host hook
+// (pcaone_set_allreduce, double sums only) is still honoured when no communicator is attached.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "ctx.hpp"
+
+struct pcaone_comm {
+  ncclComm_t comm = nullptr;
+  bool owned = false;
+};
+
+namespace pcaone {
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+};
+
+NcclApi& api() {
+  static NcclApi a = [] {
+    NcclApi n;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (n.handle) break;
+    }
+    if (!n.handle) {
+      n.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+      return n;
+    }
+    auto sym = [&](const char* s) {
+      void* p = dlsym(n.handle, s);
+      if (!p) n.why = std::string("libnccl is missing ") + s;
+      return p;
+    };
+    n.GetUniqueId = (decltype(n.GetUniqueId))sym("ncclGetUniqueId");
+    n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
+    n.CommDestroy = (decltype(n.CommDestroy))sym("ncclCommDestroy");
+    n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
+    n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
+    n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
+    n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
+    return n;
+  }();
+  return a;
+}
+
+void need_api() {
+  if (!api().why.empty() || !api().handle) throw std::runtime_error("NCCL unavailable: " + api().why);
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+  if (r != ncclSuccess)
+    throw std::runtime_error(std::string(what) + " failed: " + (api().GetErrorString ? api().GetErrorString(r) : "?"));
+}
+
+void reduce(pcaone_ctx* c, void* buf, uint64_t count, ncclDataType_t dt, ncclRedOp_t op) {
+  if (c->cfg.world <= 1 || count == 0) return;
+  Timed t(c, 5);
+  if (c->comm && c->comm->comm) {
+    nccl_check(api().AllReduce(buf, buf, (size_t)count, dt, op, c->comm->comm, c->stream), "ncclAllReduce");
+    return;
+  }
+  if (dt == ncclFloat64 && op == ncclSum && c->allreduce) {
+    if (c->allreduce(c->allreduce_user, buf, count, c->stream)) throw std::runtime_error("allreduce hook failed");
+    return;
+  }
+  throw std::runtime_error("world > 1 but no communicator attached (pcaone_comm_init / pcaone_comm_attach)");
+}
+
+}  // namespace
+
+void comm_allreduce_f64(pcaone_ctx* c, double* buf, uint64_t count) { reduce(c, buf, count, ncclFloat64, ncclSum); }
+void comm_allreduce_i64(pcaone_ctx* c, long long* buf, uint64_t count) { reduce(c, buf, count, ncclInt64, ncclSum); }
+void comm_allreduce_u64_max(pcaone_ctx* c, unsigned long long* buf, uint64_t count) {
+  reduce(c, buf, count, ncclUint64, ncclMax);
+}
+void comm_allreduce_u32(pcaone_ctx* c, uint32_t* buf, uint64_t count) { reduce(c, buf, count, ncclUint32, ncclSum); }
+
+// several reductions as ONE launch (only meaningful with the in-library communicator)
+void comm_group_begin(pcaone_ctx* c) {
+  if (c->cfg.world > 1 && c->comm && c->comm->comm) nccl_check(api().GroupStart(), "ncclGroupStart");
+}
+void comm_group_end(pcaone_ctx* c) {
+  if (c->cfg.world > 1 && c->comm && c->comm->comm) nccl_check(api().GroupEnd(), "ncclGroupEnd");
+}
+
+void comm_destroy(pcaone_ctx* c) {
+  if (!c->comm) return;
+  if (c->comm->owned && c->comm->comm && api().CommDestroy) api().CommDestroy(c->comm->comm);
+  delete c->comm;
+  c->comm = nullptr;
+}
+
+}  // namespace pcaone
+
+using namespace pcaone;
+
+extern "C" {
+
+int pcaone_comm_unique_id(uint8_t* out128) {
+  try {
+    need_api();
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    nccl_check(api().GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(out128, &id, sizeof(id));
+    return 0;
+  } catch (const std::exception&) {
+    return 1;
+  }
+}
+
+int pcaone_comm_init(pcaone_ctx* c, const uint8_t* id128, int rank, int world) {
+  CTX_GUARD(c, {
+    need_api();
+    if (rank != c->cfg.rank || world != c->cfg.world) throw std::runtime_error("comm_init: rank / world differ from the context's");
+    comm_destroy(c);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    c->comm = new pcaone_comm();
+    nccl_check(api().CommInitRank(&c->comm->comm, world, id, rank), "ncclCommInitRank");
+    c->comm->owned = true;
+  });
+}
+
+int pcaone_comm_attach(pcaone_ctx* c, void* nccl_comm) {
+  CTX_GUARD(c, {
+    need_api();
+    comm_destroy(c);
+    c->comm = new pcaone_comm();
+    c->comm->comm = (ncclComm_t)nccl_comm;
+    c->comm->owned = false;
+  });
+}
+
+}  // extern "C"

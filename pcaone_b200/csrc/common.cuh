@@ -19,6 +19,8 @@
 namespace pcaone {
 
 constexpr double kVarTol = 1e-9;  // VAR_TOL, reference src/Data.hpp:7
+constexpr int kMaxL = 112;     // k + oversamples: 2*l*l doubles of Jacobi state must fit 227 KB of shared memory (small_dense.cuh)
+constexpr int kOrthMaxL = 80;  // fused orthonormalisation: two l x 16R factor matrices must fit shared memory (orth_fused.cuh)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

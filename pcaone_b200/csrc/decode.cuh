@@ -56,7 +56,7 @@ __global__ void k_gather_f64(const double* __restrict__ src, double* __restrict_
 // masked out. F = (n00 + 0.5 n10) / (n00 + n10 + n11): the reference's running FP64 sum holds
 // only multiples of 0.5 and is exact, so one IEEE division reproduces it bit for bit.
 __global__ void k_allele_freq(const uint8_t* __restrict__ P, uint32_t pitch, uint32_t N, uint64_t nsnps,
-                              double* __restrict__ F, uint32_t* __restrict__ nmiss) {
+                              double* __restrict__ F, uint32_t* __restrict__ nmiss, uint32_t* __restrict__ counts = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -89,6 +89,12 @@ __global__ void k_allele_freq(const uint8_t* __restrict__ P, uint32_t pitch, uin
       c11 += __shfl_xor_sync(0xffffffffu, c11, o);
     }
     if (lane == 0) {
+      if (counts) {  // sample-sharded job: the three counts are summed over the ranks first (k_af_from_counts)
+        counts[3 * j + 0] = c01;
+        counts[3 * j + 1] = c10;
+        counts[3 * j + 2] = c11;
+        continue;
+      }
       const uint32_t c = N - c01;
       const uint32_t c00 = c - c10 - c11;
       double f = 0.0;
@@ -96,6 +102,21 @@ __global__ void k_allele_freq(const uint8_t* __restrict__ P, uint32_t pitch, uin
       F[j] = f;
       if (nmiss) nmiss[j] = c01;
     }
+  }
+}
+
+// F and the missing count from (c01, c10, c11) summed over the sample shards: the same single
+// IEEE division of exact integer counts as above, so F does not depend on how the samples were split.
+__global__ void k_af_from_counts(const uint32_t* __restrict__ counts, uint64_t N_total, uint64_t nsnps,
+                                 double* __restrict__ F, uint32_t* __restrict__ nmiss) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nsnps; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c01 = counts[3 * j], c10 = counts[3 * j + 1], c11 = counts[3 * j + 2];
+    const uint32_t c = (uint32_t)N_total - c01;
+    const uint32_t c00 = c - c10 - c11;
+    double f = 0.0;
+    if (c > 0) f = __ddiv_rn(__dadd_rn((double)c00, __dmul_rn(0.5, (double)c10)), (double)c);
+    F[j] = f;
+    if (nmiss) nmiss[j] = c01;
   }
 }
 

@@ -29,7 +29,6 @@ namespace pcaone {
 namespace cg = cooperative_groups;
 
 constexpr int kOrthThreads = 256;
-constexpr int kOrthMaxL = 80;  // two l x 16R factor matrices must fit shared memory
 __host__ __device__ constexpr int orth_tile_rows(int R) { return R <= 4 ? 64 : 32; }  // rows per staged tile
 
 struct OrthArgs {
@@ -64,6 +63,11 @@ struct OrthArgs {
   // that one Cholesky pass is enough (see P3); nullptr = always CholeskyQR2
   int* skip2;
   double skip_diag;  // phase-split launches: this rank's share of the identity (1 on rank 0, else 0)
+  // Row-sharded Omega update (rows of A, Q, Q2 are this rank's samples): the launch with phases = 4
+  // writes the UNSIGNED Q, leaves its flipOmg column sums (both signs) and — on the rank that owns
+  // the top l rows (want_signs) — the Householder signs in flipbuf[3 l] = {dsum, ssum, hsign} and
+  // stops; the host sums flipbuf over the ranks and a launch with phases = 8 applies hsign * flip.
+  double* flipbuf;
 };
 
 // shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
@@ -463,7 +467,45 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     }
     ++prof_i;
   };
+  // P8 body: Qs[0, 2l) holds the flipOmg column sums of the (possibly unsigned) Q; `unsigned_q`: they
+  // were taken before the Householder signs hs[] were applied (with hs = -1 they swap roles)
+  auto apply_flip = [&](bool unsigned_q, const double* hs_src) {
+    for (int c = tid; c < l; c += kOrthThreads) {
+      const double hsg = unsigned_q ? __ldcg(hs_src + c) : 1.0;
+      const double dsm = hsg < 0.0 ? Qs[l + c] : Qs[c], ssm = hsg < 0.0 ? Qs[c] : Qs[l + c];
+      const double f = (dsm > 2 * ssm) ? -1.0 : 1.0;
+      As[c] = f * hsg;
+      if (blockIdx.x == 0) a.fsign[c] = unsigned_q ? f * hsg : f * __ldcg(a.hsign + c);
+    }
+    __syncthreads();
+    const uint64_t total = (r1 - r0) * (uint64_t)lp;
+    constexpr int PB = 8;  // loads of a batch are issued before the first store (independent round trips)
+    for (uint64_t i0 = tid; i0 < total; i0 += (uint64_t)kOrthThreads * PB) {
+      double v[PB];
+#pragma unroll
+      for (int b = 0; b < PB; ++b) {
+        const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
+        v[b] = i < total ? a.Q[r0 * lp + i] : 0.0;
+      }
+#pragma unroll
+      for (int b = 0; b < PB; ++b) {
+        const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
+        if (i < total) {
+          const int c = (int)(i % lp);
+          const double w = c < l ? v[b] * As[c] : v[b];
+          a.Q[r0 * lp + i] = w;
+          if (a.Q2) a.Q2[r0 * lp + i] = w;
+        }
+      }
+    }
+  };
   const int ph = a.phases ? a.phases : 7;
+  if (ph == 8) {  // row-sharded Omega update, last launch: flipbuf = {dsum, ssum, hsign} summed over the ranks
+    for (int c = tid; c < 2 * l; c += kOrthThreads) Qs[c] = a.flipbuf[c];
+    __syncthreads();
+    apply_flip(true, a.flipbuf + 2 * l);
+    return;
+  }
   stamp();
   if (a.colmax_out && ph == 7 && blockIdx.x == 0)
     for (int i = tid; i < 2 * lp; i += kOrthThreads) a.colmax_out[i] = 0ull;
@@ -699,7 +741,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   // product goes through shared memory once more (As is free after the first product)
   double hs[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? (overlap ? 1.0 : a.hsign[tx + 16 * j]) : 0.0;
+  for (int j = 0; j < R; ++j) hs[j] = (tx + 16 * j < l) ? ((overlap || a.flipbuf) ? 1.0 : a.hsign[tx + 16 * j]) : 0.0;
   double dsum[R], ssum[R], amax[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) dsum[j] = ssum[j] = amax[j] = 0.0;
@@ -768,7 +810,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       if (m > 0.0) atomicMax(a.colmax_out + c, (unsigned long long)__double_as_longlong(m));
     }
   }
-  if (!a.want_flip) {
+  if (!a.want_flip && !a.flipbuf) {
     if (blockIdx.x == 0)
       for (int c = tid; c < l; c += kOrthThreads) a.fsign[c] = a.hsign[c];
     return;  // uniform across the grid: no further grid.sync
@@ -793,6 +835,17 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   stamp();
   grid.sync();
   stamp();
+  if (a.flipbuf) {  // row-sharded: the sums (and rank 0's signs) go through the host's allreduce first
+    if (blockIdx.x == 0) {
+      for (int c = tid; c < 2 * l; c += kOrthThreads) {
+        double v = 0.0;
+        for (unsigned p0 = 0; p0 < gridDim.x; ++p0) v += a.part[(size_t)p0 * pstride + c];  // CTA order
+        a.flipbuf[c] = v;
+      }
+      for (int c = tid; c < l; c += kOrthThreads) a.flipbuf[2 * l + c] = a.want_signs ? __ldcg(a.hsign + c) : 0.0;
+    }
+    return;
+  }
   // ---------------- P8: flip decision (every CTA, same fixed order), apply to own rows
   __syncthreads();
   for (int c = tid; c < 2 * l; c += kOrthThreads) {
@@ -807,35 +860,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     Qs[c] = v;
   }
   __syncthreads();
-  for (int c = tid; c < l; c += kOrthThreads) {
-    // overlap mode: the sums were taken on the unsigned Q; with hsign = -1 they swap roles
-    const double hsg = overlap ? __ldcg(a.hsign + c) : 1.0;
-    const double dsm = hsg < 0.0 ? Qs[l + c] : Qs[c], ssm = hsg < 0.0 ? Qs[c] : Qs[l + c];
-    const double f = (dsm > 2 * ssm) ? -1.0 : 1.0;
-    As[c] = f * hsg;
-    if (blockIdx.x == 0) a.fsign[c] = f * __ldcg(a.hsign + c);
-  }
-  __syncthreads();
-  const uint64_t total = (r1 - r0) * (uint64_t)lp;
-  constexpr int PB = 8;  // loads of a batch are issued before the first store (independent round trips)
-  for (uint64_t i0 = tid; i0 < total; i0 += (uint64_t)kOrthThreads * PB) {
-    double v[PB];
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
-      v[b] = i < total ? a.Q[r0 * lp + i] : 0.0;
-    }
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      const uint64_t i = i0 + (uint64_t)kOrthThreads * b;
-      if (i < total) {
-        const int c = (int)(i % lp);
-        const double w = c < l ? v[b] * As[c] : v[b];
-        a.Q[r0 * lp + i] = w;
-        a.Q2[r0 * lp + i] = w;
-      }
-    }
-  }
+  apply_flip(overlap, a.hsign);
   stamp();
   if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[63] = (unsigned long long)prof_i;
 }

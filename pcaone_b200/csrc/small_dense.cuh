@@ -8,7 +8,6 @@
 namespace pcaone {
 
 constexpr int kSmallThreads = 1024;
-constexpr int kMaxL = 112;  // 2*l*l doubles of Jacobi state must fit 227 KB of shared memory
 
 // status[0] = 0 ok / 1 breakdown (pivot <= tol * max diag: numerically rank deficient)
 // W (l x l, symmetric) -> R upper (W = R^T R), Rinv upper. W is not modified.
