@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+"""bench.py — BASELINE.json's metric on the config it is quoted on.
 
-metric  : genotype GB/s per power-iteration pass (packed bed bytes / pass time)
-workload: configs[1] — PCAone window-based RSVD (winSVD, 64 windows), N=10,000 samples x
-          M=1,000,000 SNPs per GPU, k=20 (l=40), in-memory on B200. One "step" = one epoch of
-          RsvdOpData::computeUSV: computeGandH (decode + X^T Omega + X G for every window and all
-          Omega updates of that epoch) followed by the dense stage (QR(G) x2, B, SVD). Steps walk
-          epochs pi = 0,1,2,... of one winSVD run (7 epochs = a complete default run).
-value   : whole-job packed GB/s with the packed shard resident in HBM (device-timed, max over ranks)
-e2e     : same metric through the C-ABI with the packed matrix in pinned HOST memory: every
-          step streams all blocks host->device (double-buffered) and reads U,S back.
-N > 1   : SNP-sharded, weak scaling (every rank owns its own 1M SNPs of a world*1M-SNP job);
-          H (N x l) is all-reduced over NCCL at every Omega update, the l x l Gram of G once per epoch.
+metric  : time-to-top-k PCs (s) at the 500k x 500k bed; genotype GB/s per power-iteration pass
+workload: configs[2] — UK-Biobank-scale synthetic bed, N = 500,000 samples x M = 500,000 SNPs, k = 40
+          (l = 80), PCAone's window-based RSVD (winSVD, 64 windows), out-of-core block plan (64 blocks =
+          the 64 windows, what `-m` gives at this size), int8x3 tensor-core route.
+step    : ONE complete PCA = RsvdOpData::computeUSV with the reference's defaults (--maxp 20,
+          --tol-rsvd 1e-4, winSVD minimum of log2(64)+1 = 7 epochs): every epoch is computeGandH over the
+          64 blocks (all Omega updates of that epoch) plus the dense stage. ms_per_step = time to PCs.
+value   : packed GB per pass = epochs x (N/4 x M bytes) / time, whole job, inputs resident in HBM (the
+          streamed blocks' re-tiled operands are in the library's HBM tile cache when the timed region
+          starts), device-timed, max over ranks.
+e2e     : the same PCA through the C-ABI from HOST buffers: the packed bed sits in pinned host memory,
+          every step invalidates the tile cache (pcaone_set_host_source), streams all 62.5 GB
+          host->device inside the timed region (double-buffered, overlapped with epoch 0) and reads
+          U, S, V back.
+N > 1   : STRONG scaling of that one PCA, sample-sharded (include/pcaone_b200.h: shard_samples): rank r
+          owns samples [r N/W, (r+1) N/W) of every SNP; per window the exact int64 partial sums of
+          G_b = X_b^T Omega (7.8k x 80) are summed over NCCL, H / Omega stay row-sharded, the
+          orthonormalisation exchanges l x l Gram matrices. (SNP-sharding would exchange the 320 MB
+          N x l partial H at each of the 133 Omega updates: 64x the bytes at this shape.)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2] [--scale f]
 """
 from __future__ import annotations
 
@@ -31,10 +39,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "genotype GB/s per power-iteration pass"
+METRIC = "time-to-top-k PCs (s) at 500k x 500k bed; genotype GB/s per power-iteration pass"
 UNIT = "GB/s"
-N_SAMPLES, M_SNPS, K, BANDS = 10_000, 1_000_000, 20, 64
-CPU_SAMPLE_SNPS = 32_768
+BANDS = 64
+SAMPLE_BLOCKS = 8           # fixed sample grid of the synthetic bed (world sizes 1, 2, 4, 8 cut along it)
+WORKLOADS = {
+    # name: (N samples, M SNPs, k, out-of-core plan, description)
+    "c3": (500_000, 500_000, 40, True, "configs[2]: UK-Biobank-scale bed, winSVD, out-of-core block plan"),
+    "c2": (10_000, 1_000_000, 20, False, "configs[1]: winSVD in-memory"),
+}
+CPU_SAMPLES_BASELINE = 2048   # cpu_baseline leg: this many samples x ALL SNPs, one full PCA
+CPU_SAMPLES_REF_ARM = 512     # --impl reference: K + W full PCAs must end within minutes
 
 
 def _peaks():
@@ -118,57 +133,75 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
-def cpu_reference_pass(packed_host, n_samples, k, steps, warmup, threads):
-    """Time the reference's own CPU computeGandH (oracle/_ref, unmodified PCAone) on a bounded
-    sample of the workload: the first CPU_SAMPLE_SNPS SNPs, all samples, winSVD in-core, -S."""
+
+def workload_dims(args):
+    n, m, k, ooc, desc = WORKLOADS[args.workload]
+    if args.scale != 1.0:
+        n = max(SAMPLE_BLOCKS * 64, int(n * args.scale) // (SAMPLE_BLOCKS * 4) * (SAMPLE_BLOCKS * 4))
+        m = max(BANDS * 64, int(m * args.scale))
+    return n, m, k, ooc, desc
+
+
+def cpu_reference_pca(n_s, m, k, pcas, warm, threads, seed=1):
+    """The reference's own CPU computeUSV (oracle/_ref = unmodified PCAone, winSVD in-core, -S, defaults
+    --maxp 20 --tol-rsvd 1e-4) on a bounded sample: n_s samples of the same population model x ALL m
+    SNPs. Sampling the SAMPLE axis keeps both the per-pass GEMM work and the Omega-update work
+    proportional to n_s, so packed GB/s per pass and (time to PCs) / n_s carry over to the full N."""
+    import torch
     from oracle import ref
     from pcaone_b200 import synth
 
     if not ref.available():
         return None
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    packed = synth.torch_packed(n_s, m, k_pop=k + 4, seed=seed, device=dev, chunk=8192).cpu().numpy()
     tmp = tempfile.mkdtemp(prefix="pcaone_cpu_")
     prefix = os.path.join(tmp, "s")
-    synth.write_bed_from_packed(prefix, packed_host, n_samples)
+    synth.write_bed_from_packed(prefix, packed, n_s)
     ref.lib().ref_set_threads(threads)
     t0 = time.perf_counter()
     r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 2 -S -o {tmp}/o -n {threads}", threads=threads)
     r.new_op()
     load_s = time.perf_counter() - t0
-    times = []
-    for i in range(warmup + steps):
-        t = r.time_gandh(i)  # epochs 0,1,2,... of one winSVD run, like the GPU arm
-        if i >= warmup:
-            times.append(t)
+    times, epochs = [], []
+    for i in range(warm + pcas):
+        t = time.perf_counter()
+        r.compute_usv(20, 1e-4, want=False)
+        dt = time.perf_counter() - t
+        if i >= warm:
+            times.append(dt)
+            epochs.append(r.last_epochs())
     r.close()
-    nbytes = packed_host.shape[0] * packed_host.shape[1]
-    return {"times": times, "load_s": load_s, "bytes": nbytes}
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return {"times": times, "epochs": epochs, "load_s": load_s, "bytes_per_pass": packed.shape[0] * packed.shape[1]}
 
 
 def run_reference_arm(args, rank):
-    """--impl reference: PCAone's CPU implementation of the pass on the box's host cores."""
+    """--impl reference: PCAone's CPU implementation of the same PCA on the box's host cores."""
     if rank != 0:
         return
-    import torch
-    from pcaone_b200 import synth
-
+    n, m, k, ooc, desc = workload_dims(args)
     threads = os.cpu_count() or 1
-    m = CPU_SAMPLE_SNPS if not args.small else 4096
-    n = N_SAMPLES if not args.small else 1000
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    packed = synth.torch_packed(n, m, k_pop=K + 4, seed=1, device=dev, chunk=8192).cpu().numpy()
-    res = cpu_reference_pass(packed, n, K, args.steps, args.warmup, threads)
+    n_s = min(n, CPU_SAMPLES_REF_ARM)
+    res = cpu_reference_pca(n_s, m, k, args.steps, min(args.warmup, 1), threads)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpcaone_ref.so was not built"}))
         return
     tot = sum(res["times"])
-    val = res["bytes"] * len(res["times"]) / tot / 1e9
-    sample = (f"first {m} of {M_SNPS} SNPs x {n} samples (1/{M_SNPS // m} of the workload), winSVD in-core -S, "
-              f"epochs {args.warmup}..{args.warmup + args.steps - 1}; Eigen built-in GEMM, no MKL")
+    passes = sum(res["epochs"])
+    val = res["bytes_per_pass"] * passes / tot / 1e9
+    sample = (f"{n_s} of {n} samples (same population model) x all {m} SNPs, unmodified PCAone winSVD in-core -S, "
+              f"defaults --maxp 20 --tol-rsvd 1e-4: {res['epochs'][0]} epochs per PCA, {tot / len(res['times']):.2f} s per PCA "
+              f"on the sample (x {n / n_s:.0f} for the full sample count); Eigen built-in GEMM, no MKL; "
+              f"{min(args.warmup, 1)} warm-up PCA")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(res["times"]), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[1]: winSVD N=10000 x M=1000000 k=20 (bounded CPU sample)",
-                       "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "time_to_pcs_s": tot / len(res["times"]) * n / n_s,
+            "time_to_pcs_note": f"measured on {n_s} samples, scaled by N / {n_s}",
+            "config": {"workload": f"{desc}, N={n} x M={m}, k={k} (bounded CPU sample)", "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -178,16 +211,18 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=7)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--small", action="store_true", help="debug-sized workload (not a bench number)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="scale N and M (debug; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default="int8x3", choices=["fp64", "int8x2", "int8x3", "int8x4"],
-                    help="GEMM arithmetic: FP64 DMMA, or the exact int8 tensor-core path with 2/3/4 slices")
+    ap.add_argument("--shard", default="auto", choices=["auto", "samples", "snps"])
+    ap.add_argument("--precision", default="int8x3", choices=["int8x2", "int8x3", "int8x4"],
+                    help="slices of the exact int8 tensor-core route")
     args = ap.parse_args()
-    if args.warmup < 3 and not args.small:
+    if args.warmup < 3 and args.scale == 1.0:
         args.warmup = 3
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,30 +240,73 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: pcaone_b200 has no CPU fallback")
     rank, world, local = pdist.init_process_group_from_env("nccl")
     torch.cuda.set_device(local)
-    n, m = (N_SAMPLES, M_SNPS) if not args.small else (1000, 65536)
+    dev = f"cuda:{local}"
+    n, m, K, ooc, desc = workload_dims(args)
+    if SAMPLE_BLOCKS % world != 0:
+        raise SystemExit(f"--gpus must divide {SAMPLE_BLOCKS}")
     peaks, peak_src = _peaks()
-    prec = {"fp64": 0, "int8x2": 2, "int8x3": 3, "int8x4": 4}[args.precision]
+    prec = {"int8x2": 2, "int8x3": 3, "int8x4": 4}[args.precision]
+    l = 2 * K
+    # exchange volume per Omega update decides the split (include/pcaone_b200.h, shard_samples)
+    by_samples = world > 1 and (args.shard == "samples" or (args.shard == "auto" and -(-m // BANDS) < n))
+    by_snps = world > 1 and not by_samples
 
-    # ---- synthetic packed shard, generated in HBM (seeded per rank)
-    packed = synth.torch_packed(n, m, k_pop=K + 4, seed=1 + rank, device=f"cuda:{local}", chunk=16384)
-    bpr = packed.shape[1]
-    shard_bytes = m * bpr
+    # ---- this rank's part of the ONE synthetic bed, generated on the GPU tile by tile into pinned host memory
+    nblk = n // SAMPLE_BLOCKS
+    if by_samples or world == 1:
+        sb0, sb1 = (rank * SAMPLE_BLOCKS // world, (rank + 1) * SAMPLE_BLOCKS // world) if by_samples else (0, SAMPLE_BLOCKS)
+        samp0, n_loc = sb0 * nblk, (sb1 - sb0) * nblk
+        snp_idx = None
+        m_loc = m
+    else:
+        sb0, sb1, samp0, n_loc = 0, SAMPLE_BLOCKS, 0, n
+        snp_idx, w_start, w_stop = pdist.shard_windows(m, BANDS, rank, world)
+        m_loc = len(snp_idx)
+    bpr = synth.bytes_per_snp(n_loc)
+    t_gen = time.perf_counter()
+    host = torch.empty((m_loc, bpr), dtype=torch.uint8, pin_memory=True)
+    chunk = max(64, min(4096, (1 << 28) // max(nblk, 1)))   # ~256M genotypes per tile
+    if snp_idx is None:
+        for s0 in range(0, m, chunk):
+            mm = min(chunk, m - s0)
+            for sb in range(sb0, sb1):
+                tile = synth.torch_packed_tile(n, sb * nblk, nblk, s0, mm, k_pop=K + 4, seed=1, device=dev)
+                c0 = (sb - sb0) * (nblk // 4)
+                host[s0:s0 + mm, c0:c0 + tile.shape[1]].copy_(tile)
+    else:
+        # SNP shard: this rank's SNPs of every window (rows of the same tiles)
+        pos = 0
+        sel = torch.from_numpy(snp_idx).to(dev)
+        for s0 in range(0, m, chunk):
+            mm = min(chunk, m - s0)
+            mine = sel[(sel >= s0) & (sel < s0 + mm)] - s0
+            if mine.numel() == 0:
+                continue
+            for sb in range(SAMPLE_BLOCKS):
+                tile = synth.torch_packed_tile(n, sb * nblk, nblk, s0, mm, k_pop=K + 4, seed=1, device=dev)
+                c0 = sb * (nblk // 4)
+                host[pos:pos + mine.numel(), c0:c0 + tile.shape[1]].copy_(tile[mine])
+            pos += int(mine.numel())
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    gen_s = time.perf_counter() - t_gen
+    bytes_per_pass = m * synth.bytes_per_snp(n)           # the whole job's packed bed
 
-    hook = pdist.make_allreduce_hook() if world > 1 else None
-
-    def make_op(src, ooc):
-        p = halko.Param(k=K, svd=2, bands=BANDS, maxp=20, tol=1e-4, no_shuffle=True, device=local,
-                        memory=1.0 if ooc else 0.0, precision=prec)
-        d = halko.FileBed(p, packed=src, nsamples=n)
-        if ooc:  # 64 streamed blocks == the 64 windows (what -m gives when nblocks < bands)
-            bs = -(-m // BANDS)
-            d.start = np.arange(BANDS, dtype=np.uint64) * np.uint64(bs)
-            d.stop = np.minimum(d.start + np.uint64(bs - 1), np.uint64(m - 1))
-            d.nblocks, d.blocksize, d.bandFactor = BANDS, bs, 1
-        op = halko.FancyRsvdOpData(d, p.k, p.oversamples, rank=rank, world=world, nsnps_total=m * world,
-                                   allreduce=hook)
-        op.setFlags(False, True)
-        return op
+    p = halko.Param(k=K, svd=2, bands=BANDS, maxp=20, tol=1e-4, no_shuffle=True, device=local,
+                    memory=64.0 if ooc else 0.0, precision=prec)
+    d = halko.FileBed(p, packed=host if ooc else host.to(dev), nsamples=n_loc)
+    if by_snps:
+        d.start, d.stop, d.nblocks, d.bandFactor = w_start, w_stop, len(w_start), 1
+    elif ooc:
+        bs = -(-m // BANDS)   # Data.cpp:66-69: nblocks < bands -> blocksize = ceil(M / bands)
+        d.start = np.arange(BANDS, dtype=np.uint64) * np.uint64(bs)
+        d.stop = np.minimum(d.start + np.uint64(bs - 1), np.uint64(m - 1))
+        d.nblocks, d.blocksize, d.bandFactor = BANDS, bs, 1
+    op = halko.FancyRsvdOpData(d, p.k, p.oversamples, rank=rank, world=world, nsnps_total=m,
+                               library_comm=world > 1, shard_samples=by_samples, nsamples_total=n,
+                               sample_offset=samp0)
+    op.setFlags(False, True)
+    stream = torch.cuda.ExternalStream(op.L.pcaone_stream(op.h))
 
     def barrier():
         if world > 1:
@@ -237,32 +315,29 @@ def main():
     def maxr(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg
-    op = make_op(packed, ooc=False)
-    stream = torch.cuda.ExternalStream(op.L.pcaone_stream(op.h))
+    import ctypes as C
+    ep = C.c_int(0)
+    df = C.c_double(0)
 
-    def step(o, i):
-        o._chk(o.L.pcaone_compute_gandh(o.h, i))
-        o._chk(o.L.pcaone_small_stage(o.h))
+    def pca():
+        op._chk(op.L.pcaone_compute_usv(op.h, p.maxp, C.c_double(p.tol), C.byref(df), C.byref(ep)))
+        return ep.value
 
-    # NVML is initialised and the sampler thread started BEFORE the warm-up (nvmlInit costs ~30 ms
-    # of driver lock, which must not land in the timed region); its samples are cleared below.
+    def new_data():
+        """the host hands the bed over again: the library forgets its cached tiles and allele frequencies"""
+        if ooc:
+            op._chk(op.L.pcaone_set_host_source(op.h, halko._vp(host), m_loc))
+
+    # ---- value leg: operands resident in HBM (tile cache warm)
     sampler = ClockSampler(local)
     sampler.start()
-    # The library's per-scope CUDA events (the kernel breakdown behind `roofline`) cost ~7 % of this
-    # launch-bound region when they are on (48.6 vs 52.2 ms for the 7 epochs, tools/step_times.py), so
-    # the timed region runs WITHOUT them and an instrumented replica of the same K steps follows it.
     op.enable_timing(False)
-    for i in range(args.warmup):
-        step(op, i)
-    # one more untimed replica of the timed loop so that every (pi -> schedule) code path, cuda
-    # function attribute and workspace of the timed steps has been touched once
-    for i in range(args.steps):
-        step(op, i)
+    for _ in range(args.warmup):
+        epochs = pca()
     op.sync()
     op.timers(reset=True)
     sampler.samples.clear()
@@ -270,160 +345,158 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
-        step(op, i)
+    passes = 0
+    for _ in range(args.steps):
+        passes += pca()
     e1.record(stream)
     op.sync()
     torch.cuda.synchronize()
     barrier()
     dev_ms = maxr(e0.elapsed_time(e1))
     clocks = sampler.stop()
-    gpu_launches = int(op.timers(reset=True).kernel_launches)
-    # instrumented replica of the timed steps: per-kernel CUDA-event times for the roofline object
+    tm0 = op.timers(reset=True)
+    gpu_launches = int(tm0.kernel_launches)
+    value = bytes_per_pass * passes / (dev_ms * 1e-3) / 1e9
+    op._fetch_usv()
+    eig = op.S ** 2 / m
+    u_orth = float(np.abs(op.U.T @ op.U - (np.eye(K) if (world == 1 or not by_samples) else 0)).max()) if world == 1 else None
+
+    # ---- instrumented replica (per-kernel CUDA events) for the roofline object
     op.enable_timing(True)
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     i0.record(stream)
-    for i in range(args.steps):
-        step(op, i)
+    ep_i = pca()
     i1.record(stream)
     op.sync()
     torch.cuda.synchronize()
     instr_ms = i0.elapsed_time(i1)
     tm = op.timers(reset=True)
-    op.enable_timing(False)
-    value = world * shard_bytes * args.steps / (dev_ms * 1e-3) / 1e9
-    l = op.size()
-    flops_per_gemm_total = 2.0 * n * m * l  # per pass, each of the two GEMMs
-    g_ms, h_ms = tm.gemm_g_ms / args.steps, tm.gemm_h_ms / args.steps
+    flops_gemm_rank = 2.0 * n_loc * m_loc * l * ep_i      # one of the two GEMMs, all epochs of the PCA, this rank
+    tg, th = tm.tc_g_ms, tm.tc_h_ms
+    dom, dom_ms = ("k_tc_gemm (H pass)", th) if th >= tg else ("k_tc_gemm (G pass)", tg)
     peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    if prec == 0:
-        # dominant kernel: the fused decode->DMMA GEMM pair; report the slower of the two
-        dom, dom_ms, dom_launches = (("k_gemm_h", h_ms, tm.gemm_h_launches) if h_ms >= g_ms else
-                                     ("k_gemm_g", g_ms, tm.gemm_g_launches))
-        note = ("FP64 DMMA path: algorithmic flops 2*N*M*l per GEMM per pass; peak is the measured bf16 "
-                "tensor figure because MEASURED_PEAKS has no FP64 entry (B200 FP64 tensor nominal ~37 TF)")
-    else:
-        # dominant kernel: k_tc_gemm (tcgen05 kind::i8, both passes use the same kernel); its
-        # own CUDA-event time (tc_g_ms / tc_h_ms), without the slice / finish kernels around it
-        tg, th = tm.tc_g_ms / args.steps, tm.tc_h_ms / args.steps
-        dom, dom_ms, dom_launches = (("k_tc_gemm (H pass)", th, tm.gemm_h_launches) if th >= tg else
-                                     ("k_tc_gemm (G pass)", tg, tm.gemm_g_launches))
-        note = (f"int8 Ozaki path, {prec} slices: algorithmic flops 2*N*M*l per GEMM per pass (the tensor cores "
-                f"execute {prec}x that as exact int8 MACs, so frac <= {1.0 / prec * 2:.2f} of the bf16 peak at the "
-                "int8 rate of 2x bf16); peak = measured bf16 sustained")
-    achieved_tf = flops_per_gemm_total / (dom_ms * 1e-3) / 1e12
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (per pass =
-    # the two full-size launches of a late epoch), to hold against the algorithmic packed bytes
-    traffic, traffic_note = None, None
+    achieved_tf = flops_gemm_rank / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else None
+    int8_peak = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tc_gemm_traffic.json")))
-        leg = tj["h_pass" if "H pass" in dom else "g_pass"]
-        if prec == 3:
-            traffic = tj["launches_per_pass_full_size"] * (leg["dram_read_bytes"] + leg["dram_write_bytes"])
-            traffic_note = (f"bytes per pass (2 full-size launches), ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                            f"{tj['source']}; algorithmic: {shard_bytes} packed bytes read + {n if 'H pass' in dom else m}"
-                            f" x {l} int64 accumulators written")
+        int8_peak = json.load(open(os.path.join(ROOT, "profiles", "r02_int8_peak.json")))
     except Exception:
         pass
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_gemm_traffic.json")))
+        leg = tj["h_pass" if "H pass" in dom else "g_pass"]
+        traffic = leg["dram_read_bytes"] + leg["dram_write_bytes"]
+        traffic_note = f"bytes per launch of one block ({tj['what']}), ncu dram__bytes_read.sum + dram__bytes_write.sum, {tj['source']}"
+    except Exception:
+        pass
+    nl = int(tm.gemm_h_launches if "H pass" in dom else tm.gemm_g_launches)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
-                "peak_source": f"{peak_src} bf16 sustained",
-                "note": note,
-                "gemm_g_ms_per_pass": g_ms, "gemm_h_ms_per_pass": h_ms, "orth_ms_per_pass": tm.orth_ms / args.steps,
-                "small_stage_ms_per_pass": tm.small_ms / args.steps,
-                "tc_g_ms_per_pass": tm.tc_g_ms / args.steps, "tc_h_ms_per_pass": tm.tc_h_ms / args.steps,
+                "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json has no int8 entry)",
+                "note": (f"int8 Ozaki route, {prec} slices: achieved = algorithmic flops 2*N*M*l per GEMM pass x {ep_i} epochs / "
+                         f"the kernel's CUDA-event time over those {nl} launches ({dom_ms / max(nl, 1):.3f} ms per launch of one "
+                         f"{-(-m // BANDS)}-SNP block); the tensor cores execute {prec}x that as exact int8 MACs"),
+                "launches": nl, "ms_per_launch": dom_ms / max(nl, 1),
+                "algorithmic_flops_per_launch": flops_gemm_rank / max(nl, 1),
+                "tc_g_ms_per_pca": tg, "tc_h_ms_per_pca": th, "gemm_g_ms_per_pca": tm.gemm_g_ms, "gemm_h_ms_per_pca": tm.gemm_h_ms,
+                "orth_ms_per_pca": tm.orth_ms, "small_stage_ms_per_pca": tm.small_ms, "allreduce_ms_per_pca": tm.allreduce_ms,
+                "omega_updates_per_pca": int(tm.omega_updates), "epochs": ep_i, "cache_hits": int(tm.cache_hits),
                 "tc_ranges": int(tm.tc_ranges), "fp64_ranges": int(tm.fp64_ranges),
-                "launches_per_pass": dom_launches / args.steps,
-                "hbm_algorithmic_gbs": shard_bytes / (dom_ms * 1e-3) / 1e9}
-    roofline["timing_note"] = (f"kernel times: CUDA events of an instrumented replica of the {args.steps} timed steps "
-                               f"({instr_ms:.2f} ms with the per-scope events on, {dev_ms:.2f} ms timed without them)")
-    # the same kernel at its full-size launches only: one more epoch with pi >= log2(bands) (one Omega
-    # update per pass, every window merged into two half-shard launches), outside the timed region
-    if prec != 0 and args.steps >= 1:
-        op.enable_timing(True)
-        pi_late = max(args.steps, 6)
-        step(op, pi_late)
-        op.sync()
-        op.timers(reset=True)
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        step(op, pi_late + 1)
-        l1.record(stream)
-        op.sync()
-        torch.cuda.synchronize()
-        tl = op.timers(reset=True)
-        op.enable_timing(False)
-        late_ms = l0.elapsed_time(l1)
-        tcl = max(tl.tc_g_ms, tl.tc_h_ms)
-        roofline["late_pass"] = {
-            "what": "one epoch with pi >= 6 (plain power iteration, 2 half-shard launches per GEMM), untimed leg",
-            "ms": late_ms, "gbs": shard_bytes / (late_ms * 1e-3) / 1e9, "tc_g_ms": tl.tc_g_ms, "tc_h_ms": tl.tc_h_ms,
-            "gemm_g_ms": tl.gemm_g_ms, "gemm_h_ms": tl.gemm_h_ms, "orth_ms": tl.orth_ms, "small_stage_ms": tl.small_ms,
-            "achieved": flops_per_gemm_total / (tcl * 1e-3) / 1e12 if tcl > 0 else None,
-            "frac": flops_per_gemm_total / (tcl * 1e-3) / 1e12 / peak_tf if tcl > 0 else None}
-    op.close()
+                "hbm_algorithmic_gbs": bytes_per_pass / world * ep_i / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None,
+                "timing_note": f"instrumented replica of one PCA: {instr_ms:.1f} ms with the per-scope events on"}
+    if int8_peak:
+        ip = int8_peak.get("int8_dense_tops")
+        roofline["int8_peak_tops"] = ip
+        roofline["frac_of_int8_over_slices"] = achieved_tf / (ip / 2.0 / prec) if (achieved_tf and ip) else None
+        roofline["int8_peak_source"] = int8_peak.get("source")
+    # one late pass on its own (pi >= 6: plain power iteration, one Omega update)
+    op.timers(reset=True)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(stream)
+    op._chk(op.L.pcaone_compute_gandh(op.h, 7))
+    op._chk(op.L.pcaone_small_stage(op.h))
+    l1.record(stream)
+    op.sync()
+    torch.cuda.synchronize()
+    tl = op.timers(reset=True)
+    late_ms = maxr(l0.elapsed_time(l1))
+    op.enable_timing(False)
+    tcl = max(tl.tc_g_ms, tl.tc_h_ms)
+    fl_late = 2.0 * n_loc * m_loc * l
+    roofline["late_pass"] = {
+        "what": "one epoch with pi >= 6 (one Omega update) + dense stage, untimed leg", "ms": late_ms,
+        "gbs": bytes_per_pass / (late_ms * 1e-3) / 1e9, "tc_g_ms": tl.tc_g_ms, "tc_h_ms": tl.tc_h_ms,
+        "gemm_g_ms": tl.gemm_g_ms, "gemm_h_ms": tl.gemm_h_ms, "orth_ms": tl.orth_ms, "small_stage_ms": tl.small_ms,
+        "allreduce_ms": tl.allreduce_ms,
+        "achieved": fl_late / (tcl * 1e-3) / 1e12 if tcl > 0 else None,
+        "frac": fl_late / (tcl * 1e-3) / 1e12 / peak_tf if tcl > 0 else None}
 
-    # ---- end-to-end leg: packed matrix in pinned host memory, streamed every pass
+    # ---- end-to-end leg: host buffers -> PCs, every step streams the bed again
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((m, bpr), dtype=torch.uint8, pin_memory=True)
-        host.copy_(packed)
-        torch.cuda.synchronize()
-        del packed
-        torch.cuda.empty_cache()
-        op2 = make_op(host, ooc=True)
-        def step2(i):
-            step(op2, i)
-            # result of the step back on the host: sigma (l) and the current PCs are device state;
-            # read the N x l H (the pass output the reference hands to computeUSV)
-            op2.getH(Hh)
-
-        Hh = np.zeros((n, l), order="F")
-        for i in range(min(args.warmup, 3)):
-            step2(i)
-        op2.sync()
-        op2.timers(reset=True)
+        e2e_steps = args.steps
+        for _ in range(1):
+            new_data()
+            if not ooc:
+                op._chk(op.L.pcaone_upload_bed(op.h, halko._vp(host), m_loc, 0))
+                op._chk(op.L.pcaone_allele_freq(op.h))
+            pca()
+            op._fetch_usv()
+        op.sync()
+        op.timers(reset=True)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            step2(i)
-        op2.sync()
+        for _ in range(e2e_steps):
+            new_data()
+            if not ooc:
+                op._chk(op.L.pcaone_upload_bed(op.h, halko._vp(host), m_loc, 0))
+                op._chk(op.L.pcaone_allele_freq(op.h))
+            pe = pca()
+            op._fetch_usv()
+        op.sync()
         barrier()
         e2e_s = maxr(time.perf_counter() - t0)
-        tm2 = op2.timers(reset=True)
-        e2e = {"value": world * shard_bytes * args.steps / e2e_s / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(tm2.h2d_bytes // args.steps), "d2h_bytes_per_step": int(tm2.d2h_bytes // args.steps),
-               "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "host wall clock between stream syncs, max over ranks"}
-        op2.close()
-        cpu_src = host.numpy()[: (CPU_SAMPLE_SNPS if not args.small else 4096)]
-    else:
-        cpu_src = packed[: (CPU_SAMPLE_SNPS if not args.small else 4096)].cpu().numpy()
+        tm2 = op.timers(reset=True)
+        h2d = torch.tensor([float(tm2.h2d_bytes)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d)
+        e2e = {"value": bytes_per_pass * pe * e2e_steps / e2e_s / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d.item() // e2e_steps), "d2h_bytes_per_step": int(tm2.d2h_bytes // e2e_steps),
+               "ms_per_step": 1e3 * e2e_s / e2e_steps, "time_to_pcs_s": e2e_s / e2e_steps, "steps": e2e_steps,
+               "cache_hits_per_step": int(tm2.cache_hits // e2e_steps),
+               "timing": "host wall clock between stream syncs, max over ranks; pinned host bed -> U, S, V on the host"}
+    op.close()
+    del host
 
-    # ---- CPU baseline (rank 0, N=1 only): the compiled reference on a bounded sample
+    # ---- CPU baseline (rank 0, N = 1 only): the compiled reference on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        res = cpu_reference_pass(np.ascontiguousarray(cpu_src), n, K, 2, 1, threads)
+        n_s = min(n, CPU_SAMPLES_BASELINE)
+        res = cpu_reference_pca(n_s, m, K, 1, 0, threads)
         if res is not None:
             tot = sum(res["times"])
-            cpu = {"value": res["bytes"] * len(res["times"]) / tot / 1e9, "unit": UNIT, "cores": threads,
-                   "kind": "reference",
-                   "sample": (f"first {cpu_src.shape[0]} of {m} SNPs x {n} samples, winSVD in-core -S, epochs 1-2 "
-                              f"({tot:.1f} s of CPU passes + {res['load_s']:.1f} s read/decode); Eigen GEMM, no MKL")}
+            cpu = {"value": res["bytes_per_pass"] * sum(res["epochs"]) / tot / 1e9, "unit": UNIT, "cores": threads,
+                   "kind": "reference", "time_to_pcs_s_extrapolated": tot * n / n_s,
+                   "sample": (f"{n_s} of {n} samples (same population model) x all {m} SNPs, unmodified PCAone winSVD "
+                              f"in-core -S, one full PCA: {res['epochs'][0]} epochs in {tot:.1f} s (+ {res['load_s']:.1f} s "
+                              f"read/decode); per-pass work and Omega-update work both scale with the sample count, so "
+                              f"GB/s carries over and time to PCs scales by N / {n_s}; Eigen GEMM, no MKL")}
         else:
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": "oracle/_ref/libpcaone_ref.so missing"}
 
     if rank == 0:
+        shard = "one GPU" if world == 1 else (f"sample-shard x{world}" if by_samples else f"snp-shard x{world}")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if prec == 0 else f"int8x{prec} (exact, FP64 epilogue)",
-                "data": "synthetic",
-                "config": {"workload": f"configs[1]: winSVD in-memory, N={n} x M={m} SNPs per GPU, k={K}, l={l}, "
-                                       f"{BANDS} windows, no-shuffle; step = one computeUSV epoch (pi = step index)",
-                           "l2": "inputs (2.5 GB packed per GPU) are larger than L2; no flush needed",
-                           "warmup_note": f"{args.warmup} warm-up steps + one untimed replica of the {args.steps} timed steps",
-                           "parallelism": f"snp-shard x{world}"},
+                "scaling": "strong", "vs_baseline": None, "dtype": f"int8x{prec} (exact integer products, FP64 epilogue)",
+                "data": "synthetic", "time_to_pcs_s": dev_ms * 1e-3 / args.steps, "epochs_per_pca": passes / args.steps,
+                "config": {"workload": f"{desc}: N={n} x M={m}, k={K}, l={l}, {BANDS} windows, no-shuffle; step = one complete "
+                                       f"PCA (computeUSV, --maxp 20 --tol-rsvd 1e-4)",
+                           "l2": f"inputs ({2 * bytes_per_pass / world / 1e9:.1f} GB of tiled operands per GPU) are larger than L2; no flush needed",
+                           "parallelism": shard, "synthetic_bed_s": gen_s,
+                           "top_eigenvalues": eig[:3].tolist(), "U_orthonormality_err": u_orth},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
                 "clocks": clocks}
         print(json.dumps(line))

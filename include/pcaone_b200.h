@@ -77,6 +77,11 @@ typedef struct pcaone_config {
  * work on it. The Python host installs torch.distributed.all_reduce (NCCL) here. */
 typedef int (*pcaone_allreduce_fn)(void* user, void* buf, uint64_t count, void* stream);
 
+/* Typed variant: `kind` says what to reduce — the sample-sharded mode also sums exact int64 partial
+ * products and uint32 genotype counts and takes maxima of IEEE bit patterns. */
+enum { PCAONE_RED_F64_SUM = 0, PCAONE_RED_I64_SUM = 1, PCAONE_RED_U64_MAX = 2, PCAONE_RED_U32_SUM = 3 };
+typedef int (*pcaone_allreduce2_fn)(void* user, void* buf, uint64_t count, int kind, void* stream);
+
 /* Block source for out-of-core passes: fill dst (pinned) with the packed rows of SNPs
  * start..stop inclusive (bpr bytes each). Replaces the ifstream.read of
  * FileBed::read_block_initial (FilePlink.cpp:125-136). */
@@ -95,6 +100,7 @@ int  pcaone_set_allreduce(pcaone_ctx* ctx, pcaone_allreduce_fn fn, void* user);
  * (one process per GPU), each calls pcaone_comm_init. A host that drives several GPUs from one
  * process creates the communicators itself (ncclCommInitAll) and attaches them. With a
  * communicator attached the allreduce hook above is not used. */
+int  pcaone_set_allreduce2(pcaone_ctx* ctx, pcaone_allreduce2_fn fn, void* user);
 int  pcaone_comm_unique_id(uint8_t* out128);
 int  pcaone_comm_init(pcaone_ctx* ctx, const uint8_t* id128, int rank, int world);
 int  pcaone_comm_attach(pcaone_ctx* ctx, void* nccl_comm);

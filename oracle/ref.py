@@ -139,10 +139,16 @@ class Ref:
             self._chk(1)
         return t
 
-    def compute_usv(self, maxp, tol):
+    def compute_usv(self, maxp, tol, want=True):
+        if not want:  # timing runs: leave U, S, V inside the reference object
+            self._chk(lib().ref_compute_usv(self.h, int(maxp), C.c_double(tol), None, None, None))
+            return None
         U, S, V = _f((self.N, self.k)), np.zeros(self.k), _f((self.M, self.k))
         self._chk(lib().ref_compute_usv(self.h, int(maxp), C.c_double(tol), _p(U), _p(S), _p(V)))
         return U, S, V
+
+    def last_epochs(self):
+        return int(lib().ref_last_epochs(self.h))
 
     def compute_u(self, G, H):
         G = np.asfortranarray(G, dtype=np.float64)

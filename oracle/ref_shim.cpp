@@ -53,6 +53,22 @@ struct RefCtx {
 
 thread_local std::string g_err;
 
+// counts the computeGandH calls (= epochs) of the last computeUSV; everything else is the reference's
+template <class Base>
+struct Counting : Base {
+  using Base::Base;
+  int calls = 0;
+  void computeGandH(Mat2D& G, Mat2D& H, int pi) override {
+    ++calls;
+    Base::computeGandH(G, H, pi);
+  }
+};
+int* g_calls(RsvdOpData* op) {
+  if (auto* f = dynamic_cast<Counting<FancyRsvdOpData>*>(op)) return &f->calls;
+  if (auto* n = dynamic_cast<Counting<NormalRsvdOpData>*>(op)) return &n->calls;
+  return nullptr;
+}
+
 std::vector<std::string> split_ws(const char* s) {
   std::vector<std::string> out;
   std::istringstream is(s);
@@ -138,9 +154,9 @@ int ref_new_op(void* h) {
     const Param& p = *c->params;
     delete c->op;
     if (p.svd_t == SvdType::PCAoneAlg2)
-      c->op = new FancyRsvdOpData(c->data, p.k, p.oversamples);
+      c->op = new Counting<FancyRsvdOpData>(c->data, p.k, p.oversamples);
     else
-      c->op = new NormalRsvdOpData(c->data, p.k, p.oversamples);
+      c->op = new Counting<NormalRsvdOpData>(c->data, p.k, p.oversamples);
     if (p.genetic)
       c->op->setFlags(false, p.ld ? false : true);
     else
@@ -229,10 +245,17 @@ double ref_time_gandh(void* h, int pi) {
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// epochs (computeGandH calls) of the last ref_compute_usv
+int ref_last_epochs(void* h) {
+  int* n = g_calls(((RefCtx*)h)->op);
+  return n ? *n : -1;
+}
+
 // RsvdOpData::computeUSV (Halko.cpp:46-97); returns U (N x k), S (k), V (M x k).
 int ref_compute_usv(void* h, int maxp, double tol, double* U, double* S, double* V) {
   RefCtx* c = (RefCtx*)h;
   return guarded([&] {
+    if (int* n = g_calls(c->op)) *n = 0;
     c->op->computeUSV(maxp, tol);
     if (U) std::memcpy(U, c->op->U.data(), sizeof(double) * c->op->U.size());
     if (S) std::memcpy(S, c->op->S.data(), sizeof(double) * c->op->S.size());

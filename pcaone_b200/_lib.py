@@ -37,6 +37,7 @@ class Timers(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+ALLREDUCE2_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p)
 READ_BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p)
 
 # every symbol include/pcaone_b200.h declares (tests check the library exports all of them)
@@ -51,7 +52,7 @@ SYMBOLS = [
     "pcaone_get_timers", "pcaone_enable_timing", "pcaone_alloc_pinned", "pcaone_free_pinned", "pcaone_device_count",
     "pcaone_upload_dense", "pcaone_dense_rsvd", "pcaone_upload_dosage", "pcaone_perform_op", "pcaone_ld_prune", "pcaone_xt_times", "pcaone_x_times",
     "pcaone_upload_gl", "pcaone_gl_em_maf",
-    "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2",
+    "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
 ]
 
 _lib = None
@@ -94,7 +95,7 @@ def load():
         "pcaone_upload_gl": [vp, vp, u64, i32], "pcaone_gl_em_maf": [vp, u32, dbl, vp],
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
         "pcaone_comm_unique_id": [vp], "pcaone_comm_init": [vp, vp, i32, i32], "pcaone_comm_attach": [vp, vp],
-        "pcaone_set_host_source2": [vp, vp, u64, u64],
+        "pcaone_set_host_source2": [vp, vp, u64, u64], "pcaone_set_allreduce2": [vp, ALLREDUCE2_FN, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.pcaone_alloc_pinned.restype = C.c_int

@@ -8,8 +8,9 @@
 //   pcaone_comm_attach                         one process, several GPUs: the host made the
 //                                             communicators itself (ncclCommInitAll)
 // libnccl is resolved at run time (dlopen), so the library loads on a box without it and a
-// Python host that already imported torch shares torch's copy. The older host hook
-// (pcaone_set_allreduce, double sums only) is still honoured when no communicator is attached.
+// Python host that already imported torch shares torch's copy. Without a communicator the host
+// hooks are used: pcaone_set_allreduce2 (typed; any transport, e.g. gloo between two ranks that
+// time-share one GPU in the tests) or the older pcaone_set_allreduce (double sums only).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -79,6 +80,12 @@ void reduce(pcaone_ctx* c, void* buf, uint64_t count, ncclDataType_t dt, ncclRed
     nccl_check(api().AllReduce(buf, buf, (size_t)count, dt, op, c->comm->comm, c->stream), "ncclAllReduce");
     return;
   }
+  if (c->allreduce2) {
+    const int kind = dt == ncclFloat64 ? PCAONE_RED_F64_SUM : dt == ncclInt64 ? PCAONE_RED_I64_SUM
+                     : dt == ncclUint64 ? PCAONE_RED_U64_MAX : PCAONE_RED_U32_SUM;
+    if (c->allreduce2(c->allreduce2_user, buf, count, kind, c->stream)) throw std::runtime_error("allreduce hook failed");
+    return;
+  }
   if (dt == ncclFloat64 && op == ncclSum && c->allreduce) {
     if (c->allreduce(c->allreduce_user, buf, count, c->stream)) throw std::runtime_error("allreduce hook failed");
     return;
@@ -139,6 +146,13 @@ int pcaone_comm_init(pcaone_ctx* c, const uint8_t* id128, int rank, int world) {
     c->comm = new pcaone_comm();
     nccl_check(api().CommInitRank(&c->comm->comm, world, id, rank), "ncclCommInitRank");
     c->comm->owned = true;
+  });
+}
+
+int pcaone_set_allreduce2(pcaone_ctx* c, pcaone_allreduce2_fn fn, void* user) {
+  CTX_GUARD(c, {
+    c->allreduce2 = fn;
+    c->allreduce2_user = user;
   });
 }
 

@@ -72,6 +72,7 @@ struct pcaone_ctx {
   uint8_t* d_blk[2] = {nullptr, nullptr};
   uint8_t* h_pin[2] = {nullptr, nullptr};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  int64_t staged_blk[2] = {-1, -1};  // block of the plan whose copy is enqueued in d_blk[i] (-1: none)
   bool af_done = false;
 
   // per-SNP
@@ -142,6 +143,8 @@ struct pcaone_ctx {
   // sharded jobs
   pcaone_allreduce_fn allreduce = nullptr;             // host hook (double sums only)
   void* allreduce_user = nullptr;
+  pcaone_allreduce2_fn allreduce2 = nullptr;           // typed host hook (any transport)
+  void* allreduce2_user = nullptr;
   pcaone_comm* comm = nullptr;                         // in-library NCCL communicator (comm.cu)
   bool shard_samples = false;                          // rows of X^T (samples) sharded instead of SNPs
   uint64_t N_total = 0;                                // samples of the whole job (== N unless shard_samples)
@@ -289,7 +292,7 @@ void xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, doubl
 void x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out);
 void dense_onepass(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder);
 void alloc_stream_buffers(pcaone_ctx* c);
-const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf);
+const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf, bool wait = true);
 void block_af_if_needed(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nrows);
 void allele_freq_rows(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nrows);
 void snp_sqnorm(pcaone_ctx* c, double* out);

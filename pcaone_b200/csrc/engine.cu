@@ -130,28 +130,49 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
   range_gemms_tc(c, PG, PH, 0, nrows, snp0, Hacc, accumulate, has_miss);
 }
 
-// One block of an out-of-core plan: stream it from the host (double-buffered, overlapped with the
-// previous block's products) unless its tiles are already in the HBM cache.
+// does block b of the plan have to come from the host on this pass?
+bool ooc_needs_stage(pcaone_ctx* c, uint32_t b) {
+  if (c->blk_stop[b] + 1 == c->blk_start[b]) return false;  // empty placeholder
+  return !(pass_uses_tc(c) && c->af_done && c->cache_mode == 1 && c->cache_pg_off[b] != SIZE_MAX && c->cache_filled[b]);
+}
+
+// enqueue the host->device copy of block b into its buffer (b & 1) unless it is already there
+const uint8_t* ooc_stage(pcaone_ctx* c, uint32_t b) {
+  const int buf = (int)(b & 1);
+  if (c->staged_blk[buf] != (int64_t)b) {
+    stage_block(c, b, buf, false);
+    c->staged_blk[buf] = b;
+  }
+  return c->d_blk[buf];
+}
+
+// One block of an out-of-core plan: streamed from the host (double-buffered: the copy of the NEXT
+// block is enqueued before this block's products, which may synchronise with the host) unless its
+// tiles are already in the HBM cache.
 void ooc_block(pcaone_ctx* c, uint32_t b, double* Hacc) {
-  const uint64_t s0 = c->blk_start[b], nrows = c->blk_stop[b] - s0 + 1;
-  if (pass_uses_tc(c)) {
-    if (c->cache_mode < 0) {
-      // the working set first (accumulators, operand images, stream buffers), the cache takes what is left
-      alloc_stream_buffers(c);
-      tc_alloc(c, c->max_block, false);
-      cache_plan(c);
-    }
-    if (c->af_done && c->cache_mode == 1 && c->cache_pg_off[b] != SIZE_MAX && c->cache_filled[b]) {
-      range_gemms(c, nullptr, (uint32_t)nrows, s0, Hacc, true, 0, b);
-      c->tm.cache_hits++;
-      return;
-    }
+  const uint64_t s0 = c->blk_start[b], nrows = c->blk_stop[b] + 1 - s0;
+  if (nrows == 0) return;
+  if (pass_uses_tc(c) && c->cache_mode < 0) {
+    // the working set first (accumulators, operand images, stream buffers), the cache takes what is left
+    alloc_stream_buffers(c);
+    tc_alloc(c, c->max_block, false);
+    cache_plan(c);
+  }
+  const uint32_t nb = (uint32_t)c->blk_start.size();
+  const bool need = ooc_needs_stage(c, b);
+  const uint8_t* P = need ? ooc_stage(c, b) : nullptr;
+  if (b + 1 < nb && ooc_needs_stage(c, b + 1)) ooc_stage(c, b + 1);
+  if (!need) {
+    range_gemms(c, nullptr, (uint32_t)nrows, s0, Hacc, true, 0, b);
+    c->tm.cache_hits++;
+    return;
   }
   const int buf = (int)(b & 1);
-  const uint8_t* P = stage_block(c, b, buf);
+  PCA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
   block_af_if_needed(c, P, s0, nrows);
   range_gemms(c, P, (uint32_t)nrows, s0, Hacc, true, buf, b);
   PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
+  c->staged_blk[buf] = -1;
 }
 
 // ---------------------------------------------------------------- the passes
@@ -559,6 +580,7 @@ void set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint
   c->band_factor = band_factor ? band_factor : 1;
   uint64_t mb = 0;
   for (uint32_t i = 0; i < nblocks; ++i) {
+    if (start[i] == stop[i] + 1) continue;  // empty placeholder window (a sharded job keeps every rank on one schedule)
     if (stop[i] >= c->M || start[i] > stop[i]) throw std::runtime_error("set_blocks: block out of range");
     mb = std::max(mb, stop[i] - start[i] + 1);
   }

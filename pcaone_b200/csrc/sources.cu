@@ -23,8 +23,9 @@ void alloc_stream_buffers(pcaone_ctx* c) {
   }
 }
 
-// enqueue the H2D of block b into buffer `buf`; returns the device pointer (pitch layout)
-const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf) {
+// enqueue the H2D of block b into buffer `buf`; returns the device pointer (pitch layout). `wait`: the
+// compute stream waits for the copy right away (else the caller does, when it consumes the block)
+const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf, bool wait) {
   const uint64_t s = c->blk_start[b], e = c->blk_stop[b];
   const uint64_t nrows = e - s + 1;
   const size_t bytes = nrows * c->bpr;
@@ -57,7 +58,7 @@ const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf) {
     c->tm.kernel_launches++;
   }
   PCA_CUDA(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
-  PCA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
+  if (wait) PCA_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
   return c->d_blk[buf];
 }
 
@@ -114,7 +115,10 @@ void cache_release(pcaone_ctx* c) {
   c->cache_mode = -1;
 }
 
-void cache_invalidate(pcaone_ctx* c) { std::fill(c->cache_filled.begin(), c->cache_filled.end(), 0); }
+void cache_invalidate(pcaone_ctx* c) {
+  std::fill(c->cache_filled.begin(), c->cache_filled.end(), 0);
+  c->staged_blk[0] = c->staged_blk[1] = -1;
+}
 
 void cache_plan(pcaone_ctx* c) {
   if (c->cache_mode >= 0) return;
@@ -309,6 +313,7 @@ int pcaone_allele_freq(pcaone_ctx* c) {
       for (uint32_t b = 0; b < c->blk_start.size(); ++b) {
         const int buf = b & 1;
         const uint8_t* P = stage_block(c, b, buf);
+        c->staged_blk[buf] = -1;
         block_af_if_needed(c, P, c->blk_start[b], c->blk_stop[b] - c->blk_start[b] + 1);
         PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
       }
@@ -411,6 +416,7 @@ int pcaone_decode_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int standa
         c->blk_stop = {s0 + nb - 1};
         try {
           P = stage_block(c, 0, 0);
+          c->staged_blk[0] = -1;
         } catch (...) {
           c->blk_start = sv;
           c->blk_stop = ev;

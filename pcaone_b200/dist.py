@@ -30,13 +30,18 @@ def shard_windows(n_snps_total: int, bands: int, rank: int, world: int):
         s = b * bs
         e = min((b + 1) * bs, n_snps_total)
         if s >= e:
+            # empty trailing window (M < bands * blocksize): kept as a placeholder so that every rank
+            # walks the same `bands`-step schedule as one GPU does (start > stop = empty)
+            start.append(pos + 1 if pos else 1)
+            stop.append(pos if pos else 0)
             continue
+        if e - s < world:
+            raise RuntimeError(f"window {b} has {e - s} SNPs, fewer than the {world} ranks")
         ls, le = shard_range(e - s, rank, world)
-        if le > ls:
-            idx.append(np.arange(s + ls, s + le, dtype=np.int64))
-            start.append(pos)
-            pos += le - ls
-            stop.append(pos - 1)
+        idx.append(np.arange(s + ls, s + le, dtype=np.int64))
+        start.append(pos)
+        pos += le - ls
+        stop.append(pos - 1)
     return (np.concatenate(idx) if idx else np.zeros(0, np.int64),
             np.array(start, dtype=np.uint64), np.array(stop, dtype=np.uint64))
 
@@ -81,6 +86,76 @@ def make_allreduce_hook(group=None, device_buffers=True):
             return 1
 
     return hook
+
+
+def make_allreduce2_hook(group=None):
+    """Typed collective hook (pcaone_allreduce2_fn) over ANY torch.distributed backend: the buffer is
+    device memory; with a CPU backend (gloo) it is staged through the host. Slow, but it lets two
+    ranks that time-share ONE GPU run the sharded schedules (NCCL refuses two ranks per device), which
+    is how the sharded paths are tested on a one-GPU box."""
+    import torch
+    import torch.distributed as dist
+
+    kinds = {0: ("<f8", torch.float64, dist.ReduceOp.SUM), 1: ("<i8", torch.int64, dist.ReduceOp.SUM),
+             2: ("<i8", torch.int64, dist.ReduceOp.MAX),   # bit patterns of non-negative doubles: order-preserving as int64
+             3: ("<i4", torch.int32, dist.ReduceOp.SUM)}   # genotype counts < 2^31
+
+    class Buf:
+        def __init__(self, ptr, count, typestr):
+            self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                             "version": 3, "strides": None}
+
+    def hook(user, buf, count, kind, stream):
+        try:
+            typestr, _, op = kinds[int(kind)]
+            t = torch.as_tensor(Buf(buf, count, typestr), device="cuda")
+            ext = torch.cuda.ExternalStream(int(stream))
+            if dist.get_backend(group) == "nccl":
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(t, op=op, group=group)
+            else:
+                ext.synchronize()
+                h = t.cpu()
+                dist.all_reduce(h, op=op, group=group)
+                with torch.cuda.stream(ext):
+                    t.copy_(h)
+                ext.synchronize()
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            print("allreduce2 hook failed:", repr(e), flush=True)
+            return 1
+
+    return hook
+
+
+def init_library_comm(L, handle, rank, world):
+    """Give the context its own NCCL communicator (include/pcaone_b200.h: pcaone_comm_unique_id /
+    pcaone_comm_init): rank 0 makes the id, torch.distributed carries the 128 bytes to the others.
+    From then on every exchange step runs inside the library on its stream."""
+    import torch
+    import torch.distributed as dist
+
+    ident = (C.c_uint8 * 128)()
+    if rank == 0 and L.pcaone_comm_unique_id(ident):
+        raise RuntimeError("pcaone_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    t = torch.tensor(list(ident), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        dist.broadcast(t, 0)
+        t = t.cpu()
+    else:
+        dist.broadcast(t, 0)
+    ident = (C.c_uint8 * 128)(*t.tolist())
+    if L.pcaone_comm_init(handle, ident, rank, world):
+        raise RuntimeError(L.pcaone_last_error(handle).decode())
+
+
+def shard_samples_range(n_samples: int, rank: int, world: int):
+    """Sample shard of a sample-sharded job: contiguous, starting at a multiple of 4 samples (whole bed bytes)."""
+    per = -(-n_samples // world)
+    per = (per + 3) // 4 * 4
+    s = min(rank * per, n_samples)
+    return s, min(s + per, n_samples)
 
 
 def init_process_group_from_env(backend=None):

@@ -313,7 +313,12 @@ class RsvdOpData:
     svd = None
 
     def __init__(self, data: FileBed, k: int, os_: int = 10, *, rank=0, world=1, nsnps_total=None,
-                 allreduce=None):
+                 allreduce=None, allreduce2=None, library_comm=False, shard_samples=False, nsamples_total=None, sample_offset=0):
+        """Multi-GPU jobs (one op per GPU): `rank` / `world`, and either SNP sharding (data holds this
+        rank's SNPs of every window, `nsnps_total` = M of the job) or `shard_samples` (data holds this
+        rank's samples [sample_offset, sample_offset + data.nsamples) of ALL SNPs). `library_comm`: the
+        collectives run inside the library (NCCL, id exchanged through torch.distributed); else through
+        the `allreduce` host hook."""
         L = _lib.load()
         self.L = L
         self.data = data
@@ -326,16 +331,27 @@ class RsvdOpData:
                           k=self.nk, oversamples=self.os, svd=self.svd, bands=p.bands, maxp=p.maxp, tol=p.tol,
                           ploidy=p.ploidy, scale=p.scale, emu=int(p.emu), out_of_core=int(p.out_of_core),
                           precision=p.precision, device=p.device, rank=rank, world=world, maxiter=p.maxiter,
-                          tolem=p.tolem)
+                          tolem=p.tolem, shard_samples=int(bool(shard_samples)),
+                          nsamples_total=int(nsamples_total or data.nsamples), sample_offset=int(sample_offset))
+        self.shard_samples = bool(shard_samples) and world > 1
+        self.nsamples_total = int(nsamples_total or data.nsamples) if self.shard_samples else data.nsamples
+        self.sample_offset = int(sample_offset) if self.shard_samples else 0
         h = C.c_void_p()
         if L.pcaone_create(C.byref(cfg), C.byref(h)):
             raise RuntimeError(L.pcaone_last_error(None).decode())
         self.h = h
         self._keep = []
+        if library_comm and world > 1:
+            from . import dist as _pdist
+            _pdist.init_library_comm(L, self.h, rank, world)
         if allreduce is not None:
             cb = _lib.ALLREDUCE_FN(allreduce)
             self._keep.append(cb)
             self._chk(L.pcaone_set_allreduce(self.h, cb, None))
+        if allreduce2 is not None:
+            cb = _lib.ALLREDUCE2_FN(allreduce2)
+            self._keep.append(cb)
+            self._chk(L.pcaone_set_allreduce2(self.h, cb, None))
         if getattr(data, "P", None) is not None:
             if data.F is None:
                 raise RuntimeError("FileBeagle: call prepare() first")
@@ -399,8 +415,15 @@ class RsvdOpData:
 
     def initOmg(self):
         p = self.data.params
-        self.Omg = _f((self.cols(), self.size()))
-        self.L.pcaone_init_omega(self.cols(), self.size(), p.seed, int(p.rand), _vp(self.Omg))
+        if self.shard_samples:
+            # the job's Omega is N_total x l (one RNG stream, column-major); this rank keeps its rows
+            full = _f((self.nsamples_total, self.size()))
+            self.L.pcaone_init_omega(self.nsamples_total, self.size(), p.seed, int(p.rand), _vp(full))
+            self.Omg = np.asfortranarray(full[self.sample_offset:self.sample_offset + self.cols()])
+            del full
+        else:
+            self.Omg = _f((self.cols(), self.size()))
+            self.L.pcaone_init_omega(self.cols(), self.size(), p.seed, int(p.rand), _vp(self.Omg))
         self._chk(self.L.pcaone_set_omega(self.h, _vp(self.Omg)))
 
     def setOmg(self, Omg):

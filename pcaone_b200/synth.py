@@ -142,3 +142,38 @@ def torch_packed(n_samples, n_snps, k_pop=4, fst=0.1, miss=0.0, seed=1, device="
         q = codes.view(m, bpr, 4)
         out[s:s + m] = q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)
     return out
+
+
+def torch_packed_tile(n_total, samp0, n_loc, snp0, m, k_pop=4, fst=0.1, miss=0.0, seed=1, device="cuda"):
+    """Packed (m, ceil(n_loc/4)) uint8 tile of ONE fixed synthetic matrix: SNPs [snp0, snp0+m) x samples
+    [samp0, samp0+n_loc) of an n_total-sample job (samp0 % 4 == 0). The allele frequencies of a SNP
+    depend on (seed, SNP) only and the genotype draws on (seed, SNP chunk start, samp0), so the matrix
+    is the same however it is cut into tiles of these boundaries — what a strong-scaling run needs:
+    every world size sees the same bed. Callers keep snp0 and samp0 on a fixed grid."""
+    import torch
+
+    assert samp0 % 4 == 0
+    g1 = torch.Generator(device=device)
+    g1.manual_seed((seed * 1_000_003 + snp0) & 0x7FFFFFFFFFFF)
+    g2 = torch.Generator(device=device)
+    g2.manual_seed(((seed * 1_000_003 + snp0) * 7919 + samp0 + 1) & 0x7FFFFFFFFFFF)
+    bpr = bytes_per_snp(n_loc)
+    npad = bpr * 4
+    gidx = torch.arange(npad, device=device) + samp0
+    pop = (gidx * k_pop // max(n_total, 1)).clamp_(max=k_pop - 1)
+    valid = (torch.arange(npad, device=device) < n_loc)
+    lut = torch.tensor([3, 2, 0], dtype=torch.uint8, device=device)
+    p_anc = torch.rand(m, generator=g1, device=device) * 0.9 + 0.05
+    sd = torch.sqrt(p_anc * (1 - p_anc) * fst)
+    p_pop = (p_anc[:, None] + sd[:, None] * torch.randn(m, k_pop, generator=g1, device=device)).clamp_(0.01, 0.99)
+    p_ind = p_pop[:, pop]  # (m, npad)
+    u1 = torch.rand(m, npad, generator=g2, device=device)
+    copies = (u1 < p_ind).to(torch.uint8)
+    u1 = torch.rand(m, npad, generator=g2, device=device)
+    copies += (u1 < p_ind).to(torch.uint8)
+    codes = lut[copies.long()]
+    if miss > 0:
+        codes = torch.where(torch.rand(m, npad, generator=g2, device=device) < miss, torch.ones_like(codes), codes)
+    codes = codes * valid.to(torch.uint8)  # padding bits 0
+    q = codes.view(m, bpr, 4)
+    return q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)
