@@ -48,8 +48,8 @@ WORKLOADS = {
     "c3": (500_000, 500_000, 40, True, "configs[2]: UK-Biobank-scale bed, winSVD, out-of-core block plan"),
     "c2": (10_000, 1_000_000, 20, False, "configs[1]: winSVD in-memory"),
 }
-CPU_SAMPLES_BASELINE = 2048   # cpu_baseline leg: this many samples x ALL SNPs, one full PCA
-CPU_SAMPLES_REF_ARM = 512     # --impl reference: K + W full PCAs must end within minutes
+CPU_SAMPLES_BASELINE = 1024   # cpu_baseline leg: this many samples x ALL SNPs, one full PCA
+CPU_SAMPLES_REF_ARM = 256     # --impl reference: K + W full PCAs must end within minutes
 
 
 def _peaks():
@@ -267,12 +267,16 @@ def main():
     host = torch.empty((m_loc, bpr), dtype=torch.uint8, pin_memory=True)
     chunk = max(64, min(4096, (1 << 28) // max(nblk, 1)))   # ~256M genotypes per tile
     if snp_idx is None:
+        stage = torch.empty((chunk, bpr), dtype=torch.uint8, device=dev)   # one contiguous D2H per SNP chunk
         for s0 in range(0, m, chunk):
             mm = min(chunk, m - s0)
             for sb in range(sb0, sb1):
                 tile = synth.torch_packed_tile(n, sb * nblk, nblk, s0, mm, k_pop=K + 4, seed=1, device=dev)
                 c0 = (sb - sb0) * (nblk // 4)
-                host[s0:s0 + mm, c0:c0 + tile.shape[1]].copy_(tile)
+                stage[:mm, c0:c0 + tile.shape[1]] = tile
+            host[s0:s0 + mm].copy_(stage[:mm], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        del stage
     else:
         # SNP shard: this rank's SNPs of every window (rows of the same tiles)
         pos = 0

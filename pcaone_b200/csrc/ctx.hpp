@@ -113,10 +113,13 @@ struct pcaone_ctx {
   bool tiles_valid = false;
   // HBM cache of the tiled operands of streamed blocks (out-of-core sources): block b of the plan
   // keeps its PG / PH tiles after the first pass if they fit, so later passes read HBM, not the host
-  uint8_t* d_cache = nullptr;
+  // The cache is ONE tiling of SNPs [0, cache_rows) — blocks write their rows / k-block bits at
+  // their global offsets — so cached blocks behave like a resident shard: consecutive blocks with no
+  // Omega update between them run as one range.
+  uint8_t *d_cache_pg = nullptr, *d_cache_ph = nullptr;
   size_t cache_bytes = 0;
-  std::vector<size_t> cache_pg_off, cache_ph_off;      // per block; SIZE_MAX = not cached (streamed every pass)
-  std::vector<uint8_t> cache_filled;
+  uint64_t cache_rows = 0;                             // SNPs [0, cache_rows) have a place in the cache
+  std::vector<uint8_t> cache_filled;                   // per block of the plan: its tiles are in the cache
   int cache_mode = -1;                                 // -1 undecided, 0 off, 1 on
   int8_t *d_BimgO = nullptr, *d_BimgW = nullptr;       // B operand images: Omega, W = s o G of the current range
   size_t bimgW_kb = 0;
@@ -257,7 +260,8 @@ void dense_transpose_in(pcaone_ctx* c, const double* stage);
 // ---- launch_tc.cu
 size_t tc_pg_bytes(const pcaone_ctx* c, uint64_t rows);
 size_t tc_ph_bytes(const pcaone_ctx* c, uint64_t rows);
-void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st);
+void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st,
+                    uint64_t row0 = 0);
 void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows, bool miss);
 void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0,
                     double* Hacc, bool accumulate, bool miss);
@@ -299,5 +303,6 @@ void snp_sqnorm(pcaone_ctx* c, double* out);
 void cache_plan(pcaone_ctx* c);
 void cache_release(pcaone_ctx* c);
 void cache_invalidate(pcaone_ctx* c);
+bool cache_covers(const pcaone_ctx* c, uint32_t b);
 
 }  // namespace pcaone

@@ -109,14 +109,16 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
     return;
   }
   uint8_t *PG, *PH;
-  if (blk >= 0 && c->cache_mode == 1 && c->cache_pg_off[blk] != SIZE_MAX) {
-    PG = c->d_cache + c->cache_pg_off[blk];
-    PH = c->d_cache + c->cache_ph_off[blk];
+  if (blk >= 0 && cache_covers(c, (uint32_t)blk)) {
+    // the cache is one tiling of SNPs [0, cache_rows): the block sits at its own SNP offset, and a
+    // range may span several cached blocks (blk = the first)
     if (!c->cache_filled[blk]) {
       if (!P) throw std::runtime_error("range_gemms: cached block without its packed rows");
-      tc_build_tiles(c, P, nrows, PG, PH, c->stream);
+      tc_build_tiles(c, P, nrows, c->d_cache_pg, c->d_cache_ph, c->stream, snp0);
       c->cache_filled[blk] = 1;
     }
+    range_gemms_tc(c, c->d_cache_pg, c->d_cache_ph, snp0, nrows, snp0, Hacc, accumulate, has_miss);
+    return;
   } else {
     if (!P) throw std::runtime_error("range_gemms: streamed block without its packed rows");
     if (!c->d_PGb[buf]) {
@@ -133,7 +135,7 @@ void range_gemms(pcaone_ctx* c, const uint8_t* P, uint32_t nrows, uint64_t snp0,
 // does block b of the plan have to come from the host on this pass?
 bool ooc_needs_stage(pcaone_ctx* c, uint32_t b) {
   if (c->blk_stop[b] + 1 == c->blk_start[b]) return false;  // empty placeholder
-  return !(pass_uses_tc(c) && c->af_done && c->cache_mode == 1 && c->cache_pg_off[b] != SIZE_MAX && c->cache_filled[b]);
+  return !(pass_uses_tc(c) && c->af_done && cache_covers(c, b) && c->cache_filled[b]);
 }
 
 // enqueue the host->device copy of block b into its buffer (b & 1) unless it is already there
@@ -173,6 +175,21 @@ void ooc_block(pcaone_ctx* c, uint32_t b, double* Hacc) {
   range_gemms(c, P, (uint32_t)nrows, s0, Hacc, true, buf, b);
   PCA_CUDA(cudaEventRecord(c->ev_done[buf], c->stream));
   c->staged_blk[buf] = -1;
+}
+
+// blocks [b, e] of the plan as one step: a span of cached blocks runs as ONE range of the cache's
+// tiling (like merged windows of a resident shard), anything else block by block
+bool ooc_cached(pcaone_ctx* c, size_t b) {
+  return pass_uses_tc(c) && c->af_done && cache_covers(c, (uint32_t)b) && c->cache_filled[b];
+}
+void ooc_span(pcaone_ctx* c, size_t b, size_t e, double* Hacc) {
+  if (e > b) {
+    const uint64_t s0 = c->blk_start[b], nrows = c->blk_stop[e] + 1 - s0;
+    range_gemms(c, nullptr, (uint32_t)nrows, s0, Hacc, true, 0, (int64_t)b);
+    c->tm.cache_hits += e - b + 1;
+    return;
+  }
+  ooc_block(c, (uint32_t)b, Hacc);
 }
 
 // ---------------------------------------------------------------- the passes
@@ -274,7 +291,13 @@ void compute_gandh(pcaone_ctx* c, int pi) {
       }
     } else {
       zero_async(c, c->d_H, HN);
-      for (uint32_t b = 0; b < c->blk_start.size(); ++b) ooc_block(c, b, c->d_H);
+      const size_t nb = c->blk_start.size();
+      for (size_t b = 0; b < nb;) {
+        size_t e2 = b;
+        while (ooc_cached(c, b) && e2 + 1 < nb && ooc_cached(c, e2 + 1) && c->blk_start[e2 + 1] == c->blk_stop[e2] + 1) ++e2;
+        ooc_span(c, b, e2, c->d_H);
+        b = e2 + 1;
+      }
       c->af_done = true;
     }
     allreduce_H(c, c->d_H);
@@ -299,10 +322,10 @@ void compute_gandh(pcaone_ctx* c, int pi) {
   while (b < steps.size()) {
     // merge resident windows that share a target and have no Omega update between them
     size_t e = b;
-    if (!ooc) {
+    if (!ooc || ooc_cached(c, b)) {  // (streamed source: blocks whose tiles sit in the HBM cache)
       while (!steps[e].update && e + 1 < steps.size() && steps[e + 1].target == steps[b].target &&
              steps[e + 1].stop >= steps[e + 1].start && steps[e].stop >= steps[e].start &&
-             steps[e + 1].start == steps[e].stop + 1)
+             steps[e + 1].start == steps[e].stop + 1 && (!ooc || ooc_cached(c, e + 1)))
         ++e;
     }
     double* Hacc = steps[b].target == 1 ? c->d_H1 : c->d_H2;
@@ -317,7 +340,7 @@ void compute_gandh(pcaone_ctx* c, int pi) {
       if (!ooc) {
         range_gemms(c, c->d_packed + s0 * c->pitch, (uint32_t)nrows, s0, Hacc, true, -1);
       } else {
-        ooc_block(c, (uint32_t)b, Hacc);
+        ooc_span(c, b, e, Hacc);
       }
     }
     c->sum_other = nullptr;

@@ -17,14 +17,16 @@ size_t tc_ph_bytes(const pcaone_ctx* c, uint64_t rows) {
   return (size_t)((rows + tc::kKB - 1) / tc::kKB) * tc_nrt_samples(c) * tc::kChunkBytes;
 }
 
-// tiled copies of `rows` packed SNP rows at P: PG (rows = SNPs) and PH (rows = samples)
-void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st) {
+// tiled copies of `rows` packed SNP rows at P: PG (rows = SNPs) and PH (rows = samples). `row0`: SNP
+// index of P's first row inside the tiling PG / PH point at (0 for a stand-alone block)
+void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st,
+                    uint64_t row0) {
   const uint32_t nkb = (uint32_t)tc_nkb_samples(c), nrt = (uint32_t)tc_nrt_samples(c);
   const uint64_t work = (uint64_t)((rows + tc::kRowTile - 1) / tc::kRowTile) * nkb * tc::kRowTile;
-  tc::k_tile_rows<<<grid_for(work, 256, c->sms), 256, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nkb, PG);
+  tc::k_tile_rows<<<grid_for(work, 256, c->sms), 256, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nkb, PG, row0);
   PCA_CHECK_LAUNCH();
-  const uint64_t nkbh = (rows + tc::kKB - 1) / tc::kKB;
-  tc::k_tile_transpose<<<(unsigned)(nkbh * nrt), 128, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nrt, PH);
+  const uint64_t nkbh = (row0 + rows - 1) / tc::kKB - row0 / tc::kKB + 1;
+  tc::k_tile_transpose<<<(unsigned)(nkbh * nrt), 128, 0, st>>>(P, c->pitch, rows, (uint32_t)c->N, nrt, PH, row0);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches += 2;
 }

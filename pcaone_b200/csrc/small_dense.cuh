@@ -112,7 +112,12 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
     if (tid == 0) s_rot = s_big = 0;
     __syncthreads();
     for (int round = 0; round < n - 1; ++round) {
-      for (int pi = warp; pi < n / 2; pi += nw) {
+      // one HALF-warp per column pair: 64 pairs in flight per pass, so a round of l <= 128 columns is
+      // one pass (a warp per pair took two passes at l = 80 and left half of its lanes idle at
+      // l <= 40); the three dot products fold over 16 lanes
+      for (int pi = (tid >> 4); pi < n / 2; pi += (nt >> 4)) {
+        const int hl = tid & 15;
+        const unsigned hmask = 0xffffu << (tid & 16);
         int p, q;
         if (pi == 0) {
           p = n - 1;
@@ -130,19 +135,22 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
         double* ap = A + p * l;
         double* aq = A + q * l;
         double alpha = 0.0, beta = 0.0, gamma = 0.0;
-        for (int r = lane; r < l; r += 32) {
+        for (int r = hl; r < l; r += 16) {
           const double x = ap[r], y = aq[r];
           alpha += x * x;
           beta += y * y;
           gamma += x * y;
         }
-        alpha = warp_sum(alpha);
-        beta = warp_sum(beta);
-        gamma = warp_sum(gamma);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          alpha += __shfl_xor_sync(hmask, alpha, o);
+          beta += __shfl_xor_sync(hmask, beta, o);
+          gamma += __shfl_xor_sync(hmask, gamma, o);
+        }
         // the rotation parameters are a serial chain every lane waits for: reciprocal / rsqrt
         // forms instead of three divisions and three square roots (same test, squared)
         if (gamma * gamma > (eps * eps) * (alpha * beta) && gamma != 0.0) {
-          if (lane == 0) {
+          if (hl == 0) {
             s_rot = 1;
             if (gamma * gamma > 1e-16 * (alpha * beta)) s_big = 1;
           }
@@ -152,7 +160,7 @@ k_jacobi_svd(const double* __restrict__ Ain, int l, int ld, int symmetric_psd, d
           const double c = rsqrt(1.0 + tt * tt), s = c * tt;
           double* vp = V + p * l;
           double* vq = V + q * l;
-          for (int r = lane; r < l; r += 32) {
+          for (int r = hl; r < l; r += 16) {
             const double x = ap[r], y = aq[r];
             ap[r] = c * x - s * y;
             aq[r] = s * x + c * y;

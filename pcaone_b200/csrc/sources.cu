@@ -106,11 +106,11 @@ void snp_sqnorm(pcaone_ctx* c, double* out) {
 // instead of at the host link's. Blocks that do not fit keep streaming. PCAONE_TILE_CACHE=0 turns
 // the cache off, PCAONE_TILE_CACHE_MB caps it.
 void cache_release(pcaone_ctx* c) {
-  if (c->d_cache) cudaFree(c->d_cache);
-  c->d_cache = nullptr;
+  if (c->d_cache_pg) cudaFree(c->d_cache_pg);
+  if (c->d_cache_ph) cudaFree(c->d_cache_ph);
+  c->d_cache_pg = c->d_cache_ph = nullptr;
   c->cache_bytes = 0;
-  c->cache_pg_off.clear();
-  c->cache_ph_off.clear();
+  c->cache_rows = 0;
   c->cache_filled.clear();
   c->cache_mode = -1;
 }
@@ -120,45 +120,43 @@ void cache_invalidate(pcaone_ctx* c) {
   c->staged_blk[0] = c->staged_blk[1] = -1;
 }
 
+bool cache_covers(const pcaone_ctx* c, uint32_t b) {
+  return c->cache_mode == 1 && c->blk_stop[b] + 1 > c->blk_start[b] && c->blk_stop[b] < c->cache_rows;
+}
+
 void cache_plan(pcaone_ctx* c) {
   if (c->cache_mode >= 0) return;
   c->cache_mode = 0;
   const size_t nb = c->blk_start.size();
-  c->cache_pg_off.assign(nb, SIZE_MAX);
-  c->cache_ph_off.assign(nb, SIZE_MAX);
   c->cache_filled.assign(nb, 0);
   if (const char* e = getenv("PCAONE_TILE_CACHE"))
     if (atoi(e) == 0) return;
   if (c->slices == 0 || c->cfg.emu) return;  // FP64 kernels (and EMU update passes) read the packed rows
-  size_t total = 0;
-  std::vector<size_t> need(nb);
-  for (size_t b = 0; b < nb; ++b) {
-    const uint64_t rows = c->blk_stop[b] - c->blk_start[b] + 1;
-    need[b] = round_up(tc_pg_bytes(c, rows), 256) + round_up(tc_ph_bytes(c, rows), 256);
-    total += need[b];
-  }
   size_t free_b = 0, total_b = 0;
   PCA_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t reserve = (size_t)3 << 30;
   const size_t dbl = 2 * (tc_pg_bytes(c, c->max_block) + tc_ph_bytes(c, c->max_block));  // uncached blocks' double buffers
-  size_t budget = 0;
-  if (total + reserve <= free_b)
-    budget = total;
-  else if (free_b > reserve + dbl)
-    budget = free_b - reserve - dbl;
+  auto need = [&](uint64_t rows) { return tc_pg_bytes(c, rows) + tc_ph_bytes(c, rows) + 512; };
+  size_t budget = free_b > reserve ? free_b - reserve : 0;
   if (const char* e = getenv("PCAONE_TILE_CACHE_MB")) budget = std::min<size_t>(budget, (size_t)atoll(e) << 20);
-  size_t used = 0;
-  for (size_t b = 0; b < nb && used + need[b] <= budget; ++b) used += need[b];
-  if (used == 0) return;
-  PCA_CUDA(cudaMalloc((void**)&c->d_cache, used));
-  c->cache_bytes = used;
-  size_t off = 0;
-  for (size_t b = 0; b < nb && off + need[b] <= used; ++b) {
-    const uint64_t rows = c->blk_stop[b] - c->blk_start[b] + 1;
-    c->cache_pg_off[b] = off;
-    c->cache_ph_off[b] = off + round_up(tc_pg_bytes(c, rows), 256);
-    off += need[b];
+  // the longest prefix of the plan (contiguous blocks from SNP 0) whose tiling fits
+  uint64_t rows = 0;
+  for (size_t b = 0; b < nb; ++b) {
+    if (c->blk_stop[b] + 1 == c->blk_start[b]) continue;  // empty placeholder
+    if (c->blk_start[b] != rows) break;
+    const uint64_t upto = c->blk_stop[b] + 1;
+    const bool last = upto == c->M;
+    if (need(upto) + (last ? 0 : dbl) > budget) break;
+    rows = upto;
   }
+  if (rows == 0) return;
+  PCA_CUDA(cudaMalloc((void**)&c->d_cache_pg, tc_pg_bytes(c, rows)));
+  PCA_CUDA(cudaMalloc((void**)&c->d_cache_ph, tc_ph_bytes(c, rows)));
+  // zero once: bits of SNP slots that no block fills (the tail of the last k-block) stay code 00
+  PCA_CUDA(cudaMemsetAsync(c->d_cache_pg, 0, tc_pg_bytes(c, rows), c->stream));
+  PCA_CUDA(cudaMemsetAsync(c->d_cache_ph, 0, tc_ph_bytes(c, rows), c->stream));
+  c->cache_bytes = tc_pg_bytes(c, rows) + tc_ph_bytes(c, rows);
+  c->cache_rows = rows;
   c->cache_mode = 1;
 }
 

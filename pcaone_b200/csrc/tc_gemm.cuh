@@ -372,23 +372,27 @@ __global__ void __launch_bounds__(tc_threads(RT), 1) k_tc_gemm(const TcGemmArgs 
 // operand preparation
 // ------------------------------------------------------------------------------------------
 
-// Row-tiled copy of the SNP-major packed rows ([rows][pitch]): chunk (rt, kb) holds, for each of
-// 128 rows, the 16 bytes of k-block kb. dst chunk = dst + (rt * nkb + kb) * 2 KB.
-// Entries beyond `ncols` (sample padding of the last byte; the reference ignores those bits,
-// FilePlink.cpp:42) and rows beyond `rows` are code 00 (u = 0).
+// Row-tiled copy of the SNP-major packed rows ([rows][pitch]) into a tiling whose row 0 is `row0` rows
+// before P's first row: chunk (rt, kb) holds, for each of 128 rows, the 16 bytes of k-block kb;
+// dst chunk = dst + (rt * nkb + kb) * 2 KB. Entries beyond `ncols` (sample padding of the last
+// byte; the reference ignores those bits, FilePlink.cpp:42) are code 00 (u = 0). Rows of the first /
+// last tile that P does not cover are left as they are: the GEMM masks its output rows to the range,
+// and an output row depends on its own operand row only.
 __global__ void k_tile_rows(const uint8_t* __restrict__ P, uint32_t pitch, uint64_t rows, uint32_t ncols,
-                            uint32_t nkb, uint8_t* __restrict__ dst) {
+                            uint32_t nkb, uint8_t* __restrict__ dst, uint64_t row0) {
   const uint64_t total = (uint64_t)((rows + kRowTile - 1) / kRowTile) * nkb * kRowTile;
   for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t r = (uint32_t)(idx % kRowTile);
-    const uint64_t chunk = idx / kRowTile;
-    const uint32_t kb = (uint32_t)(chunk % nkb);
-    const uint64_t rt = chunk / nkb;
-    const uint64_t row = rt * kRowTile + r;
+    // consecutive threads: consecutive rows of one k-block (16-byte stores side by side in the chunk)
+    const uint64_t blk = idx / kRowTile, r_in = idx % kRowTile;
+    const uint64_t rgrp = blk / nkb;
+    const uint32_t kb = (uint32_t)(blk % nkb);
+    const uint64_t lrow = rgrp * kRowTile + r_in;  // row of P
+    if (lrow >= rows) continue;
+    const uint64_t grow = row0 + lrow;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < rows && kb * 16 < pitch) {
-      v = *reinterpret_cast<const uint4*>(P + row * pitch + kb * 16);
+    if (kb * 16 < pitch) {
+      v = *reinterpret_cast<const uint4*>(P + lrow * pitch + kb * 16);
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
@@ -401,25 +405,32 @@ __global__ void k_tile_rows(const uint8_t* __restrict__ P, uint32_t pitch, uint6
       }
       v = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(dst + chunk * kChunkBytes + r * 16) = v;
+    *reinterpret_cast<uint4*>(dst + ((grow / kRowTile) * nkb + kb) * kChunkBytes + (grow % kRowTile) * 16) = v;
   }
 }
 
 // Transposed tiled copy: rows = samples, contraction = SNPs. chunk (kb, rt) = dst + (kb * nrt + rt)
 // * 2 KB; row r = sample rt*128 + r, byte q = SNPs kb*64 + 4q .. +3 (two bits each, same bit
-// order as the bed file along its own axis). SNPs >= nsnps and samples >= N are code 00.
+// order as the bed file along its own axis). P holds SNPs [snp0, snp0 + nsnps) of the tiling; block
+// (x, rt) builds k-block snp0/64 + x. A k-block that P covers only partly (a streamed block that
+// starts or ends inside it) is merged into what is there: the bits of the other SNPs are kept (the
+// neighbouring block wrote or will write them; the H-pass image is zero outside its range, so
+// whatever they hold never contributes). Samples >= N are code 00.
 __global__ void __launch_bounds__(128) k_tile_transpose(const uint8_t* __restrict__ P, uint32_t pitch, uint64_t nsnps,
-                                                        uint32_t N, uint32_t nrt, uint8_t* __restrict__ dst) {
+                                                        uint32_t N, uint32_t nrt, uint8_t* __restrict__ dst,
+                                                        uint64_t snp0) {
   __shared__ uint32_t tile[kKB][9];  // 64 SNP rows x 32 bytes (128 samples), padded
   const uint32_t rt = blockIdx.x % nrt;
-  const uint64_t kb = blockIdx.x / nrt;
+  const uint64_t kb = snp0 / kKB + blockIdx.x / nrt;
   const int tid = threadIdx.x;
+  const long long g_lo = (long long)snp0 - (long long)(kb * kKB);            // first covered SNP slot of this k-block (may be < 0)
+  const long long g_hi = (long long)(snp0 + nsnps) - (long long)(kb * kKB);  // one past the last covered slot (may be > 64)
   for (int i = tid; i < kKB * 8; i += 128) {
     const int g = i >> 3, wq = i & 7;
-    const uint64_t snp = kb * kKB + g;
     const uint32_t byte0 = rt * 32 + wq * 4;
     uint32_t w = 0;
-    if (snp < nsnps && byte0 < pitch) w = *reinterpret_cast<const uint32_t*>(P + snp * pitch + byte0);
+    if (g >= g_lo && g < g_hi && byte0 < pitch)
+      w = *reinterpret_cast<const uint32_t*>(P + (uint64_t)((long long)(kb * kKB) + g - (long long)snp0) * pitch + byte0);
     tile[g][wq] = w;
   }
   __syncthreads();
@@ -433,8 +444,23 @@ __global__ void __launch_bounds__(128) k_tile_transpose(const uint8_t* __restric
       out[g >> 4] |= code << (2 * (g & 15));
     }
   }
-  *reinterpret_cast<uint4*>(dst + ((uint64_t)kb * nrt + rt) * kChunkBytes + tid * 16) =
-      make_uint4(out[0], out[1], out[2], out[3]);
+  uint4* d = reinterpret_cast<uint4*>(dst + (kb * nrt + rt) * kChunkBytes + tid * 16);
+  if (g_lo > 0 || g_hi < kKB) {
+    uint32_t m[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      uint32_t mm = 0;
+      for (int b2 = 0; b2 < 16; ++b2) {
+        const int g = 16 * x + b2;
+        if (g >= g_lo && g < g_hi) mm |= 3u << (2 * b2);
+      }
+      m[x] = mm;
+    }
+    const uint4 o = *d;
+    *d = make_uint4((o.x & ~m[0]) | out[0], (o.y & ~m[1]) | out[1], (o.z & ~m[2]) | out[2], (o.w & ~m[3]) | out[3]);
+  } else {
+    *d = make_uint4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 // column abs-max of X[r0..r1)[0..l) -> colmax bits (atomicMax on the IEEE pattern, which is
