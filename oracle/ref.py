@@ -278,3 +278,35 @@ def rsvd_one(A, k, os_=10, rand=1, p=3, windows=0, finder=1):
     if rc:
         raise RuntimeError("reference failed: " + lib().ref_last_error().decode())
     return U, S, V
+
+
+# ---- the compiled drop-in: reference host code + integration/HalkoGpu.hpp + libpcaone_b200.so ----------
+GPU_LIB_PATH = os.path.join(_HERE, "_ref", "libpcaone_ref_gpu.so")
+_gpu_lib = None
+
+
+def gpu_available() -> bool:
+    return os.path.exists(GPU_LIB_PATH)
+
+
+def gpu_run(cmdline: str, precision: int, on_device: bool = False):
+    """Run a PCAone command line through the UNMODIFIED reference host code with the GPU ops of
+    integration/HalkoGpu.hpp (oracle/ref_gpu_shim.cpp). Returns U, S, V (V in run order) and perm."""
+    global _gpu_lib
+    if _gpu_lib is None:
+        _gpu_lib = C.CDLL(GPU_LIB_PATH)
+        _gpu_lib.refgpu_last_error.restype = C.c_char_p
+    dims = (C.c_longlong * 3)()
+    # sizes first (cheap: the shim only needs the .fam / .bim line counts, so ask the host side)
+    toks = cmdline.split()
+    prefix = toks[toks.index("-b") + 1]
+    n = sum(1 for _ in open(prefix + ".fam"))
+    m = sum(1 for _ in open(prefix + ".bim"))
+    k = int(toks[toks.index("-k") + 1])
+    U, S, V = _f((n, k)), np.zeros(k), _f((m, k))
+    perm = np.full(m, -1, dtype=np.int32)
+    rc = _gpu_lib.refgpu_run(cmdline.encode(), int(precision), int(on_device), _p(U), _p(S), _p(V), dims, _p(perm))
+    if rc:
+        raise RuntimeError("reference-on-GPU run failed: " + _gpu_lib.refgpu_last_error().decode())
+    assert (dims[0], dims[1], dims[2]) == (n, m, k)
+    return U, S, V, (perm if perm[0] >= 0 or (perm >= 0).all() else None)
