@@ -193,6 +193,34 @@ int pcaone_shuffle_indices(uint64_t n, uint32_t* out);
 int pcaone_ld_r2(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
                  uint64_t nwin, double* r2_out);
 
+/* The same tiles on the other operands of the reference's LD path, without the 8 N M-byte host matrix:
+ *   PCAONE_LD_DENSE_F64       data = N x M column-centred doubles on the host (pcaone_ld_r2 with G != NULL)
+ *   PCAONE_LD_PACKED          the resident packed shard centred by F          (pcaone_ld_r2 with G == NULL)
+ *   PCAONE_LD_RESID_F32       data = the float32 rows of a `.residuals` file (`-B`): cast to double and
+ *                             centred per SNP as FileBin::read_all does (FileBinary.cpp:21-30); 4 N M host bytes,
+ *                             streamed chunk by chunk
+ *   PCAONE_LD_PACKED_RESID    the resident packed shard turned into those residuals ON THE DEVICE: centred
+ *                             decode, `G -= U S V^T` with the context's U, S, V when ld_stats == 0
+ *                             (Data::write_residuals, Data.cpp:242-291), column-centred, rounded through float32
+ *                             and centred again — bit for bit what `--ld` writes and `-B` reads back, minus the file
+ *   PCAONE_LD_PACKED_PROJECT  the resident packed shard with `(I - U U^T) G` applied, data = U of `--USV`
+ *                             (nsamples x ncols doubles, column-major; LD.cpp:491-496)
+ * r2_out (may be NULL with keep_out) and af / r2_tol / keep_out (pruning; keep_out may be NULL) as above. */
+enum { PCAONE_LD_DENSE_F64 = 0, PCAONE_LD_PACKED = 1, PCAONE_LD_RESID_F32 = 2, PCAONE_LD_PACKED_RESID = 3,
+       PCAONE_LD_PACKED_PROJECT = 4 };
+typedef struct pcaone_ld_source {
+  int32_t kind;       /* PCAONE_LD_* */
+  int32_t ld_stats;   /* PACKED_RESID: 0 = ancestry-adjusted (subtract U S V^T), 1 = standardized-genotype LD */
+  const void* data;   /* host operand of the kinds that have one */
+  uint32_t ncols;     /* PACKED_PROJECT: columns of U */
+} pcaone_ld_source;
+int pcaone_ld_r2_ex(pcaone_ctx* ctx, const pcaone_ld_source* src, uint64_t nsnps, const int32_t* ws, const int32_t* we,
+                    uint64_t nwin, double* r2_out, const double* af, double r2_tol, uint8_t* keep_out);
+/* Data::write_residuals (Data.cpp:242-291) for SNPs start..stop of the resident shard: out receives the
+ * float32 rows of `<out>.residuals` ([stop - start + 1][nsamples], SNP-major); the host writes the 8-byte
+ * header, seeks by the permutation (Data.cpp:264-267) and saves the .mbim. */
+int pcaone_residuals_block(pcaone_ctx* ctx, uint64_t start, uint64_t stop, int ld_stats, float* out);
+
 /* ---- IRAM operator: ArnoldiOpData::perform_op (Arnoldi.cpp:18-46, Arnoldi.hpp:6-34) ---------
  * y = sum over blocks G_b (G_b^T x): x_in, y_out are nsamples doubles on the host (what Spectra's
  * SymEigsSolver hands to perform_op). Uses the context's source (resident, streamed blocks,

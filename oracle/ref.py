@@ -147,6 +147,10 @@ class Ref:
         self._chk(lib().ref_compute_usv(self.h, int(maxp), C.c_double(tol), _p(U), _p(S), _p(V)))
         return U, S, V
 
+    def write_residuals(self):
+        """Data::write_residuals (Data.cpp:242-291) with the op's U, S, V -> <fileout>.residuals + .mbim."""
+        self._chk(lib().ref_write_residuals(self.h))
+
     def last_epochs(self):
         return int(lib().ref_last_epochs(self.h))
 

@@ -24,6 +24,14 @@ class Config(C.Structure):
     ]
 
 
+class LdSource(C.Structure):
+    """pcaone_ld_source: which operand pcaone_ld_r2_ex builds its tiles from."""
+    _fields_ = [("kind", C.c_int32), ("ld_stats", C.c_int32), ("data", C.c_void_p), ("ncols", C.c_uint32)]
+
+
+LD_DENSE_F64, LD_PACKED, LD_RESID_F32, LD_PACKED_RESID, LD_PACKED_PROJECT = 0, 1, 2, 3, 4
+
+
 class Timers(C.Structure):
     _fields_ = [
         ("gemm_g_ms", C.c_double), ("gemm_h_ms", C.c_double), ("orth_ms", C.c_double), ("small_ms", C.c_double),
@@ -53,6 +61,7 @@ SYMBOLS = [
     "pcaone_upload_dense", "pcaone_dense_rsvd", "pcaone_upload_dosage", "pcaone_perform_op", "pcaone_ld_prune", "pcaone_xt_times", "pcaone_x_times",
     "pcaone_upload_gl", "pcaone_gl_em_maf",
     "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
+    "pcaone_ld_r2_ex", "pcaone_residuals_block",
 ]
 
 _lib = None
@@ -95,6 +104,8 @@ def load():
         "pcaone_upload_gl": [vp, vp, u64, i32], "pcaone_gl_em_maf": [vp, u32, dbl, vp],
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
         "pcaone_comm_unique_id": [vp], "pcaone_comm_init": [vp, vp, i32, i32], "pcaone_comm_attach": [vp, vp],
+        "pcaone_ld_r2_ex": [vp, C.POINTER(LdSource), u64, vp, vp, u64, vp, vp, dbl, vp],
+        "pcaone_residuals_block": [vp, u64, u64, i32, vp],
         "pcaone_set_host_source2": [vp, vp, u64, u64], "pcaone_set_allreduce2": [vp, ALLREDUCE2_FN, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

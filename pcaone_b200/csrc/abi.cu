@@ -7,6 +7,13 @@ using namespace pcaone;
 namespace {
 thread_local std::string g_create_err;
 
+pcaone_ld_source ld_source_of(const double* G) {
+  pcaone_ld_source s{};
+  s.kind = G ? PCAONE_LD_DENSE_F64 : PCAONE_LD_PACKED;
+  s.data = G;
+  return s;
+}
+
 int supported_nt(int l) {
   static const int opts[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
   const int need = (l + 7) / 8;
@@ -305,7 +312,7 @@ int pcaone_ld_prune(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_
                     const double* af, double r2_tol, uint8_t* keep_out) {
   CTX_GUARD(c, {
     if (!keep_out) throw std::runtime_error("ld_prune: keep_out is NULL");
-    ld_r2(c, G, nsnps, ws, we, nwin, nullptr, af, r2_tol, keep_out);
+    ld_r2(c, ld_source_of(G), nsnps, ws, we, nwin, nullptr, af, r2_tol, keep_out);
   });
 }
 
@@ -369,7 +376,19 @@ int pcaone_dense_rsvd(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder) {
 
 int pcaone_ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
                  double* r2_out) {
-  CTX_GUARD(c, ld_r2(c, G, nsnps, ws, we, nwin, r2_out, nullptr, 0.0, nullptr));
+  CTX_GUARD(c, ld_r2(c, ld_source_of(G), nsnps, ws, we, nwin, r2_out, nullptr, 0.0, nullptr));
+}
+
+int pcaone_ld_r2_ex(pcaone_ctx* c, const pcaone_ld_source* src, uint64_t nsnps, const int32_t* ws, const int32_t* we,
+                    uint64_t nwin, double* r2_out, const double* af, double r2_tol, uint8_t* keep_out) {
+  CTX_GUARD(c, {
+    if (!src) throw std::runtime_error("ld_r2_ex: source is NULL");
+    ld_r2(c, *src, nsnps, ws, we, nwin, r2_out, af, r2_tol, keep_out);
+  });
+}
+
+int pcaone_residuals_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int ld_stats, float* out) {
+  CTX_GUARD(c, residuals_block(c, start, stop, ld_stats, out));
 }
 
 int pcaone_get_timers(pcaone_ctx* c, pcaone_timers* out, int reset) {

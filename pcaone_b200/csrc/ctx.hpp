@@ -282,8 +282,9 @@ void download_colmajor(pcaone_ctx* c, const double* d, uint64_t rows, int cols, 
 void colmajor_to_rowmajor(pcaone_ctx* c, const double* src, uint64_t rows, int cols, double* dst);
 
 // ---- launch_ld.cu
-void ld_r2(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
+void ld_r2(pcaone_ctx* c, const pcaone_ld_source& src, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
            double* r2_out, const double* af, double r2_tol, unsigned char* keep_out);
+void residuals_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int ld_stats, float* out);
 
 // ---- engine.cu / sources.cu
 void resolve_timers(pcaone_ctx* c);
@@ -300,6 +301,8 @@ const uint8_t* stage_block(pcaone_ctx* c, uint32_t b, int buf, bool wait = true)
 void block_af_if_needed(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nrows);
 void allele_freq_rows(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nrows);
 void snp_sqnorm(pcaone_ctx* c, double* out);
+uint64_t stage_range_max(pcaone_ctx* c, uint64_t want);
+const uint8_t* stage_range(pcaone_ctx* c, uint64_t s0, uint64_t nb);
 void cache_plan(pcaone_ctx* c);
 void cache_release(pcaone_ctx* c);
 void cache_invalidate(pcaone_ctx* c);

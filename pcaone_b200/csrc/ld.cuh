@@ -74,6 +74,135 @@ __global__ void k_decode_rows(const uint8_t* __restrict__ P, uint32_t pitch, uin
   }
 }
 
+// ---- residual operands (Data::write_residuals, Data.cpp:242-291; FileBin::read_all, FileBinary.cpp:21-30;
+// run_ld_stuff's (I - U U^T) G, LD.cpp:491-496) ---------------------------------------------------------
+// dst[j][i] = centred unscaled genotype (code 01 -> 0) - sum_k (U[i][k] S[k]) V[j][k]: the `G -= U * S * V^T`
+// of write_residuals with ld_stats = 0 on a chunk of SNP rows. CTA = 32 SNPs x 128 samples; the U tile and
+// the S-scaled V rows sit in shared memory. nk == 0: plain centred decode.
+constexpr int kResSnps = 32, kResSamples = 128;
+__global__ void __launch_bounds__(256) k_resid_rows(const uint8_t* __restrict__ P, uint32_t pitch, uint32_t N, uint32_t Np,
+                                                     uint64_t rows, const double* __restrict__ F, LutParams lp,
+                                                     const double* __restrict__ U, int ldu, const double* __restrict__ S,
+                                                     const double* __restrict__ V, int ldv, int nk,
+                                                     double* __restrict__ dst) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Us = reinterpret_cast<double*>(smem_raw);      // [128][nk + 1]
+  double* Vs = Us + (size_t)kResSamples * (nk + 1);      // [32][nk]  (V[j][k] * S[k])
+  const int tid = threadIdx.x;
+  const uint32_t ntile_s = (Np + kResSamples - 1) / kResSamples;
+  const uint64_t j0 = (uint64_t)(blockIdx.x / ntile_s) * kResSnps;
+  const uint32_t i0 = (blockIdx.x % ntile_s) * kResSamples;
+  for (int idx = tid; idx < kResSamples * nk; idx += 256) {
+    const int r = idx / nk, k = idx - r * nk;
+    Us[r * (nk + 1) + k] = (i0 + r < N) ? U[(uint64_t)(i0 + r) * ldu + k] : 0.0;
+  }
+  for (int idx = tid; idx < kResSnps * nk; idx += 256) {
+    const int r = idx / nk, k = idx - r * nk;
+    Vs[r * nk + k] = (j0 + r < rows) ? V[(j0 + r) * ldv + k] * S[k] : 0.0;
+  }
+  __syncthreads();
+  const int si = tid & (kResSamples - 1), half = tid >> 7;   // sample of this thread, which 16 SNPs
+  const uint32_t i = i0 + si;
+  if (i >= Np) return;
+  const double* u = Us + si * (nk + 1);
+#pragma unroll 1
+  for (int r = half * 16; r < half * 16 + 16; ++r) {
+    const uint64_t j = j0 + r;
+    if (j >= rows) break;
+    double x = 0.0;
+    if (i < N) {
+      const SnpLut t = make_lut(F[j], lp);
+      const uint32_t byte = P[j * pitch + (i >> 2)];
+      x = t.v[(byte >> (2 * (i & 3))) & 3u];
+      const double* v = Vs + r * nk;
+      double acc = 0.0;
+      for (int k = 0; k < nk; ++k) acc = fma(u[k], v[k], acc);
+      x -= acc;
+    }
+    dst[j * Np + i] = x;
+  }
+}
+
+// Per SNP row: subtract the mean over the N samples (`G.rowwise() -= G.colwise().mean()`), optionally
+// round through float32 the way the .residuals file does (write_residuals casts, FileBin::read_all reads
+// back and centres AGAIN), and optionally hand the floats out ([rows][N], the file's row layout).
+// One warp per row.
+__global__ void __launch_bounds__(256) k_center_rows(double* __restrict__ Gs, uint64_t rows, uint32_t N, uint32_t Np,
+                                                      int through_f32, float* __restrict__ f32_out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t j = warp; j < rows; j += nwarps) {
+    double* row = Gs + j * Np;
+    double s = 0.0;
+    for (uint32_t i = lane; i < N; i += 32) s += row[i];
+    s = warp_sum(s);
+    const double mean = s / (double)N;
+    if (!through_f32) {
+      for (uint32_t i = lane; i < N; i += 32) row[i] -= mean;
+      continue;
+    }
+    double s2 = 0.0;
+    for (uint32_t i = lane; i < N; i += 32) {
+      const float f = (float)(row[i] - mean);
+      if (f32_out) f32_out[j * N + i] = f;
+      row[i] = (double)f;
+      s2 += (double)f;
+    }
+    s2 = warp_sum(s2);
+    const double mean2 = s2 / (double)N;
+    for (uint32_t i = lane; i < N; i += 32) row[i] -= mean2;
+  }
+}
+
+// float32 rows of a .residuals file ([rows][N]) -> padded doubles [rows][Np] (centred afterwards by k_center_rows)
+__global__ void k_pad_rows_f32(const float* __restrict__ src, uint64_t rows, uint32_t N, uint32_t Np,
+                               double* __restrict__ dst) {
+  const uint64_t total = rows * Np;
+  for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = idx / Np;
+    const uint32_t i = (uint32_t)(idx - r * Np);
+    dst[idx] = i < N ? (double)src[r * N + i] : 0.0;
+  }
+}
+
+// (I - U U^T) g for every SNP row g (LD.cpp:494): one warp per row, two sweeps over the samples
+// (t = U^T g in registers / shared memory, then g -= U t). U: [N][ldu] row-major, nk <= 64.
+__global__ void __launch_bounds__(256) k_project_out(double* __restrict__ Gs, uint64_t rows, uint32_t N, uint32_t Np,
+                                                      const double* __restrict__ U, int ldu, int nk) {
+  __shared__ double s_t[8][64];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t j = warp; j < rows; j += nwarps) {
+    double* row = Gs + j * Np;
+    for (int k0 = 0; k0 < nk; k0 += 8) {   // eight projections at a time
+      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (uint32_t i = lane; i < N; i += 32) {
+        const double g = row[i];
+        const double* u = U + (uint64_t)i * ldu + k0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (k0 + q < nk) t[q] = fma(u[q], g, t[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        t[q] = warp_sum(t[q]);
+        if (lane == 0 && k0 + q < nk) s_t[wib][k0 + q] = t[q];
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < N; i += 32) {
+      const double* u = U + (uint64_t)i * ldu;
+      double acc = 0.0;
+      for (int k = 0; k < nk; ++k) acc = fma(u[k], s_t[wib][k], acc);
+      row[i] -= acc;
+    }
+    __syncwarp();
+  }
+}
+
 struct LdArgs {
   const double* Gs;         // [rows][Np], chunk-local row 0 = SNP snp0
   uint32_t Np;              // padded sample count (multiple of 16)

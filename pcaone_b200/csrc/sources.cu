@@ -92,6 +92,33 @@ void block_af_if_needed(pcaone_ctx* c, const uint8_t* P, uint64_t s, uint64_t nr
   allele_freq_rows(c, P, s, nrows);
 }
 
+// Packed rows of SNPs [s0, s0 + nb) of a streamed source on the device (buffer 0, pitch layout), outside
+// the block plan: decode_block / residuals_block ask for arbitrary ranges. nb <= stage_range_max(c).
+// The caller records ev_done[0] on the compute stream when it is done with the rows.
+uint64_t stage_range_max(pcaone_ctx* c, uint64_t want) {
+  if (c->d_blk[0]) return std::min<uint64_t>(want, c->max_block);  // buffers are sized by the plan once streaming began
+  c->max_block = std::max(c->max_block, want);
+  return want;
+}
+const uint8_t* stage_range(pcaone_ctx* c, uint64_t s0, uint64_t nb) {
+  alloc_stream_buffers(c);
+  std::vector<uint64_t> sv = c->blk_start, ev = c->blk_stop;
+  c->blk_start = {s0};
+  c->blk_stop = {s0 + nb - 1};
+  const uint8_t* P = nullptr;
+  try {
+    P = stage_block(c, 0, 0);
+  } catch (...) {
+    c->blk_start = sv;
+    c->blk_stop = ev;
+    throw;
+  }
+  c->blk_start = sv;
+  c->blk_stop = ev;
+  c->staged_blk[0] = -1;
+  return P;
+}
+
 void snp_sqnorm(pcaone_ctx* c, double* out) {
   k_snp_sqnorm<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_packed, c->pitch, (uint32_t)c->N, c->M,
                                                                        c->d_F, c->lut, out);
@@ -391,38 +418,13 @@ int pcaone_decode_block(pcaone_ctx* c, uint64_t start, uint64_t stop, int standa
     p.standardize = (standardize && c->cfg.scale == -9) ? 1 : 0;
     const int emu = (update && c->cfg.emu) ? 1 : 0;
     if (emu && !c->have_usv) throw std::runtime_error("decode_block(update) without U,S,V");
-    // a streamed source is staged through buffer 0 in pieces no larger than the plan's blocks (the
-    // buffers are sized by the plan once streaming has begun)
+    // a streamed source is staged through buffer 0 in pieces no larger than the plan's blocks
     const bool streamed = c->source != PCAONE_SRC_RESIDENT;
-    uint64_t piece = B;
-    if (streamed) {
-      if (c->d_blk[0])
-        piece = std::min<uint64_t>(B, c->max_block);
-      else
-        c->max_block = std::max(c->max_block, B);
-      alloc_stream_buffers(c);
-    }
+    const uint64_t piece = streamed ? stage_range_max(c, B) : B;
     ensure_stage(c, c->N * piece);
     for (uint64_t s0 = start; s0 <= stop; s0 += piece) {
       const uint64_t nb = std::min<uint64_t>(piece, stop - s0 + 1);
-      const uint8_t* P;
-      if (!streamed) {
-        P = c->d_packed + s0 * c->pitch;
-      } else {
-        std::vector<uint64_t> sv = c->blk_start, ev = c->blk_stop;
-        c->blk_start = {s0};
-        c->blk_stop = {s0 + nb - 1};
-        try {
-          P = stage_block(c, 0, 0);
-          c->staged_blk[0] = -1;
-        } catch (...) {
-          c->blk_start = sv;
-          c->blk_stop = ev;
-          throw;
-        }
-        c->blk_start = sv;
-        c->blk_stop = ev;
-      }
+      const uint8_t* P = streamed ? stage_range(c, s0, nb) : c->d_packed + s0 * c->pitch;
       if (!c->af_done) allele_freq_rows(c, P, s0, nb);
       Timed t(c, 6);
       k_decode_block<<<grid_for(((c->N + 3) / 4) * nb, 256, c->sms), 256, 0, c->stream>>>(

@@ -266,28 +266,20 @@ void Data::write_residuals(const Mat1D& S, const Mat2D& U, const Mat2D& VT) {
   std::fwrite(&m32, 4, 1, fp);
   std::fwrite(&n32, 4, 1, fp);
   const uint64 bytes_per_snp = nsamples * 4, magic = 8;
-  const uint64 B = std::max<uint64>(1, std::min<uint64>(nsnps, (256ull << 20) / (nsamples * 8)));
-  std::vector<float> fg(nsamples);
-  const uint k = (uint)S.size();
+  // the float32 rows come from the device (pcaone_residuals_block: decode, G -= U S V^T from the
+  // context's U, S, V, column-centre, cast) — resident or streamed through the block plan's buffers
+  (void)S;
+  (void)U;
+  (void)VT;
+  const uint64 B = std::max<uint64>(1, std::min<uint64>(nsnps, (256ull << 20) / (nsamples * 4)));
+  std::vector<float> fg(B * nsamples);
   for (uint64 s = 0; s < nsnps; s += B) {
     const uint64 e = std::min(nsnps, s + B) - 1;
-    read_block_initial(s, e, false);
+    check(pcaone_residuals_block(ctx, s, e, params.ld_stats, fg.data()));
     for (uint64 ib = 0; ib <= e - s; ++ib) {
-      double* g = G.data() + ib * nsamples;
-      if (params.ld_stats == 0) {
-        for (uint c = 0; c < k; ++c) {
-          const double sv = S(c) * VT(c, s + ib);
-          const double* u = U.data() + (uint64)c * nsamples;
-          for (uint64 i = 0; i < nsamples; ++i) g[i] -= u[i] * sv;
-        }
-      }
-      double mean = 0;
-      for (uint64 i = 0; i < nsamples; ++i) mean += g[i];
-      mean /= (double)nsamples;
-      for (uint64 i = 0; i < nsamples; ++i) fg[i] = (float)(g[i] - mean);
       const uint64 orig = perm.empty() ? s + ib : perm[s + ib];
       fseeko(fp, (off_t)(magic + orig * bytes_per_snp), SEEK_SET);
-      std::fwrite(fg.data(), 4, nsamples, fp);
+      std::fwrite(fg.data() + ib * nsamples, 4, nsamples, fp);
     }
   }
   std::fclose(fp);

@@ -231,3 +231,33 @@ def test_cli_beagle_pcangsd_vs_reference_golden(tmp_path):
     U2, S2, V2 = _load(out2, k, M)
     assert col_cos(U2[:, :1], U[:, :1]).min() > 0.99 and V2.shape == (M, k)
     assert _run(["--beagle", bgl, "-m", "0.001", "-o", out], ok=False).returncode != 0   # Cmd.cpp:233
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mem,svd", [(0, 1), (0.02, 1), (0.02, 2)])
+def test_cli_ld_residuals_vs_reference(tmp_path, mem, svd):
+    """--ld [-m]: <out>.residuals (Data::write_residuals, Data.cpp:242-291 — float32 rows at their ORIGINAL SNP
+    positions, un-permuted by seek) against the file the unmodified reference writes for the same command.
+    The float rows come from pcaone_residuals_block (resident, or streamed through the block plan's buffers)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, k, maxp = 300, 12000, 3, 7
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=5, seed=41, miss=0.01)
+    memf = f"-m {mem}" if mem else ""
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d {svd} {memf} --ld -o {tmp_path}/r --maxp {maxp} --tol-rsvd 0 -n 8 -w 16", threads=8)
+    r.new_op()
+    r.compute_usv(maxp, 0.0)
+    r.write_residuals()
+    r.close()
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "-k", k, "-d", svd, "--ld", "-o", out, "--maxp", maxp, "--tol-rsvd", 0, "-w", 16,
+          "--precision", "fp64"] + (["-m", mem] if mem else []))
+    a = np.fromfile(f"{tmp_path}/r.residuals", dtype=np.uint8)
+    b = np.fromfile(out + ".residuals", dtype=np.uint8)
+    assert a.size == b.size == 8 + 4 * N * M and np.array_equal(a[:8], b[:8])
+    ra, rb = a[8:].view(np.float32).reshape(M, N), b[8:].view(np.float32).reshape(M, N)
+    # U S V^T of two runs of a randomized SVD agree to ~1e-9 relative (7 epochs, tol 0): compare the residual rows
+    assert np.abs(ra - rb).max() <= 1e-5 * np.abs(ra).max()
+    assert np.array_equal(open(f"{tmp_path}/r.mbim").read().split()[:14], open(out + ".mbim").read().split()[:14])

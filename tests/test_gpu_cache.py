@@ -76,7 +76,8 @@ def test_cached_equals_streamed_equals_resident(svd, miss):
                         band_factor=d.bandFactor)
     oo.set_flags(False, True)
     U, S, V = oo.compute_usv(7, 0.0)
-    assert_usv_close(cached["U"], cached["S"], cached["V"], U, S, V, eig_rtol=1e-9, min_corr=1 - 1e-9)
+    otol = 1e-9 if miss == 0.0 else 1e-8   # (missing calls: the mask operand is rounded to 23 bits)
+    assert_usv_close(cached["U"], cached["S"], cached["V"], U, S, V, eig_rtol=otol, min_corr=1 - otol)
 
 
 def test_partial_cache_and_invalidation():

@@ -127,3 +127,78 @@ def test_ld_prune_vs_oracle(N, M, bp, chunk, tol, monkeypatch):
     keep = ld.ld_prune_big(op, None, ws, we, tol, od.F)
     assert np.array_equal(keep, orc.ld_prune(od.block(0, M - 1, False), ws, we, tol, od.F))
     op.close()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("ld_stats", [0, 1])
+def test_residuals_and_adjusted_ld_vs_live_reference(tmp_path, ld_stats):
+    """The ancestry-adjusted LD path end to end against the UNMODIFIED reference run here (oracle/_ref):
+    `PCAone -b X -k K --ld --ld-stats s` -> Data::write_residuals (Data.cpp:242-291) -> `PCAone -B X.residuals
+    --print-r2` (FileBin::read_all + ld_r2_big). On the device: pcaone_residuals_block (the float32 rows of the
+    file), pcaone_ld_r2_ex from those floats (-B) and straight from the bed without the file (PACKED_RESID)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref was not built")
+    N, M, k = 211, 1500, 3
+    prefix = str(tmp_path / "g")
+    packed = synth.write_bed(prefix, N, M, k_pop=4, seed=17, miss=0.01)
+    out = str(tmp_path / "a")
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 1 --ld --ld-stats {ld_stats} -o {out} --maxp 3 --tol-rsvd 0 -n 2", threads=2)
+    r.new_op()
+    U, S, V = r.compute_usv(3, 0.0)
+    r.write_residuals()
+    r.close()
+    raw = np.fromfile(out + ".residuals", dtype=np.uint8)
+    hdr = raw[:8].view(np.uint32)
+    assert tuple(hdr) == (M, N)
+    resid_ref = raw[8:].view(np.float32).reshape(M, N)
+    r2_ = ref.Ref(f"PCAone -B {out}.residuals -F {out}.mbim --print-r2 --ld-bp 1500 -o {out}2 -n 2", threads=2)
+    r2_ref, ws, we = r2_.ld_r2(out + ".mbim", 1500)
+    r2_.close()
+    assert len(r2_ref) > 1000
+
+    p = halko.Param(k=k, svd=1, ld=True)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    d.prepare()
+    op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+    op.setFlags(False, False)
+    op.setUSV(U, S, V)          # the same U, S, V the reference subtracted
+    # (1) the float32 rows of the .residuals file
+    path = str(tmp_path / "ours.residuals")
+    ld.write_residuals(op, path, ld_stats=ld_stats, chunk=400)
+    mine = np.fromfile(path, dtype=np.uint8)
+    assert np.array_equal(mine[:8], raw[:8])
+    resid = mine[8:].view(np.float32).reshape(M, N)
+    # identical up to float32 rounding of doubles that differ in the last bits (summation order of U S V^T / the mean)
+    scale = np.abs(resid_ref).max()
+    assert np.abs(resid - resid_ref).max() <= 2.5e-7 * scale
+    assert (resid == resid_ref).mean() > 0.98
+    # (2) -B: r2 from the reference's own file content
+    r2_b = ld.ld_from_residuals_file(op, resid_ref, ws, we)
+    np.testing.assert_allclose(r2_b, r2_ref, rtol=0, atol=1e-12)
+    # (3) straight from the bed, no file
+    r2_d = ld.ld_adjusted_from_bed(op, ws, we, ld_stats=ld_stats)
+    np.testing.assert_allclose(r2_d, r2_ref, rtol=0, atol=5e-7)
+    # pruning on the same operand: equal keep masks away from knife-edge pairs
+    tol = 0.1
+    if np.abs(r2_ref - tol).min() > 1e-5:
+        keep_b = ld.ld_from_residuals_file(op, resid_ref, ws, we, r2_tol=tol)
+        keep_d = ld.ld_adjusted_from_bed(op, ws, we, ld_stats=ld_stats, r2_tol=tol)
+        assert np.array_equal(keep_b, keep_d)
+    op.close()
+
+
+def test_ld_projected_from_bed_vs_oracle():
+    """bed + --USV: data->G = (I - U U^T) G (LD.cpp:491-496) on the device against numpy."""
+    N, M, k = 300, 1800, 4
+    packed = np.concatenate([synth.pack_codes(c) for _, c in synth.balding_nichols_codes(N, M, k_pop=5, seed=8)])
+    od = orc.OracleData(packed, N)
+    G = od.block(0, M - 1, False)
+    U, _ = np.linalg.qr(np.random.default_rng(1).standard_normal((N, k)))
+    Gp = G - U @ (U.T @ G)
+    chrom, pos = _bim(M, nchr=3)
+    ws, we = ld.divide_pos_by_window(chrom, pos, 4000)
+    op = _ctx(packed, N)
+    r2 = ld.ld_projected_from_bed(op, U, ws, we)
+    np.testing.assert_allclose(r2, orc.ld_r2(Gp, ws, we), rtol=0, atol=1e-11)
+    op.close()

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/s5_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s5_pytest.log
+tail -30 gpurun_out/s5_pytest.log
+PCAONE_ORTH_PROF=4 PCAONE_SMALL_PROF=3 timeout 300 python bench.py --scale 0.125 --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/s5_bench_s0125.log 2>&1
+tail -c 2500 gpurun_out/s5_bench_s0125.log
