@@ -1,0 +1,107 @@
+"""-m gpu: parity against the UNMODIFIED reference run here (oracle/_ref) at the shapes the target is quoted on,
+scaled so the CPU side finishes in tens of seconds:
+
+  configs[2]-shaped   N = M = 24k, k = 40 (l = 80), winSVD, out-of-core block plan, -w 64: the reference streams
+                      the bed from disk (FileBed::read_block_initial), the GPU side streams it from host memory
+                      into the HBM tile cache — same plan, same Omega, north_star tolerance
+  configs[3]-shaped   N = 2.5k x M = 25k, 10 % missing calls, --emu, k = 10
+  ill-conditioned     3 real PCs, k = 10 (BASELINE.md section 2's shape): both sides run all 21 epochs; stresses
+                      the data-driven shortcuts of the orthonormalisation (second Cholesky pass skipped for
+                      cond^2 <= 1e5, first-order T2) on a G whose trailing columns are noise
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_usv_close, col_cos
+from pcaone_b200 import _lib, halko, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.ref]
+
+
+def _ref_or_skip():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    return ref
+
+
+def _write(prefix, packed, N, k_pop):
+    synth.write_bed_from_packed(prefix, packed, N, k_pop=k_pop)
+
+
+def test_configs2_shape_out_of_core_vs_reference(tmp_path):
+    ref = _ref_or_skip()
+    N = M = 24_000
+    k, bands, maxp = 40, 64, 7
+    packed = synth.torch_packed(N, M, k_pop=k + 4, seed=5, device="cuda:0", chunk=4096).cpu().numpy()
+    prefix = str(tmp_path / "c3")
+    _write(prefix, packed, N, k + 4)
+    mem = 0.9   # GB: nblocks < bands -> the 64 blocks are the 64 windows, like -m at 500k x 500k (Data.cpp:66-69)
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 2 -m {mem} -S -w {bands} -o {tmp_path}/r --maxp {maxp} --tol-rsvd 0 -n 16",
+                threads=16)
+    r.new_op()
+    start, stop = r.block_plan()
+    Ur, Sr, Vr = r.compute_usv(maxp, 0.0)
+    epochs = r.last_epochs()
+    r.close()
+    p = halko.Param(k=k, svd=2, bands=bands, maxp=maxp, tol=0.0, no_shuffle=True, memory=mem, precision=_lib.PREC_INT8X3)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    d.prepare()
+    assert d.nblocks == len(start) == bands and np.array_equal(d.start, start) and np.array_equal(d.stop, stop)
+    op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+    op.setFlags(False, True)
+    op.computeUSV(maxp, 0.0)
+    assert op.epochs == epochs == maxp + 1
+    assert int(op.timers().cache_hits) >= maxp * bands       # passes 2.. came from the HBM tile cache
+    assert_usv_close(op.U, op.S, op.V, Ur, Sr, Vr)            # north_star: 1e-6 / 0.9999
+    assert np.max(np.abs(op.S ** 2 - Sr ** 2) / Sr ** 2) < 1e-9, "int8x3 keeps the eigenvalues to 1e-9 here"
+    op.close()
+
+
+def test_configs3_shape_emu_vs_reference(tmp_path):
+    ref = _ref_or_skip()
+    N, M, k = 2_500, 25_000, 10
+    packed = synth.torch_packed(N, M, k_pop=k + 2, miss=0.10, seed=6, device="cuda:0", chunk=4096).cpu().numpy()
+    prefix = str(tmp_path / "c4")
+    _write(prefix, packed, N, k + 2)
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 1 --emu -o {tmp_path}/r -n 16 --maxiter 8", threads=16)
+    r.new_op()
+    Ur, Sr, Vr, it_ref = r.run_em()
+    r.close()
+    for prec in (_lib.PREC_FP64, _lib.PREC_INT8X3):
+        p = halko.Param(k=k, svd=1, emu=True, maxiter=8, precision=prec)
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        d.prepare()
+        op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+        it = op.runEM()
+        assert it == it_ref
+        assert_usv_close(op.U, op.S, op.V, Ur, Sr, Vr)
+        op.close()
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP64, _lib.PREC_INT8X3])
+def test_ill_conditioned_three_real_pcs_k10(tmp_path, prec):
+    ref = _ref_or_skip()
+    N, M, k = 1_200, 30_000, 10
+    packed = synth.torch_packed(N, M, k_pop=4, seed=7, device="cuda:0", chunk=4096).cpu().numpy()   # 3 real PCs
+    prefix = str(tmp_path / "ill")
+    _write(prefix, packed, N, 4)
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 2 -S -o {tmp_path}/r -n 16", threads=16)   # defaults: maxp 20, tol 1e-4
+    r.new_op()
+    Ur, Sr, Vr = r.compute_usv(20, 1e-4)
+    epochs = r.last_epochs()
+    r.close()
+    p = halko.Param(k=k, svd=2, no_shuffle=True, precision=prec)
+    d = halko.FileBed(p, packed=packed, nsamples=N)
+    d.prepare()
+    op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+    op.setFlags(False, True)
+    op.computeUSV(p.maxp, p.tol)
+    assert op.epochs == epochs
+    # all 10 eigenvalues at the north_star tolerance; the 3 real PCs as vectors (the 7 below them are a
+    # near-degenerate noise cluster: any basis of it is a valid answer, their VALUES still agree)
+    assert np.max(np.abs(op.S ** 2 - Sr ** 2) / Sr ** 2) <= 1e-6
+    assert col_cos(op.U[:, :3], Ur[:, :3]).min() >= 0.9999
+    assert col_cos(op.V[:, :3], Vr[:, :3]).min() >= 0.9999
+    assert np.abs(op.U.T @ op.U - np.eye(k)).max() < 1e-10
+    op.close()
