@@ -92,6 +92,9 @@ int  pcaone_create(const pcaone_config* cfg, pcaone_ctx** out);
 void pcaone_destroy(pcaone_ctx* ctx);
 const char* pcaone_last_error(const pcaone_ctx* ctx); /* ctx may be NULL: creation errors */
 int  pcaone_abi_version(void);
+/* The arithmetic the context actually runs (PCAONE_PREC_*): an INT8Xs request whose s * (k + oversamples)
+ * exceeds the 256 columns of one UMMA falls back to the FP64 DMMA kernels at creation. */
+int  pcaone_precision(const pcaone_ctx* ctx);
 void* pcaone_stream(pcaone_ctx* ctx);                  /* the cudaStream_t all work runs on */
 int  pcaone_sync(pcaone_ctx* ctx);
 int  pcaone_set_allreduce(pcaone_ctx* ctx, pcaone_allreduce_fn fn, void* user);

@@ -71,9 +71,16 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     if (cfg->precision != PCAONE_PREC_FP64) {
       c->slices = cfg->precision;
       c->NP = (int)round_up((size_t)c->slices * c->l, 16);
-      if (c->NP > kTcMaxNP)
-        throw std::runtime_error("slices * (k + oversamples) must be <= 256 for the tensor-core path");
-      c->RT = c->NP <= 128 ? 2 : 1;
+      if (c->NP > kTcMaxNP) {
+        // the UMMA N dimension holds slices * l columns: beyond 256 the request runs on the FP64 DMMA
+        // kernels instead (the reference has no bound on k); pcaone_precision() tells the host
+        if (cfg->shard_samples) throw std::runtime_error("sample-sharded jobs need slices * (k + oversamples) <= 256");
+        c->slices = 0;
+        c->NP = 0;
+        c->cfg.precision = PCAONE_PREC_FP64;
+      } else {
+        c->RT = c->NP <= 128 ? 2 : 1;
+      }
     }
     c->bpr = (uint32_t)((c->N + 3) >> 2);
     c->pitch = (uint32_t)round_up(c->bpr, 16);
@@ -171,6 +178,7 @@ void pcaone_destroy(pcaone_ctx* c) {
   delete c;
 }
 
+int pcaone_precision(const pcaone_ctx* c) { return c ? c->cfg.precision : -1; }
 void* pcaone_stream(pcaone_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int pcaone_alloc_pinned(void** out, size_t bytes) {
   if (!out) return 1;

@@ -131,6 +131,8 @@ void Data::create_context() {
   cfg.tolem = params.tolem;
   svd_code = cfg.svd;
   if (pcaone_create(&cfg, &ctx)) cao.error(std::string(pcaone_last_error(nullptr)));
+  if (pcaone_precision(ctx) != cfg.precision)
+    cao.warn("--precision int8x* holds (k + oversamples) x slices <= 256 columns; this run uses the FP64 tensor-core kernels");
 }
 
 static std::pair<uint64, uint64> shard_range(uint64 n, int rank, int world) {

@@ -125,32 +125,32 @@ void make_plink2_eigenvec_file(int K, const std::string& fout, const std::string
 // ---------------------------------------------------------------------------- multi-GPU
 #ifdef PCAONE_WITH_NCCL
 namespace {
-struct NcclHook {
-  ncclComm_t comm;
-};
-int nccl_allreduce(void* user, void* buf, uint64_t count, void* stream) {
-  auto* h = static_cast<NcclHook*>(user);
-  return ncclAllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, h->comm, (cudaStream_t)stream) == ncclSuccess
-             ? 0
-             : 1;
-}
+// breakable barrier: a worker that throws releases the others instead of leaving them waiting
 class Barrier {
   std::mutex m;
   std::condition_variable cv;
   int count, waiting = 0, gen = 0;
+  bool broken = false;
 
  public:
   explicit Barrier(int n) : count(n) {}
   void wait() {
     std::unique_lock<std::mutex> lk(m);
+    if (broken) throw std::runtime_error("another GPU worker failed");
     const int g = gen;
     if (++waiting == count) {
       waiting = 0;
       ++gen;
       cv.notify_all();
     } else {
-      cv.wait(lk, [&] { return g != gen; });
+      cv.wait(lk, [&] { return g != gen || broken; });
+      if (broken) throw std::runtime_error("another GPU worker failed");
     }
+  }
+  void brk() {
+    std::lock_guard<std::mutex> lk(m);
+    broken = true;
+    cv.notify_all();
   }
 };
 }  // namespace
@@ -173,13 +173,21 @@ void run_pca_sharded(const Param& params) {
   Barrier bar(g);
   std::vector<std::string> errors(g);
   std::atomic<bool> failed{false};
+  std::mutex abort_m;
+  bool aborted = false;
+  auto abort_all = [&]() {  // peers blocked inside a collective return with an error instead of hanging
+    std::lock_guard<std::mutex> lk(abort_m);
+    if (aborted) return;
+    aborted = true;
+    for (auto& cm : comms) ncclCommAbort(cm);
+  };
   auto worker = [&](int rank) {
     Logger::muted = rank != 0;
     try {
       FileBed data(params, rank, g);
       data.prepare();
-      NcclHook hook{comms[rank]};
-      data.check(pcaone_set_allreduce(data.ctx, &nccl_allreduce, &hook));
+      // the library enqueues its collectives on this communicator itself (include/pcaone_b200.h)
+      data.check(pcaone_comm_attach(data.ctx, (void*)comms[rank]));
       run_pca_with_halko(&data, params, [&](RsvdOpData* op) {
         if (rank == 0) {
           Vfull.resize(data.nsnps, op->ranks());
@@ -203,12 +211,15 @@ void run_pca_sharded(const Param& params) {
     } catch (const std::exception& e) {
       errors[rank] = e.what();
       failed = true;
+      bar.brk();
+      abort_all();
     }
   };
   std::vector<std::thread> th;
   for (int r = 0; r < g; ++r) th.emplace_back(worker, r);
   for (auto& t : th) t.join();
-  for (auto& c : comms) ncclCommDestroy(c);
+  if (!aborted)
+    for (auto& c : comms) ncclCommDestroy(c);
   if (failed)
     for (auto& e : errors)
       if (!e.empty()) cao.error(e);

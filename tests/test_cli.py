@@ -261,3 +261,36 @@ def test_cli_ld_residuals_vs_reference(tmp_path, mem, svd):
     # U S V^T of two runs of a randomized SVD agree to ~1e-9 relative (7 epochs, tol 0): compare the residual rows
     assert np.abs(ra - rb).max() <= 1e-4 * np.abs(ra).max()
     assert np.array_equal(open(f"{tmp_path}/r.mbim").read().split()[:14], open(out + ".mbim").read().split()[:14])
+
+
+@pytest.mark.gpu
+def test_cli_large_k_falls_back_to_fp64(tmp_path):
+    """-k 45 with the default --precision int8x3 needs 3 x 90 > 256 UMMA columns: the library runs the FP64
+    kernels instead of refusing (the reference has no bound on k) and the front-end says so."""
+    N, M, k = 300, 4000, 45
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=50, seed=43)
+    out = str(tmp_path / "o")
+    r = _run(["-b", prefix, "-k", k, "-d", 1, "-o", out, "--maxp", 3, "--tol-rsvd", 0])
+    assert "FP64" in r.stdout + r.stderr
+    S = np.loadtxt(out + ".sigvals", ndmin=1)
+    assert S.shape == (k,) and np.all(np.diff(S) <= 0)
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_in_one_process(tmp_path):
+    """--gpus 2: one host thread per GPU in ONE process (per-context kernel attributes, library-side NCCL
+    through pcaone_comm_attach) equals the one-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    N, M, k, maxp = 500, 20000, 5, 6
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=7, seed=44)
+    one, two = str(tmp_path / "o1"), str(tmp_path / "o2")
+    _run(["-b", prefix, "-k", k, "-d", 2, "-S", "-o", one, "--maxp", maxp, "--tol-rsvd", 0, "-V"])
+    _run(["-b", prefix, "-k", k, "-d", 2, "-S", "-o", two, "--maxp", maxp, "--tol-rsvd", 0, "-V", "--gpus", 2])
+    U1, S1, V1 = _load(one, k, M)
+    U2, S2, V2 = _load(two, k, M)
+    assert np.max(np.abs(S1 - S2) / S1) < 1e-5
+    assert col_cos(U1, U2).min() > 0.9999 and col_cos(V1, V2).min() > 0.9999
