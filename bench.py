@@ -48,8 +48,9 @@ WORKLOADS = {
     "c3": (500_000, 500_000, 40, True, "configs[2]: UK-Biobank-scale bed, winSVD, out-of-core block plan"),
     "c2": (10_000, 1_000_000, 20, False, "configs[1]: winSVD in-memory"),
 }
-CPU_SAMPLES_BASELINE = 1024   # cpu_baseline leg: this many samples x ALL SNPs, one full PCA
-CPU_SAMPLES_REF_ARM = 256     # --impl reference: K + W full PCAs must end within minutes
+CPU_SAMPLES_BASELINE = 1024   # cpu_baseline leg: this many samples x ALL SNPs, one full PCA (44.6 s on the box's 16 cores)
+CPU_SAMPLES_REF_ARM = 256     # --impl reference: K + W full PCAs must end within minutes, so the sample is 256 samples x
+CPU_SNP_FRACTION_REF_ARM = 8  # every 8th of the SNP axis (a PCA on 256 x 500k took 37 s; per-pass time scales with N x M)
 
 
 def _peaks():
@@ -142,7 +143,7 @@ def workload_dims(args):
     return n, m, k, ooc, desc
 
 
-def cpu_reference_pca(n_s, m, k, pcas, warm, threads, seed=1):
+def cpu_reference_pca(n_s, m, k, pcas, warm, threads, seed=1, m_s=None):
     """The reference's own CPU computeUSV (oracle/_ref = unmodified PCAone, winSVD in-core, -S, defaults
     --maxp 20 --tol-rsvd 1e-4) on a bounded sample: n_s samples of the same population model x ALL m
     SNPs. Sampling the SAMPLE axis keeps both the per-pass GEMM work and the Omega-update work
@@ -154,7 +155,7 @@ def cpu_reference_pca(n_s, m, k, pcas, warm, threads, seed=1):
     if not ref.available():
         return None
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    packed = synth.torch_packed(n_s, m, k_pop=k + 4, seed=seed, device=dev, chunk=8192).cpu().numpy()
+    packed = synth.torch_packed(n_s, m_s or m, k_pop=k + 4, seed=seed, device=dev, chunk=8192).cpu().numpy()
     tmp = tempfile.mkdtemp(prefix="pcaone_cpu_")
     prefix = os.path.join(tmp, "s")
     synth.write_bed_from_packed(prefix, packed, n_s)
@@ -185,22 +186,25 @@ def run_reference_arm(args, rank):
     n, m, k, ooc, desc = workload_dims(args)
     threads = os.cpu_count() or 1
     n_s = min(n, CPU_SAMPLES_REF_ARM)
-    res = cpu_reference_pca(n_s, m, k, args.steps, min(args.warmup, 1), threads)
+    m_s = max(BANDS * 64, m // CPU_SNP_FRACTION_REF_ARM)
+    res = cpu_reference_pca(n_s, m, k, args.steps, min(args.warmup, 1), threads, m_s=m_s)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpcaone_ref.so was not built"}))
         return
     tot = sum(res["times"])
     passes = sum(res["epochs"])
     val = res["bytes_per_pass"] * passes / tot / 1e9
-    sample = (f"{n_s} of {n} samples (same population model) x all {m} SNPs, unmodified PCAone winSVD in-core -S, "
+    scale_up = (n / n_s) * (m / m_s)
+    sample = (f"{n_s} of {n} samples (same population model) x {m_s} of {m} SNPs, unmodified PCAone winSVD in-core -S, "
               f"defaults --maxp 20 --tol-rsvd 1e-4: {res['epochs'][0]} epochs per PCA, {tot / len(res['times']):.2f} s per PCA "
-              f"on the sample (x {n / n_s:.0f} for the full sample count); Eigen built-in GEMM, no MKL; "
+              f"on the sample; GEMM and Omega-update work per pass both scale with samples x SNPs, so packed GB/s per pass "
+              f"carries over and time to PCs scales by {scale_up:.0f}; Eigen built-in GEMM, no MKL; "
               f"{min(args.warmup, 1)} warm-up PCA")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(res["times"]), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "time_to_pcs_s": tot / len(res["times"]) * n / n_s,
-            "time_to_pcs_note": f"measured on {n_s} samples, scaled by N / {n_s}",
+            "time_to_pcs_s": tot / len(res["times"]) * scale_up,
+            "time_to_pcs_note": f"measured on {n_s} samples x {m_s} SNPs, scaled by {scale_up:.0f}",
             "config": {"workload": f"{desc}, N={n} x M={m}, k={k} (bounded CPU sample)", "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -385,15 +389,19 @@ def main():
         int8_peak = json.load(open(os.path.join(ROOT, "profiles", "r02_int8_peak.json")))
     except Exception:
         pass
+    nl = int(tm.gemm_h_launches if "H pass" in dom else tm.gemm_g_launches)
+    packed_per_launch = bytes_per_pass / world * ep_i / max(nl, 1)   # algorithmic packed bytes of an average launch
     traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_gemm_traffic.json")))
         leg = tj["h_pass" if "H pass" in dom else "g_pass"]
-        traffic = leg["dram_read_bytes"] + leg["dram_write_bytes"]
-        traffic_note = f"bytes per launch of one block ({tj['what']}), ncu dram__bytes_read.sum + dram__bytes_write.sum, {tj['source']}"
+        traffic = leg["ratio"] * packed_per_launch
+        traffic_note = (f"per launch: {leg['ratio']:.3f} x the {packed_per_launch / 1e9:.2f} GB of packed operand an average launch reads; "
+                        f"the ratio (dram__bytes_read.sum + dram__bytes_write.sum over algorithmic packed bytes) is from ONE ncu --set "
+                        f"full capture at 1/4 linear scale ({tj['source']}): kernel replay cannot save / restore the 130 GB of the "
+                        f"full-size run; tensor pipe active {leg['tensor_pipe_active_pct']} % in that capture")
     except Exception:
         pass
-    nl = int(tm.gemm_h_launches if "H pass" in dom else tm.gemm_g_launches)
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json has no int8 entry)",
@@ -411,7 +419,8 @@ def main():
     if int8_peak:
         ip = int8_peak.get("int8_dense_tops")
         roofline["int8_peak_tops"] = ip
-        roofline["frac_of_int8_over_slices"] = achieved_tf / (ip / 2.0 / prec) if (achieved_tf and ip) else None
+        # the tensor cores execute prec x the algorithmic flops as int8 ops: fraction of the measured kind::i8 rate
+        roofline["frac_of_int8_peak"] = achieved_tf * prec / ip if (achieved_tf and ip) else None
         roofline["int8_peak_source"] = int8_peak.get("source")
     # one late pass on its own (pi >= 6: plain power iteration, one Omega update)
     op.timers(reset=True)
