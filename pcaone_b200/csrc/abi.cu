@@ -130,6 +130,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     PCA_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
     dmalloc(&c->d_jscratch, (size_t)2 * c->l * c->l + 2 * c->l + 8);
     if (const char* e = getenv("PCAONE_FUSED_ORTH")) c->fused_orth = atoi(e);
+    if (const char* e = getenv("PCAONE_ORTH_ONE_SHOT")) c->one_shot_q = atoi(e);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
     c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;

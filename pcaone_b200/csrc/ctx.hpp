@@ -142,6 +142,7 @@ struct pcaone_ctx {
   bool g_is_q = false;                                 // d_G holds Q = G T after small_stage (else raw G)
   double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
   int fused_orth = 1;                                  // PCAONE_FUSED_ORTH=0 selects the multi-kernel path
+  int one_shot_q = 1;                                  // int8 route: Omega = H (T1 T2) in one tile product (PCAONE_ORTH_ONE_SHOT=0: two)
 
   // sharded jobs
   pcaone_allreduce_fn allreduce = nullptr;             // host hook (double sums only)

@@ -130,6 +130,7 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
                 bool flip, int phases = 7, unsigned long long* colmax_out = nullptr, double* flipbuf = nullptr) {
   OrthArgs a{};
   a.flipbuf = flipbuf;
+  a.one_shot = (Q != nullptr && c->slices > 0 && c->one_shot_q) ? 1 : 0;
   a.phases = phases;
   a.colmax_out = colmax_out;
   a.A = A;

@@ -29,7 +29,9 @@ namespace pcaone {
 namespace cg = cooperative_groups;
 
 constexpr int kOrthThreads = 256;
-__host__ __device__ constexpr int orth_tile_rows(int R) { return R <= 4 ? 64 : 32; }  // rows per staged tile
+// rows per staged tile. 64-row tiles at R = 5 fit since the sign replay's l x l block moved to global scratch, but
+// measured SLOWER on the B200 (P1 318 vs 288 us, P4 527 vs 495 us at 500k x 80): 32 rows keep more tiles in flight per SM
+__host__ __device__ constexpr int orth_tile_rows(int R) { return R <= 4 ? 64 : 32; }
 
 struct OrthArgs {
   const double* A;   // [rows][lp] input (H or G); may alias Q
@@ -68,13 +70,17 @@ struct OrthArgs {
   // the top l rows (want_signs) — the Householder signs in flipbuf[3 l] = {dsum, ssum, hsign} and
   // stops; the host sums flipbuf over the ranks and a launch with phases = 8 applies hsign * flip.
   double* flipbuf;
+  // int8 route: write Q = A (T1 T2) with ONE tile product instead of (A T1) T2. The two forms differ by
+  // ~eps * cond(A) in the orthogonality of Q (1e-13 here); the int8 route rounds Omega to 8S-1 = 23 bits
+  // right after, so the difference cannot be seen, and a third of the sweep's flops go away.
+  int one_shot;
 };
 
 // shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
 // (= 4 mod 16), which makes every DMMA fragment load below bank-conflict free
 __host__ __device__ inline size_t orth_smem_bytes(int l, int R) {
   const int LD = 16 * R + 4;
-  return ((size_t)2 * l * LD + (size_t)2 * orth_tile_rows(R) * LD + (size_t)l * l) * sizeof(double);
+  return ((size_t)2 * l * LD + (size_t)2 * orth_tile_rows(R) * LD) * sizeof(double);
 }
 
 // W (l x l, row-major ld, global) -> T (l x l row-major ld, global) with (A T) orthonormal:
@@ -343,7 +349,8 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   double* T2s = T1s + (size_t)a.l * LD;               // [l][LD]
   double* As = T2s + (size_t)a.l * LD;                // [TR][LD]
   double* Qs = As + TR * LD;                          // [TR][LD]
-  double* Ws = Qs + TR * LD;                          // [l][l]
+  double* Ws = a.jscratch;                            // [l][l] in GLOBAL scratch (CTA 0 only, the sign replay's top block):
+                                                      // keeping it out of shared memory lets R = 5 stage 64-row tiles too
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const int fg = lane >> 2, ft = lane & 3;            // DMMA fragment coordinates (common.cuh dmma884)
   const int m0 = (warp % MT) * 8;                     // this warp's row tile in tile x factor products
@@ -626,6 +633,25 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
       } else {
         orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
       }
+      if (a.one_shot && a.Q) {  // T2s / T2g <- T1 T2 (both upper triangular) before anybody else reads T2
+        double* tmp = As;  // [l][LC]: the tile buffers (As, Qs are contiguous) are idle in this phase
+        for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
+          const int r = idx / LC, c = idx - r * LC;
+          double acc = 0.0;
+          if (c < l && r <= c)
+            for (int k = r; k <= c; ++k) acc += T1s[r * LD + k] * T2s[k * LD + c];
+          tmp[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
+          const int r = idx / LC, c = idx - r * LC;
+          T2s[r * LD + c] = tmp[idx];
+          if (c < lp) a.T2g[r * lp + c] = tmp[idx];
+        }
+        __syncthreads();
+        zero_pad_cols();
+        __syncthreads();
+      }
       stamp();
     }
     if (blockIdx.x == 0 && stage == (overlap ? 1 : 0)) {
@@ -650,10 +676,14 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
           }
           __syncthreads();
           double q[NPW][2];
-          tile_times_T(As, T1s, q);
-          store_tile(Qs, q);
-          __syncthreads();
-          tile_times_T(Qs, T2s, q);
+          if (a.one_shot) {
+            tile_times_T(As, T2s, q);  // T2s holds T1 T2
+          } else {
+            tile_times_T(As, T1s, q);
+            store_tile(Qs, q);
+            __syncthreads();
+            tile_times_T(Qs, T2s, q);
+          }
 #pragma unroll
           for (int n = 0; n < NPW; ++n)
 #pragma unroll
@@ -768,16 +798,25 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         }
       }
     }
+    const double* Res = a.one_shot ? Qs : As;  // where the tile of Q ends up
     {
       double q[NPW][2];
-      tile_times_T(As, T1s, q);
-      store_tile(Qs, q);
-      __syncthreads();
-      stamp();
-      tile_times_T(Qs, T2s, q);
-      store_tile(As, q);  // every warp finished reading As before the barrier above
-      __syncthreads();
-      stamp();
+      if (a.one_shot) {
+        tile_times_T(As, T2s, q);  // T2s holds T1 T2
+        store_tile(Qs, q);
+        __syncthreads();
+        stamp();
+        stamp();
+      } else {
+        tile_times_T(As, T1s, q);
+        store_tile(Qs, q);
+        __syncthreads();
+        stamp();
+        tile_times_T(Qs, T2s, q);
+        store_tile(As, q);  // every warp finished reading As before the barrier above
+        __syncthreads();
+        stamp();
+      }
     }
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
@@ -787,7 +826,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         for (int j = 0; j < R; ++j) {
           const int c = tx + 16 * j;
           if (c < lp) {
-            const double qv = c < l ? As[(ty + 16 * i) * LD + c] * hs[j] : 0.0;
+            const double qv = c < l ? Res[(ty + 16 * i) * LD + c] * hs[j] : 0.0;
             amax[j] = fmax(amax[j], fabs(qv));
             if (a.want_flip && c < l) {
               dsum[j] += fabs(o2[i][j] - qv);
