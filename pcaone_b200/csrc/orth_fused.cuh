@@ -634,22 +634,21 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
       }
       if (a.one_shot && a.Q) {  // T2s / T2g <- T1 T2 (both upper triangular) before anybody else reads T2
-        double* tmp = As;  // [l][LC]: the tile buffers (As, Qs are contiguous) are idle in this phase
-        for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
-          const int r = idx / LC, c = idx - r * LC;
+        double* tmp = a.jscratch + (size_t)l * l;  // [l][l] global scratch (second half; the first holds the sign replay's block)
+        for (int idx = tid; idx < l * l; idx += kOrthThreads) {
+          const int r = idx / l, c = idx - r * l;
           double acc = 0.0;
-          if (c < l && r <= c)
+          if (r <= c)
             for (int k = r; k <= c; ++k) acc += T1s[r * LD + k] * T2s[k * LD + c];
           tmp[idx] = acc;
         }
         __syncthreads();
-        for (int idx = tid; idx < l * LC; idx += kOrthThreads) {
-          const int r = idx / LC, c = idx - r * LC;
-          T2s[r * LD + c] = tmp[idx];
-          if (c < lp) a.T2g[r * lp + c] = tmp[idx];
+        for (int idx = tid; idx < l * l; idx += kOrthThreads) {
+          const int r = idx / l, c = idx - r * l;
+          const double v = tmp[idx];
+          T2s[r * LD + c] = v;
+          a.T2g[r * lp + c] = v;
         }
-        __syncthreads();
-        zero_pad_cols();
         __syncthreads();
       }
       stamp();

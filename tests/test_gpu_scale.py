@@ -56,6 +56,19 @@ def test_configs2_shape_out_of_core_vs_reference(tmp_path):
     assert_usv_close(op.U, op.S, op.V, Ur, Sr, Vr)            # north_star: 1e-6 / 0.9999
     assert np.max(np.abs(op.S ** 2 - Sr ** 2) / Sr ** 2) < 1e-9, "int8x3 keeps the eigenvalues to 1e-9 here"
     op.close()
+    # the precision mode is chosen by measured accuracy (north_star): the 2-slice route (15-bit operands, a third
+    # less tensor work) on the same bed against the same reference run
+    p2 = halko.Param(k=k, svd=2, bands=bands, maxp=maxp, tol=0.0, no_shuffle=True, memory=mem, precision=_lib.PREC_INT8X2)
+    d2 = halko.FileBed(p2, packed=packed, nsamples=N)
+    d2.prepare()
+    op2 = halko.FancyRsvdOpData(d2, p2.k, p2.oversamples)
+    op2.setFlags(False, True)
+    op2.computeUSV(maxp, 0.0)
+    e2 = float(np.max(np.abs(op2.S ** 2 - Sr ** 2) / Sr ** 2))
+    c2 = float(min(col_cos(op2.U, Ur).min(), col_cos(op2.V, Vr).min()))
+    print(f"int8x2 vs reference: eigenvalue rel err {e2:.3e}, min |cos| {c2:.10f}")
+    assert e2 <= 1e-6 and c2 >= 0.9999
+    op2.close()
 
 
 def test_configs3_shape_emu_vs_reference(tmp_path):
