@@ -107,6 +107,13 @@ int  pcaone_set_allreduce2(pcaone_ctx* ctx, pcaone_allreduce2_fn fn, void* user)
 int  pcaone_comm_unique_id(uint8_t* out128);
 int  pcaone_comm_init(pcaone_ctx* ctx, const uint8_t* id128, int rank, int world);
 int  pcaone_comm_attach(pcaone_ctx* ctx, void* nccl_comm);
+/* Peer-memory mailboxes for sample-sharded jobs with one process per GPU: every rank exports a 64-byte CUDA IPC
+ * handle of its mailbox, the host gathers the world's handles (rank order) and hands them to every rank. The
+ * row-sharded Omega update then runs as ONE cooperative launch whose three small exchanges (two l x l Gram
+ * matrices; flipOmg sums + Householder signs + column maxima) are NVLink stores into the peers' mailboxes inside the
+ * kernel, instead of three NCCL launches between four kernel launches. PCAONE_PEER_EXCHANGE=0 keeps the NCCL form. */
+int  pcaone_comm_peer_export(pcaone_ctx* ctx, uint8_t* out64);
+int  pcaone_comm_peer_import(pcaone_ctx* ctx, const uint8_t* handles, int nranks);
 /* Page-locked host buffers for the packed bed (FileBed::inbed, FilePlink.hpp:43-46): a host that
  * reads the .bed into one of these gets full-rate cudaMemcpyAsync in upload / streaming. */
 int  pcaone_alloc_pinned(void** out, size_t bytes);

@@ -61,7 +61,7 @@ SYMBOLS = [
     "pcaone_upload_dense", "pcaone_dense_rsvd", "pcaone_upload_dosage", "pcaone_perform_op", "pcaone_ld_prune", "pcaone_xt_times", "pcaone_x_times",
     "pcaone_upload_gl", "pcaone_gl_em_maf",
     "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
-    "pcaone_ld_r2_ex", "pcaone_residuals_block", "pcaone_precision",
+    "pcaone_ld_r2_ex", "pcaone_residuals_block", "pcaone_precision", "pcaone_comm_peer_export", "pcaone_comm_peer_import",
 ]
 
 _lib = None
@@ -105,7 +105,7 @@ def load():
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
         "pcaone_comm_unique_id": [vp], "pcaone_comm_init": [vp, vp, i32, i32], "pcaone_comm_attach": [vp, vp],
         "pcaone_ld_r2_ex": [vp, C.POINTER(LdSource), u64, vp, vp, u64, vp, vp, dbl, vp],
-        "pcaone_residuals_block": [vp, u64, u64, i32, vp], "pcaone_precision": [vp],
+        "pcaone_residuals_block": [vp, u64, u64, i32, vp], "pcaone_precision": [vp], "pcaone_comm_peer_export": [vp, vp], "pcaone_comm_peer_import": [vp, vp, i32],
         "pcaone_set_host_source2": [vp, vp, u64, u64], "pcaone_set_allreduce2": [vp, ALLREDUCE2_FN, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

@@ -124,7 +124,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     dmalloc(&c->d_sigma, c->lp);
     dmalloc(&c->d_sign, c->lp);
     dmalloc(&c->d_hsign, c->lp);
-    dmalloc(&c->d_flipbuf, 3 * (size_t)c->lp);
+    dmalloc(&c->d_flipbuf, 4 * (size_t)c->lp);
     dmalloc(&c->d_scal, 64);
     dmalloc(&c->d_status, 4);
     PCA_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(int)));

@@ -111,6 +111,15 @@ void comm_group_end(pcaone_ctx* c) {
 }
 
 void comm_destroy(pcaone_ctx* c) {
+  for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
+  c->peer_opened.clear();
+  if (c->d_mbox) cudaFree(c->d_mbox);
+  if (c->d_peer_mbox) cudaFree(c->d_peer_mbox);
+  if (c->d_peer_flag) cudaFree(c->d_peer_flag);
+  c->d_mbox = nullptr;
+  c->d_peer_mbox = nullptr;
+  c->d_peer_flag = nullptr;
+  c->peer_ready = false;
   if (!c->comm) return;
   if (c->comm->owned && c->comm->comm && api().CommDestroy) api().CommDestroy(c->comm->comm);
   delete c->comm;
@@ -153,6 +162,54 @@ int pcaone_set_allreduce2(pcaone_ctx* c, pcaone_allreduce2_fn fn, void* user) {
   CTX_GUARD(c, {
     c->allreduce2 = fn;
     c->allreduce2_user = user;
+  });
+}
+
+// Peer-memory mailboxes (one process per GPU): every rank exports its mailbox as a CUDA IPC handle, the host
+// gathers the world's handles, every rank imports them. From then on the row-sharded Omega update is ONE
+// cooperative launch whose three small exchanges run inside the kernel over NVLink (orth_fused.cuh).
+static constexpr int kSlots = 4;   // == kPeerSlots of orth_fused.cuh
+int pcaone_comm_peer_export(pcaone_ctx* c, uint8_t* out64) {
+  CTX_GUARD(c, {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (c->cfg.world < 2 || c->cfg.world > 16) throw std::runtime_error("peer_export: world must be 2..16");
+    if (!c->d_mbox) {
+      const size_t data = (size_t)kSlots * c->cfg.world * c->l * c->lp * sizeof(double);
+      c->mbox_flag_off = round_up(data, 256);
+      c->mbox_bytes = c->mbox_flag_off + (size_t)kSlots * c->cfg.world * sizeof(unsigned long long);
+      PCA_CUDA(cudaMalloc((void**)&c->d_mbox, c->mbox_bytes));
+      PCA_CUDA(cudaMemset(c->d_mbox, 0, c->mbox_bytes));
+    }
+    cudaIpcMemHandle_t hnd;
+    PCA_CUDA(cudaIpcGetMemHandle(&hnd, c->d_mbox));
+    memcpy(out64, &hnd, sizeof(hnd));
+  });
+}
+
+int pcaone_comm_peer_import(pcaone_ctx* c, const uint8_t* handles, int nranks) {
+  CTX_GUARD(c, {
+    if (nranks != c->cfg.world || !c->d_mbox) throw std::runtime_error("peer_import: call pcaone_comm_peer_export first, pass world handles");
+    std::vector<double*> mb(nranks);
+    std::vector<unsigned long long*> fl(nranks);
+    for (int r = 0; r < nranks; ++r) {
+      void* base = nullptr;
+      if (r == c->cfg.rank) {
+        base = c->d_mbox;
+      } else {
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, handles + (size_t)r * 64, sizeof(hnd));
+        PCA_CUDA(cudaIpcOpenMemHandle(&base, hnd, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened.push_back(base);
+      }
+      mb[r] = reinterpret_cast<double*>(base);
+      fl[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + c->mbox_flag_off);
+    }
+    PCA_CUDA(cudaMalloc((void**)&c->d_peer_mbox, nranks * sizeof(double*)));
+    PCA_CUDA(cudaMalloc((void**)&c->d_peer_flag, nranks * sizeof(unsigned long long*)));
+    PCA_CUDA(cudaMemcpy(c->d_peer_mbox, mb.data(), nranks * sizeof(double*), cudaMemcpyHostToDevice));
+    PCA_CUDA(cudaMemcpy(c->d_peer_flag, fl.data(), nranks * sizeof(unsigned long long*), cudaMemcpyHostToDevice));
+    c->peer_seq = 1;
+    c->peer_ready = getenv("PCAONE_PEER_EXCHANGE") ? atoi(getenv("PCAONE_PEER_EXCHANGE")) != 0 : true;
   });
 }
 

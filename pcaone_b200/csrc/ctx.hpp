@@ -150,6 +150,14 @@ struct pcaone_ctx {
   pcaone_allreduce2_fn allreduce2 = nullptr;           // typed host hook (any transport)
   void* allreduce2_user = nullptr;
   pcaone_comm* comm = nullptr;                         // in-library NCCL communicator (comm.cu)
+  // peer-memory mailboxes for the in-kernel exchanges of the row-sharded Omega update (orth_fused.cuh)
+  double* d_mbox = nullptr;                            // this rank's mailbox [slots][world][l * lp] + flags behind it
+  size_t mbox_bytes = 0, mbox_flag_off = 0;
+  std::vector<void*> peer_opened;                      // cudaIpcOpenMemHandle'd bases (closed at destroy)
+  double** d_peer_mbox = nullptr;                      // device array [world] of mailbox pointers
+  unsigned long long** d_peer_flag = nullptr;          // device array [world] of flag-array pointers
+  unsigned long long peer_seq = 1;                     // next exchange sequence number
+  bool peer_ready = false;
   bool shard_samples = false;                          // rows of X^T (samples) sharded instead of SNPs
   uint64_t N_total = 0;                                // samples of the whole job (== N unless shard_samples)
   uint64_t samp0 = 0;                                  // first global sample of this rank (shard_samples)

@@ -131,6 +131,15 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
   OrthArgs a{};
   a.flipbuf = flipbuf;
   a.one_shot = (Q != nullptr && c->slices > 0 && c->one_shot_q) ? 1 : 0;
+  if (flipbuf && phases == 7) {  // single-launch row-sharded update: in-kernel exchanges over peer memory
+    if (!c->peer_ready) throw std::runtime_error("orth_fused: peer mailboxes are not set up");
+    a.peer_world = c->cfg.world;
+    a.peer_rank = c->cfg.rank;
+    a.peer_mbox = c->d_peer_mbox;
+    a.peer_flag = c->d_peer_flag;
+    a.peer_seq = c->peer_seq;
+    c->peer_seq += 3;
+  }
   a.phases = phases;
   a.colmax_out = colmax_out;
   a.A = A;
@@ -238,6 +247,15 @@ void update_omega_sharded(pcaone_ctx* c, const double* H, bool flip) {
   if (top && c->N < (uint64_t)c->l) throw std::runtime_error("sample shard of rank 0 is shorter than k + oversamples");
   unsigned long long* cm = (c->slices > 0 && c->d_tcs) ? c->d_tcs : nullptr;
   double* Q2 = flip ? c->d_Omg2 : nullptr;
+  if (c->peer_ready) {
+    // ONE cooperative launch: the Gram / flip exchanges run inside the kernel over peer memory (NVLink stores into
+    // the peers' mailboxes), no NCCL launch and no extra kernel launch per exchange
+    orth_fused(c, H, c->N, c->d_Omg, Q2, nullptr, top, flip, 7, cm, c->d_flipbuf);
+    c->tm.omega_updates++;
+    c->omega_img_valid = false;
+    c->omega_colmax_valid = cm != nullptr;
+    return;
+  }
   orth_fused(c, H, c->N, c->d_Omg, Q2, nullptr, false, false, 1);
   comm_allreduce_f64(c, c->d_W, (uint64_t)c->l * c->lp);
   orth_fused(c, H, c->N, c->d_Omg, Q2, nullptr, false, false, 2);

@@ -74,7 +74,112 @@ struct OrthArgs {
   // ~eps * cond(A) in the orthogonality of Q (1e-13 here); the int8 route rounds Omega to 8S-1 = 23 bits
   // right after, so the difference cannot be seen, and a third of the sweep's flops go away.
   int one_shot;
+  // Row-sharded update as ONE launch: the three small exchanges (two l x l Gram matrices; flipOmg sums + signs +
+  // column maxima) run INSIDE the kernel over peer memory instead of through three NCCL launches between four
+  // kernel launches. Every rank owns a mailbox [kPeerSlots][world][l * lp doubles] plus flags
+  // [kPeerSlots][world] in its HBM, mapped into every peer (CUDA IPC / peer access). CTA 0 PUSHES its contribution
+  // into slot (seq % kPeerSlots), row `rank`, of every rank's mailbox (NVLink stores), fences, raises flag
+  // [slot][rank] = seq on every rank, waits until its own flags of that slot all show seq, and sums its local copies
+  // in rank order — the same order on every rank, so all ranks hold the same bits. A slot is reused kPeerSlots
+  // exchanges later; passing an exchange implies every peer has consumed the previous one.
+  int peer_world, peer_rank;
+  double* const* peer_mbox;                 // [world] device pointers (this rank's view) to the mailboxes
+  unsigned long long* const* peer_flag;     // [world] device pointers to the flag arrays
+  unsigned long long peer_seq;              // sequence number of the launch's first exchange (monotonic, > 0)
 };
+
+constexpr int kPeerSlots = 4;
+constexpr int kPeerMaxWorld = 16;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// In-kernel allreduce of buf[0, n) over the ranks of the job, in two halves:
+//   peer_push      any thread that owns element i of this rank's contribution stores it into slot row `rank` of
+//                  EVERY rank's mailbox (NVLink stores; the grid-wide Gram reduction pushes from all SMs at once),
+//                  followed by __threadfence_system() and a grid / block barrier
+//   peer_complete  ONE CTA raises this rank's flag on every rank, waits for the world's flags in its own mailbox
+//                  and sums its local copies in rank order (loads batched 4 elements x world at a time).
+// Elements [0, nsum) are summed as doubles, [nsum, n) are combined with max on their bit patterns
+// (non-negative doubles). A peer that never shows up ends the wait after ~2 s with *status |= 0x100.
+__device__ __forceinline__ size_t peer_row_off(const OrthArgs& a, unsigned long long seq, int stride) {
+  return ((size_t)(seq % kPeerSlots) * a.peer_world + a.peer_rank) * stride;
+}
+__device__ inline void peer_complete(const OrthArgs& a, double* buf, int n, int nsum, unsigned long long seq, int stride,
+                                     int* status) {
+  const int tid = threadIdx.x, nt = blockDim.x, W = a.peer_world, me = a.peer_rank;
+  const int slot = (int)(seq % kPeerSlots);
+  if (tid < W) st_release_sys(a.peer_flag[tid] + slot * W + me, seq);
+  if (tid < W) {
+    const unsigned long long* f = a.peer_flag[me] + slot * W + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < seq) {
+      if (clock64() - t0 > 4000000000ll) {
+        atomicOr(status, 0x100);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const double* mine = a.peer_mbox[me] + (size_t)slot * W * stride;
+  constexpr int EB = 4;
+  for (int i0 = tid; i0 < n; i0 += nt * EB) {
+    double v[EB][kPeerMaxWorld];
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      const int i = i0 + nt * e;
+#pragma unroll
+      for (int src = 0; src < kPeerMaxWorld; ++src)
+        v[e][src] = (i < n && src < W) ? __ldcg(mine + (size_t)src * stride + i) : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      const int i = i0 + nt * e;
+      if (i >= n) continue;
+      if (i < nsum) {
+        double acc = 0.0;
+#pragma unroll
+        for (int src = 0; src < kPeerMaxWorld; ++src)
+          if (src < W) acc += v[e][src];
+        buf[i] = acc;
+      } else {
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int src = 0; src < kPeerMaxWorld; ++src) {
+          const unsigned long long x = (unsigned long long)__double_as_longlong(v[e][src]);
+          if (src < W) m = x > m ? x : m;
+        }
+        buf[i] = __longlong_as_double((long long)m);
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+}
+// one CTA pushes a small buffer itself, then completes
+__device__ inline void peer_allreduce_small(const OrthArgs& a, double* buf, int n, int nsum, unsigned long long seq,
+                                            int stride, int* status) {
+  const int tid = threadIdx.x, nt = blockDim.x, W = a.peer_world;
+  const size_t off = peer_row_off(a, seq, stride);
+  for (int idx = tid; idx < n * W; idx += nt) {
+    const int dst = idx / n, i = idx - dst * n;
+    a.peer_mbox[dst][off + i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  peer_complete(a, buf, n, nsum, seq, stride, status);
+}
 
 // shared-memory strides: rows of the staged tiles and of the factor matrices are LC + 4 doubles
 // (= 4 mod 16), which makes every DMMA fragment load below bank-conflict free
@@ -320,14 +425,19 @@ __device__ inline void orth_factor(const double* __restrict__ W, int l, int ld, 
 }
 
 // out[e] = sum_p part[p*stride + e], one warp per element, lanes stride over parts, fixed order
+// (push_to: optional peer mailboxes — lane d also stores the element into rank d's mailbox at row offset push_off)
 __device__ __forceinline__ void orth_reduce_parts(const double* __restrict__ part, int nparts, size_t stride,
-                                                  int nelem, double* __restrict__ out, int gwarp, int nwarps, int lane) {
+                                                  int nelem, double* __restrict__ out, int gwarp, int nwarps, int lane,
+                                                  double* const* push_to = nullptr, int push_world = 0,
+                                                  size_t push_off = 0) {
   for (int e = gwarp; e < nelem; e += nwarps) {
     double v = 0.0;
     for (int p = lane; p < nparts; p += 32) v += part[(size_t)p * stride + e];
     v = warp_sum(v);
     if (lane == 0) out[e] = v;
+    if (push_to && lane < push_world) push_to[lane][push_off + e] = v;
   }
+  if (push_to) __threadfence_system();
 }
 
 template <int R>
@@ -507,6 +617,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     }
   };
   const int ph = a.phases ? a.phases : 7;
+  const bool peer = a.peer_world > 1 && ph == 7;  // single-launch row-sharded update (exchanges over peer memory)
   if (ph == 8) {  // row-sharded Omega update, last launch: flipbuf = {dsum, ssum, hsign} summed over the ranks
     for (int c = tid; c < 2 * l; c += kOrthThreads) Qs[c] = a.flipbuf[c];
     __syncthreads();
@@ -535,7 +646,8 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     grid.sync();
     stamp();
     // ---------------- P2: W = sum of partials
-    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane, peer ? a.peer_mbox : nullptr,
+                      a.peer_world, peer ? peer_row_off(a, a.peer_seq, l * lp) : 0);
     stamp();
     if (ph & 6) grid.sync();
     stamp();
@@ -543,6 +655,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
   // ---------------- P3: T1
   if (ph & 2) {
     if (blockIdx.x == 0) {
+      if (peer) peer_complete(a, a.Wg, l * lp, l * lp, a.peer_seq, l * lp, a.status);
       orth_factor<R>(a.Wg, l, lp, a.T1g, Ws, T1s, LD, a.jscratch, a.status);
       if (a.skip2) {
         // One Cholesky pass leaves |Q1^T Q1 - I| ~ eps * cond_2(A)^2; cond_F(A)^2 = trace(W) * |T1|_F^2
@@ -611,7 +724,8 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
     grid.sync();
     stamp();
     // ---------------- P5
-    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane);
+    orth_reduce_parts(a.part, gridDim.x, pstride, l * lp, a.Wg, gwarp, nwarps, lane, peer ? a.peer_mbox : nullptr,
+                      a.peer_world, peer ? peer_row_off(a, a.peer_seq + 1, l * lp) : 0);
     if (ph & 4) grid.sync();
     stamp();
   }
@@ -631,6 +745,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         for (int i = tid; i < l * lp; i += kOrthThreads) a.T2g[i] = (i / lp == i % lp) ? 1.0 : 0.0;
         __syncthreads();
       } else {
+        if (peer) peer_complete(a, a.Wg, l * lp, l * lp, a.peer_seq + 1, l * lp, a.status);
         orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
       }
       if (a.one_shot && a.Q) {  // T2s / T2g <- T1 T2 (both upper triangular) before anybody else reads T2
@@ -881,7 +996,23 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         a.flipbuf[c] = v;
       }
       for (int c = tid; c < l; c += kOrthThreads) a.flipbuf[2 * l + c] = a.want_signs ? __ldcg(a.hsign + c) : 0.0;
+      if (peer) {
+        // {dsum, ssum, hsign} summed, the column maxima of |Q| (bit patterns) max'ed, in one exchange
+        for (int c = tid; c < l; c += kOrthThreads)
+          a.flipbuf[3 * l + c] = a.colmax_out ? __longlong_as_double((long long)__ldcg(a.colmax_out + c)) : 0.0;
+        __syncthreads();
+        peer_allreduce_small(a, a.flipbuf, 4 * l, 3 * l, a.peer_seq + 2, l * lp, a.status);
+        if (a.colmax_out)
+          for (int c = tid; c < l; c += kOrthThreads)
+            a.colmax_out[c] = (unsigned long long)__double_as_longlong(a.flipbuf[3 * l + c]);
+        __threadfence();
+      }
     }
+    if (!peer) return;
+    grid.sync();
+    for (int c = tid; c < 2 * l; c += kOrthThreads) Qs[c] = __ldcg(a.flipbuf + c);
+    __syncthreads();
+    apply_flip(true, a.flipbuf + 2 * l);
     return;
   }
   // ---------------- P8: flip decision (every CTA, same fixed order), apply to own rows

@@ -128,7 +128,7 @@ def make_allreduce2_hook(group=None):
     return hook
 
 
-def init_library_comm(L, handle, rank, world):
+def init_library_comm(L, handle, rank, world, peer_mailboxes=False):
     """Give the context its own NCCL communicator (include/pcaone_b200.h: pcaone_comm_unique_id /
     pcaone_comm_init): rank 0 makes the id, torch.distributed carries the 128 bytes to the others.
     From then on every exchange step runs inside the library on its stream."""
@@ -148,6 +148,18 @@ def init_library_comm(L, handle, rank, world):
     ident = (C.c_uint8 * 128)(*t.tolist())
     if L.pcaone_comm_init(handle, ident, rank, world):
         raise RuntimeError(L.pcaone_last_error(handle).decode())
+    if peer_mailboxes and dist.get_backend() == "nccl":
+        # one GPU per rank: map every rank's mailbox into every other rank (CUDA IPC) so that the small
+        # exchanges of the row-sharded Omega update run inside its kernel over NVLink
+        mine = (C.c_uint8 * 64)()
+        if L.pcaone_comm_peer_export(handle, mine):
+            raise RuntimeError(L.pcaone_last_error(handle).decode())
+        allh = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
+        allh[rank * 64:(rank + 1) * 64] = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+        dist.all_reduce(allh)   # disjoint slots: the sum is an all-gather
+        blob = (C.c_uint8 * (world * 64))(*allh.cpu().tolist())
+        if L.pcaone_comm_peer_import(handle, blob, world):
+            raise RuntimeError(L.pcaone_last_error(handle).decode())
 
 
 def shard_samples_range(n_samples: int, rank: int, world: int):

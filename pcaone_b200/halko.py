@@ -343,7 +343,7 @@ class RsvdOpData:
         self._keep = []
         if library_comm and world > 1:
             from . import dist as _pdist
-            _pdist.init_library_comm(L, self.h, rank, world)
+            _pdist.init_library_comm(L, self.h, rank, world, peer_mailboxes=self.shard_samples)
         if allreduce is not None:
             cb = _lib.ALLREDUCE_FN(allreduce)
             self._keep.append(cb)

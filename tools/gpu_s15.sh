@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tests/mgpu_check.py --transport nccl > gpurun_out/s15_mgpu8.log 2>&1; echo "mgpu rc=$?"
+grep -E "sample-shard|MGPU_OK|Error|error" gpurun_out/s15_mgpu8.log | head -8
+PCAONE_PEER_EXCHANGE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 5 --warmup 3 --no-e2e > gpurun_out/s15_bench_n8_peer1.log 2>&1; echo "rc=$?"
+grep '^{' gpurun_out/s15_bench_n8_peer1.log > gpurun_out/s15_n8_peer1.json; python -c "
+import json
+d=json.load(open('gpurun_out/s15_n8_peer1.json')); r=d['roofline']
+print('peer=1', {k:d[k] for k in ['value','time_to_pcs_s']}, {k:r[k] for k in ['tc_g_ms_per_pca','tc_h_ms_per_pca','orth_ms_per_pca','small_stage_ms_per_pca','allreduce_ms_per_pca','gemm_g_ms_per_pca','gemm_h_ms_per_pca']}, r['late_pass']['ms'], d['config']['top_eigenvalues'][0])"
