@@ -66,8 +66,11 @@ void ts_rightmult(pcaone_ctx* c, const double* A, int l1, const double* T, int l
 }
 
 int read_status(pcaone_ctx* c) {
-  PCA_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PCA_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   PCA_CUDA(cudaStreamSynchronize(c->stream));
+  // d_status[1]: eigen-route count of k_orth_fused, bit 0x40000000 = an in-kernel peer exchange gave up waiting
+  if (c->h_status[1] & 0x40000000)
+    throw std::runtime_error("a rank of the job never reached an in-kernel exchange of the Omega update (peer mailbox timeout)");
   return c->h_status[0];
 }
 

@@ -112,7 +112,7 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 //   peer_complete  ONE CTA raises this rank's flag on every rank, waits for the world's flags in its own mailbox
 //                  and sums its local copies in rank order (loads batched 4 elements x world at a time).
 // Elements [0, nsum) are summed as doubles, [nsum, n) are combined with max on their bit patterns
-// (non-negative doubles). A peer that never shows up ends the wait after ~2 s with *status |= 0x100.
+// (non-negative doubles). A peer that never shows up ends the wait after ~2 s with *status |= 0x40000000.
 __device__ __forceinline__ size_t peer_row_off(const OrthArgs& a, unsigned long long seq, int stride) {
   return ((size_t)(seq % kPeerSlots) * a.peer_world + a.peer_rank) * stride;
 }
@@ -126,7 +126,7 @@ __device__ inline void peer_complete(const OrthArgs& a, double* buf, int n, int 
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < seq) {
       if (clock64() - t0 > 4000000000ll) {
-        atomicOr(status, 0x100);
+        atomicOr(status, 0x40000000);
         break;
       }
     }
