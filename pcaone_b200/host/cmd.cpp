@@ -111,7 +111,10 @@ Param::Param(int argc, char** argv) {
 #undef NUM
   // reference flags whose subsystems are outside the GPU hot path (SURVEY §8 "out of scope")
   off_path("p", "pgen", true);
-  off_path("B", "binary", true);
+  val("B", "binary", "path of binary file (the .residuals written by --ld); LD options only.", [this](const std::string& v) {
+    filein = v;
+    file_t = FileType::BINARY;
+  });
   off_path("c", "csv", true);
   off_path("g", "bgen", true);
   val("G", "beagle", "path of BEAGLE file compressed by gzip (genotype likelihoods, PCAngsd algorithm).",
@@ -212,8 +215,8 @@ Param::Param(int argc, char** argv) {
       svd_t = SvdType::PCAoneAlg2;
     else
       throw std::invalid_argument("--svd 0 (IRAM) and 3 (full SVD) are outside the B200 randomized-SVD path; use --svd 1 or 2");
-    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE)
-      throw std::invalid_argument("please give the PLINK prefix with -b/--bfile or a BEAGLE file with -G/--beagle");
+    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY)
+      throw std::invalid_argument("please give the PLINK prefix with -b/--bfile, a BEAGLE file with -G/--beagle, or -B residuals for LD");
     genetic = true;
     if (!usvprefix.empty()) {
       fileU = usvprefix + ".eigvecs";

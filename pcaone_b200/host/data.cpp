@@ -4,6 +4,9 @@
 // in the CUDA library.
 #include "data.hpp"
 
+#include <sys/mman.h>
+#include <sys/stat.h>
+
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -414,6 +417,35 @@ void FileBed::read_block_update(uint64 start_idx, uint64 stop_idx, const Mat2D& 
     for (uint64 j = 0; j < VT.cols(); ++j) V(j, i) = VT(i, j);
   check(pcaone_set_usv(ctx, U.data(), svals.data(), V.data()));
   check(pcaone_decode_block(ctx, start_idx, stop_idx, standardize ? 1 : 0, 1, G.data()));
+}
+
+// ---------------------------------------------------------------------------- FileBin
+FileBin::FileBin(const Param& p) : Data(p) {
+  cao.print(tick.date(), "start parsing binary format (LD residuals)");
+  const int fd2 = ::open(p.filein.c_str(), O_RDONLY);
+  if (fd2 < 0) cao.error("Cannot open binary file.");
+  uint32_t hdr[2];
+  if (::pread(fd2, hdr, 8, 0) != 8) cao.error("binary file is too short");
+  nsnps = hdr[0];
+  nsamples = hdr[1];
+  nsnps_local = nsnps;
+  map_bytes = 8 + (size_t)nsnps * nsamples * 4;
+  struct stat st;
+  if (fstat(fd2, &st) != 0 || (size_t)st.st_size < map_bytes) cao.error("binary file is shorter than its header says");
+  map = mmap(nullptr, map_bytes, PROT_READ, MAP_PRIVATE, fd2, 0);
+  ::close(fd2);
+  if (map == MAP_FAILED) cao.error("cannot map the binary file");
+  rows = reinterpret_cast<const float*>(reinterpret_cast<const char*>(map) + 8);
+  cao.print(tick.date(), "shape of input matrix (features x samples) is", nsnps, " x", nsamples);
+}
+
+FileBin::~FileBin() {
+  if (map && map != MAP_FAILED) munmap(map, map_bytes);
+}
+
+void FileBin::prepare_ld() {
+  shard.snps.clear();
+  create_context();
 }
 
 }  // namespace pcaone_host

@@ -103,4 +103,26 @@ class FileBed : public Data {
   uint8_t* pinned = nullptr;   // in-core: the packed shard in page-locked memory
 };
 
+// `-B file.residuals` (FileBinary.hpp / FileBinary.cpp:21-46): [uint32 M][uint32 N][M x N float32], the LD input the
+// reference writes with --ld. The floats stay in the (memory-mapped) file; the device converts, centres and tiles
+// them chunk by chunk (pcaone_ld_r2_ex, PCAONE_LD_RESID_F32).
+class FileBin : public Data {
+ public:
+  explicit FileBin(const Param& p);
+  ~FileBin() override;
+  void read_all() override {}
+  void check_file_offset_first_var() override {}
+  void read_block_initial(uint64, uint64, bool) override { cao.error("FileBin: the device reads the float rows itself"); }
+  void read_block_update(uint64, uint64, const Mat2D&, const Mat1D&, const Mat2D&, bool) override {
+    cao.error("FileBin: no EMU on residual input");
+  }
+  void attach_stream_source() override {}
+  void prepare_ld();            // sizes + a device context; no genotype source
+  const float* rows = nullptr;  // M x N floats, SNP-major
+
+ private:
+  void* map = nullptr;
+  size_t map_bytes = 0;
+};
+
 }  // namespace pcaone_host

@@ -72,7 +72,18 @@ std::vector<std::string> read_variant_labels(const std::string& filebim) {
 
 void run_ld_stuff(Data* data, const Param& params) {
   cao.print(tick.date(), "run LD stuff");
-  data->prepare();
+  // operand of the r2 tiles: the float rows of a `-B` residual file (FileBin::read_all, FileBinary.cpp:21-30) or the
+  // centred genotypes of the resident bed
+  pcaone_ld_source src{};
+  if (auto* fb = dynamic_cast<FileBin*>(data)) {
+    fb->prepare_ld();
+    src.kind = PCAONE_LD_RESID_F32;
+    src.data = fb->rows;
+    if (params.filebim.empty()) cao.error("-B needs -F/--match-bim (the .mbim written next to the residuals)");
+  } else {
+    data->prepare();
+    src.kind = PCAONE_LD_PACKED;
+  }
   SNPld snp;
   const std::string filebim = params.filebim.empty() ? params.filein + ".bim" : params.filebim;
   get_snp_pos_bim(snp, filebim);
@@ -86,7 +97,7 @@ void run_ld_stuff(Data* data, const Param& params) {
               pick_random_one);
     if (!snp.af.empty() && snp.af.size() != data->nsnps) cao.error("the 7th column (allele frequency) must be on every line");
     std::vector<uint8_t> keep(data->nsnps, 1);
-    data->check(pcaone_ld_prune(data->ctx, nullptr, data->nsnps, snp.ws.data(), snp.we.data(), snp.ws.size(),
+    data->check(pcaone_ld_r2_ex(data->ctx, &src, data->nsnps, snp.ws.data(), snp.we.data(), snp.ws.size(), nullptr,
                                 snp.af.empty() ? nullptr : snp.af.data(), params.ld_r2, keep.data()));
     uint64 nkeep = 0;
     for (uint8_t k : keep) nkeep += k;
@@ -109,7 +120,8 @@ void run_ld_stuff(Data* data, const Param& params) {
   cao.print(tick.date(), "LD windows:", snp.ws.size(), ", pairs:", npairs);
   std::vector<double> r2(npairs);
   // centred genotypes of the resident packed shard (G == NULL), one banded Gram on the GPU
-  data->check(pcaone_ld_r2(data->ctx, nullptr, data->nsnps, snp.ws.data(), snp.we.data(), snp.ws.size(), r2.data()));
+  data->check(pcaone_ld_r2_ex(data->ctx, &src, data->nsnps, snp.ws.data(), snp.we.data(), snp.ws.size(), r2.data(), nullptr,
+                              0.0, nullptr));
   cao.print(tick.date(), "r2 computed on the device; writing", params.fileout + ".ld.gz");
   auto bims = read_variant_labels(filebim);
   gzFile gz = gzopen((params.fileout + ".ld.gz").c_str(), "wb1");

@@ -33,10 +33,16 @@ int main(int argc, char* argv[]) {
     if (params.print_r2 || params.ld_r2 > 0) {
       params.memory = 0, params.out_of_core = false;  // Main.cpp:84
       params.perm = false;
+      if (params.file_t == FileType::BINARY) {  // Main.cpp:149-150: -B file.residuals
+        FileBin data(params);
+        run_ld_stuff(&data, params);
+        return bye();
+      }
       FileBed data(params);
       run_ld_stuff(&data, params);
       return bye();
     }
+    if (params.file_t == FileType::BINARY) cao.error("-B (binary residuals) is an LD input: give --print-r2 or --ld-r2");
     if (params.file_t == FileType::BEAGLE) {  // Main.cpp:117-120 + Halko.cpp:290-311 (PCAngsd EM)
       FileBeagle data(params);
       data.tolmaf = params.tolmaf;

@@ -294,3 +294,32 @@ def test_cli_two_gpus_in_one_process(tmp_path):
     U2, S2, V2 = _load(two, k, M)
     assert np.max(np.abs(S1 - S2) / S1) < 1e-5
     assert col_cos(U1, U2).min() > 0.9999 and col_cos(V1, V2).min() > 0.9999
+
+
+@pytest.mark.gpu
+def test_cli_ld_two_step_through_residual_file(tmp_path):
+    """config-5 flow of the reference, both commands on the GPU front-end: `--ld` writes <out>.residuals + .mbim,
+    `-B <out>.residuals -F <out>.mbim --print-r2` reads them back (FileBin) — against the reference's r2 for the same
+    two commands (the residual rows come from two independent randomized SVDs: loose tolerance on r2)."""
+    import gzip
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, k = 250, 3000, 3
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=5, seed=45)
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 1 --ld -o {tmp_path}/r --maxp 8 --tol-rsvd 0 -n 4", threads=4)
+    r.new_op()
+    r.compute_usv(8, 0.0)
+    r.write_residuals()
+    r.close()
+    r2 = ref.Ref(f"PCAone -B {tmp_path}/r.residuals -F {tmp_path}/r.mbim --print-r2 --ld-bp 2000 -o {tmp_path}/r2 -n 4", threads=4)
+    want, ws, we = r2.ld_r2(f"{tmp_path}/r.mbim", 2000)
+    r2.close()
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "-k", k, "-d", 1, "--ld", "-o", out, "--maxp", 8, "--tol-rsvd", 0, "--precision", "fp64"])
+    _run(["-B", out + ".residuals", "-F", out + ".mbim", "--print-r2", "--ld-bp", 2000, "-o", out + "2"])
+    lines = gzip.open(out + "2.ld.gz", "rt").read().splitlines()
+    assert lines[0].split("\t")[-1] == "R2" and len(lines) == len(want) + 1
+    got = np.array([float(x.split("\t")[-1]) for x in lines[1:]])
+    assert np.abs(got - want).max() < 2e-5   # 6 decimals in the text + two independent RSVD runs behind the residuals
