@@ -66,7 +66,9 @@ typedef struct pcaone_config {
    * SNPs; the exact int64 partial sums of G_b = X_b^T Omega (window x l) are summed instead, H and
    * Omega stay row-sharded, and the orthonormalisation exchanges only l x l Gram matrices. The
    * exchange per Omega update is N x l doubles in mode 0, (window SNPs) x l in mode 1: hosts pick
-   * mode 1 when the windows are shorter than N (configs[2]: 7.8k-SNP windows, N = 500k). */
+   * mode 1 when the windows are shorter than N (configs[2]: 7.8k-SNP windows, N = 500k). In mode 1 every matrix with
+   * one row per sample (Omega, H, U) holds THIS RANK's nsamples rows in pcaone_set_omega / pcaone_get_omega /
+   * pcaone_get_GH / pcaone_get_usv; G, V, S and F are the whole job's and identical on every rank. */
   int32_t  shard_samples;
   uint64_t nsamples_total; /* N of the whole job (0 = nsamples)                        */
   uint64_t sample_offset;  /* first sample of this rank (shard_samples)                */

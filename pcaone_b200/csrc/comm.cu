@@ -189,6 +189,7 @@ int pcaone_comm_peer_export(pcaone_ctx* c, uint8_t* out64) {
 int pcaone_comm_peer_import(pcaone_ctx* c, const uint8_t* handles, int nranks) {
   CTX_GUARD(c, {
     if (nranks != c->cfg.world || !c->d_mbox) throw std::runtime_error("peer_import: call pcaone_comm_peer_export first, pass world handles");
+    if (c->d_peer_mbox) throw std::runtime_error("peer_import: mailboxes are already mapped");
     std::vector<double*> mb(nranks);
     std::vector<unsigned long long*> fl(nranks);
     for (int r = 0; r < nranks; ++r) {

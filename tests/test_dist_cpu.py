@@ -68,3 +68,26 @@ def test_allreduce_hook_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)], res
+
+
+def test_sample_shard_ranges_and_placeholder_windows():
+    """sample-sharded jobs cut the sample axis on whole bed bytes; SNP-sharded winSVD keeps every rank on the same
+    `bands`-step schedule (empty trailing windows stay as start = stop + 1 placeholders) and refuses a
+    window with fewer SNPs than ranks instead of letting the ranks issue different numbers of collectives."""
+    import pytest
+    for n, w in ((900, 2), (900, 8), (500_000, 8), (1003, 4)):
+        got = [pdist.shard_samples_range(n, r, w) for r in range(w)]
+        assert got[0][0] == 0 and got[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+        assert all(s % 4 == 0 for s, _ in got)
+    # M < bands * blocksize: the trailing window is empty on every rank, the schedule keeps `bands` entries
+    M, bands, world = 130, 16, 2          # blocksize 9 -> 15 windows of SNPs, window 15 is empty
+    lens = []
+    for r in range(world):
+        idx, start, stop = pdist.shard_windows(M, bands, r, world)
+        assert len(start) == len(stop) == bands
+        assert int(start[-1]) == int(stop[-1]) + 1      # placeholder
+        lens.append(len(idx))
+    assert sum(lens) == M
+    with pytest.raises(RuntimeError):
+        pdist.shard_windows(40, 16, 0, 8)               # 3-SNP windows cannot be cut 8 ways
