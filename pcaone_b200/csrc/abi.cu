@@ -126,11 +126,12 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     dmalloc(&c->d_hsign, c->lp);
     dmalloc(&c->d_flipbuf, 4 * (size_t)c->lp);
     dmalloc(&c->d_scal, 64);
-    dmalloc(&c->d_status, 4);
-    PCA_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(int)));
+    dmalloc(&c->d_status, 8);
+    PCA_CUDA(cudaMemset(c->d_status, 0, 8 * sizeof(int)));
     dmalloc(&c->d_jscratch, (size_t)2 * c->l * c->l + 2 * c->l + 8);
     if (const char* e = getenv("PCAONE_FUSED_ORTH")) c->fused_orth = atoi(e);
     if (const char* e = getenv("PCAONE_ORTH_ONE_SHOT")) c->one_shot_q = atoi(e);
+    if (const char* e = getenv("PCAONE_OMEGA_SKIP2")) c->omega_skip2 = atoi(e);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
     c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;

@@ -142,6 +142,9 @@ struct pcaone_ctx {
   bool g_is_q = false;                                 // d_G holds Q = G T after small_stage (else raw G)
   double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
   int fused_orth = 1;                                  // PCAONE_FUSED_ORTH=0 selects the multi-kernel path
+  int omega_skip2 = 1;                                 // int8 route: Omega updates may skip the second CholeskyQR pass (PCAONE_OMEGA_SKIP2=0: never)
+  int omega_force_full = 0;
+  uint64_t omega_update_no = 0;
   int one_shot_q = 1;                                  // int8 route: Omega = H (T1 T2) in one tile product (PCAONE_ORTH_ONE_SHOT=0: two)
 
   // sharded jobs

@@ -166,6 +166,14 @@ void orth_fused(pcaone_ctx* c, const double* A, uint64_t rows, double* Q, double
   // dropped when the first one shows cond_F(G)^2 <= 1e5 (PCAONE_QR2_ALWAYS=1 keeps it)
   static const bool qr2_always = getenv("PCAONE_QR2_ALWAYS") && atoi(getenv("PCAONE_QR2_ALWAYS")) != 0;
   a.skip2 = (!Q && (phases == 7 || phases == 2) && !qr2_always) ? c->d_status + 3 : nullptr;
+  a.skip_thresh = 1e5;
+  if (Q && c->slices > 0 && c->omega_skip2 && !qr2_always) {  // Omega update on the int8 route (see OrthArgs::skip_thresh)
+    a.skip2 = (phases == 7 || phases == 2) ? c->d_status + 3 : nullptr;
+    a.skip_thresh = 3e-7 / 2.220446049250313e-16;
+    a.force_full = c->omega_force_full;
+    a.veto = c->d_status + 4;
+    a.veto_tol = 3e-7;
+  }
   a.skip_diag = c->cfg.rank == 0 ? 1.0 : 0.0;
   static unsigned long long* d_prof = nullptr;
   static int prof_left = getenv("PCAONE_ORTH_PROF") ? atoi(getenv("PCAONE_ORTH_PROF")) : 0;
@@ -278,6 +286,7 @@ void update_omega_sharded(pcaone_ctx* c, const double* H, bool flip) {
 // Omega = thinQ(H) (+ flipOmg)   Halko.cpp:120-124 / 208-213
 void update_omega(pcaone_ctx* c, const double* H, bool flip) {
   Timed t(c, 2);
+  c->omega_force_full = (c->omega_update_no++ % 16 == 0) ? 1 : 0;  // every 16th update measures what skipping leaves out
   if (c->shard_samples && c->cfg.world > 1) {
     update_omega_sharded(c, H, flip);
     return;

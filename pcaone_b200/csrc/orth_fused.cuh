@@ -65,6 +65,16 @@ struct OrthArgs {
   // that one Cholesky pass is enough (see P3); nullptr = always CholeskyQR2
   int* skip2;
   double skip_diag;  // phase-split launches: this rank's share of the identity (1 on rank 0, else 0)
+  // The same decision for Omega updates on the int8 route (Q != nullptr): there Omega is rounded to 8S-1 = 23 bits
+  // per column scale right after this kernel, which moves every column by ~3e-7 of its norm, so an orthonormality
+  // defect below that cannot be seen: the second pass is skipped while eps * cond_F(H)^2 <= 3e-7 (skip_thresh holds
+  // the bound on cond_F^2; 1e5 for the factors-only calls above). Because eps * cond^2 is what the defect IS in
+  // practice, not a rigorous bound, every 16th update runs both passes anyway (force_full) and MEASURES
+  // |Q1^T Q1 - I|: above veto_tol it sets *veto and no later update skips.
+  double skip_thresh;
+  int force_full;
+  int* veto;
+  double veto_tol;
   // Row-sharded Omega update (rows of A, Q, Q2 are this rank's samples): the launch with phases = 4
   // writes the UNSIGNED Q, leaves its flipOmg column sums (both signs) and — on the rank that owns
   // the top l rows (want_signs) — the Householder signs in flipbuf[3 l] = {dsum, ssum, hsign} and
@@ -680,7 +690,7 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
             tr += s_red[0][w];
             tf += s_red[1][w];
           }
-          *a.skip2 = (tr * tf <= 1e5) ? 1 : 0;  // NaN -> 0
+          *a.skip2 = (!a.force_full && !(a.veto && *a.veto) && tr * tf <= a.skip_thresh) ? 1 : 0;  // NaN -> 0
         }
       }
     }
@@ -746,6 +756,14 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_orth_fused(const OrthArgs a
         __syncthreads();
       } else {
         if (peer) peer_complete(a, a.Wg, l * lp, l * lp, a.peer_seq + 1, l * lp, a.status);
+        if (a.veto) {  // a full update on a route that may skip the second pass: measure the defect it removes
+          bool big = false;
+          for (int i = tid; i < l * l; i += kOrthThreads) {
+            const int r = i / l, c = i - r * l;
+            big |= !(fabs(a.Wg[r * lp + c] - (r == c ? 1.0 : 0.0)) <= a.veto_tol);
+          }
+          if (__syncthreads_or(big) && tid == 0) *a.veto = 1;
+        }
         orth_factor<R>(a.Wg, l, lp, a.T2g, Ws, T2s, LD, a.jscratch, a.status);
       }
       if (a.one_shot && a.Q) {  // T2s / T2g <- T1 T2 (both upper triangular) before anybody else reads T2
