@@ -256,10 +256,16 @@ def main():
     by_snps = world > 1 and not by_samples
 
     # ---- this rank's part of the ONE synthetic bed, generated on the GPU tile by tile into pinned host memory
-    nblk = n // SAMPLE_BLOCKS
+    nblk = (-(-n // SAMPLE_BLOCKS) + 3) // 4 * 4          # block boundaries on whole bed bytes; the last block may be short
+
+    def blk(sb):
+        lo = min(n, sb * nblk)
+        return lo, min(n, lo + nblk) - lo
+
     if by_samples or world == 1:
         sb0, sb1 = (rank * SAMPLE_BLOCKS // world, (rank + 1) * SAMPLE_BLOCKS // world) if by_samples else (0, SAMPLE_BLOCKS)
-        samp0, n_loc = sb0 * nblk, (sb1 - sb0) * nblk
+        samp0 = blk(sb0)[0]
+        n_loc = blk(sb1 - 1)[0] + blk(sb1 - 1)[1] - samp0
         snp_idx = None
         m_loc = m
     else:
@@ -275,8 +281,9 @@ def main():
         for s0 in range(0, m, chunk):
             mm = min(chunk, m - s0)
             for sb in range(sb0, sb1):
-                tile = synth.torch_packed_tile(n, sb * nblk, nblk, s0, mm, k_pop=K + 4, seed=1, device=dev)
-                c0 = (sb - sb0) * (nblk // 4)
+                lo, cnt = blk(sb)
+                tile = synth.torch_packed_tile(n, lo, cnt, s0, mm, k_pop=K + 4, seed=1, device=dev)
+                c0 = (lo - samp0) // 4
                 stage[:mm, c0:c0 + tile.shape[1]] = tile
             host[s0:s0 + mm].copy_(stage[:mm], non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -291,8 +298,9 @@ def main():
             if mine.numel() == 0:
                 continue
             for sb in range(SAMPLE_BLOCKS):
-                tile = synth.torch_packed_tile(n, sb * nblk, nblk, s0, mm, k_pop=K + 4, seed=1, device=dev)
-                c0 = sb * (nblk // 4)
+                lo, cnt = blk(sb)
+                tile = synth.torch_packed_tile(n, lo, cnt, s0, mm, k_pop=K + 4, seed=1, device=dev)
+                c0 = lo // 4
                 host[pos:pos + mine.numel(), c0:c0 + tile.shape[1]].copy_(tile[mine])
             pos += int(mine.numel())
     torch.cuda.synchronize()
