@@ -308,6 +308,7 @@ typedef struct pcaone_timers {
   uint64_t ld_tiles, ld_pairs;     /* 128 x 128 Gram tiles computed / r2 values produced */
   uint64_t tc_miss_ranges;         /* of tc_ranges: ranges with missing calls (count + mask GEMM pairs) */
   uint64_t cache_hits;             /* streamed blocks served from the HBM tile cache instead of the host */
+  uint64_t tc_emu_ranges;          /* of tc_miss_ranges: EMU update passes (FP64 correction over the missing calls) */
 } pcaone_timers;
 int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
 int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */

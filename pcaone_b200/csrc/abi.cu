@@ -132,6 +132,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     if (const char* e = getenv("PCAONE_FUSED_ORTH")) c->fused_orth = atoi(e);
     if (const char* e = getenv("PCAONE_ORTH_ONE_SHOT")) c->one_shot_q = atoi(e);
     if (const char* e = getenv("PCAONE_OMEGA_SKIP2")) c->omega_skip2 = atoi(e);
+    if (const char* e = getenv("PCAONE_EMU_TC")) c->emu_tc = atoi(e);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
     c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;
@@ -407,10 +408,11 @@ int pcaone_get_timers(pcaone_ctx* c, pcaone_timers* out, int reset) {
     c->tm.tc_ranges = c->tc_ranges;
     c->tm.fp64_ranges = c->fp64_ranges;
     c->tm.tc_miss_ranges = c->tc_miss_ranges;
+    c->tm.tc_emu_ranges = c->tc_emu_ranges;
     if (out) *out = c->tm;
     if (reset) {
       c->tm = pcaone_timers{};
-      c->tc_ranges = c->fp64_ranges = c->tc_miss_ranges = 0;
+      c->tc_ranges = c->fp64_ranges = c->tc_miss_ranges = c->tc_emu_ranges = 0;
     }
   });
 }

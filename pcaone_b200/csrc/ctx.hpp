@@ -137,7 +137,7 @@ struct pcaone_ctx {
   bool sum_done = false;
   std::vector<uint32_t> h_nmiss;                       // per local SNP; UINT32_MAX = not known yet
   std::vector<uint64_t> nmiss_prefix;
-  uint64_t tc_ranges = 0, fp64_ranges = 0, tc_miss_ranges = 0;
+  uint64_t tc_ranges = 0, fp64_ranges = 0, tc_miss_ranges = 0, tc_emu_ranges = 0;
   int half = 3;                                        // which products a range runs: 1 = G rows only, 2 = H only, 3 = both
   bool g_is_q = false;                                 // d_G holds Q = G T after small_stage (else raw G)
   double* d_jscratch = nullptr;                        // eigen-fallback scratch of k_orth_fused
@@ -145,6 +145,7 @@ struct pcaone_ctx {
   int omega_skip2 = 1;                                 // int8 route: Omega updates may skip the second CholeskyQR pass (PCAONE_OMEGA_SKIP2=0: never)
   int omega_force_full = 0;
   uint64_t omega_update_no = 0;
+  int emu_tc = 1;                                      // EMU update passes on the int8 route + FP64 correction over the missing calls (PCAONE_EMU_TC=0: FP64 DMMA kernels)
   int one_shot_q = 1;                                  // int8 route: Omega = H (T1 T2) in one tile product (PCAONE_ORTH_ONE_SHOT=0: two)
 
   // sharded jobs
@@ -275,6 +276,7 @@ size_t tc_ph_bytes(const pcaone_ctx* c, uint64_t rows);
 void tc_build_tiles(pcaone_ctx* c, const uint8_t* P, uint64_t rows, uint8_t* PG, uint8_t* PH, cudaStream_t st,
                     uint64_t row0 = 0);
 void tc_alloc(pcaone_ctx* c, uint64_t max_range_rows, bool miss);
+bool emu_tc_supported(const pcaone_ctx* c);
 void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0,
                     double* Hacc, bool accumulate, bool miss);
 

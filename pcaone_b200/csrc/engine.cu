@@ -60,9 +60,15 @@ void tc_fetch_nmiss(pcaone_ctx* c, uint64_t s, uint64_t n) {
   }
 }
 
-// does the current pass run its products on the int8 tensor-core kernels? (EMU update passes fill
-// every missing entry with its own FP64 value, half passes are GEMV-shaped: FP64 kernels)
-bool pass_uses_tc(const pcaone_ctx* c) { return c->slices > 0 && !(c->update && c->cfg.emu) && c->half == 3; }
+// does the current pass run its products on the int8 tensor-core kernels? Half passes are GEMV-shaped: FP64
+// kernels. EMU update passes fill every missing entry with its own FP64 value: tensor-core products of the
+// mean-imputed block plus the FP64 correction over the missing calls (emu_fix.cuh), unless switched off
+// (PCAONE_EMU_TC=0) or k is beyond what the correction kernels hold in registers — then the FP64 DMMA kernels.
+bool pass_uses_tc(const pcaone_ctx* c) {
+  if (c->slices <= 0 || c->half != 3) return false;
+  if (c->update && c->cfg.emu) return emu_tc_supported(c);
+  return true;
+}
 
 // G rows of the range = X^T Omega ; Hacc (+)= X G. `buf` = streamed block buffer holding P, or -1
 // when P points into the resident shard; `blk` = block of the plan the range is (streamed sources;

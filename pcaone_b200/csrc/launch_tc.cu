@@ -1,6 +1,7 @@
 // pcaone_b200 — launchers of the int8 tensor-core products (tc_gemm.cuh).
 #include "ctx.hpp"
 #include "tc_gemm.cuh"
+#include "emu_fix.cuh"
 
 namespace pcaone {
 
@@ -146,12 +147,46 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
   if (nkb_out) *nkb_out = nkb;
 }
 
+// ---------------------------------------------------------------- EMU fill on the int8 route (emu_fix.cuh)
+bool emu_tc_supported(const pcaone_ctx* c) { return c->emu_tc && c->k <= emu::kMaxK; }
+
+#define EMU_KR_DISPATCH(FN, ...)                  \
+  do {                                            \
+    if (c->k <= 16) FN<16>(__VA_ARGS__);          \
+    else if (c->k <= 32) FN<32>(__VA_ARGS__);     \
+    else FN<emu::kMaxK>(__VA_ARGS__);             \
+  } while (0)
+
+template <int KR>
+void emu_fix_g_kr(pcaone_ctx* c, const uint8_t* PG, uint64_t loc0, uint32_t nrows, uint64_t snp0, unsigned long long* w_colmax) {
+  const uint32_t rt0 = (uint32_t)(loc0 / tc::kRowTile), rt1 = (uint32_t)((loc0 + nrows - 1) / tc::kRowTile);
+  const dim3 grid(rt1 - rt0 + 1, (unsigned)((c->l + emu::kLT - 1) / emu::kLT));
+  const uint32_t nkb = (uint32_t)tc_nkb_samples(c);
+  emu::k_emu_fix_g<KR><<<grid, emu::kThreads, emu::smem_g(KR), c->stream>>>(
+      PG, (uint64_t)nkb * tc::kChunkBytes, nkb, (uint32_t)c->N, loc0, nrows, c->d_U, c->lp, c->d_S, c->k,
+      c->d_V + snp0 * c->lp, c->lp, c->d_Omg, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+template <int KR>
+void emu_fix_h_kr(pcaone_ctx* c, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0, double* Hacc, double* Hsum) {
+  const uint32_t nrt = (uint32_t)tc_nrt_samples(c);
+  const dim3 grid(nrt, (unsigned)((c->l + emu::kLT - 1) / emu::kLT));
+  emu::k_emu_fix_h<KR><<<grid, emu::kThreads, emu::smem_h(KR), c->stream>>>(
+      PH, nrt, (uint32_t)c->N, loc0, nrows, c->d_U, c->lp, c->d_S, c->k, c->d_V + snp0 * c->lp, c->lp,
+      c->d_G + snp0 * c->lp, c->lp, c->l, c->d_F + snp0, c->lut, Hacc, Hsum);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
 // tensor-core version of range_gemms. PG/PH: tiled operands in which the range starts at local
 // row / contraction index `loc0`; snp0 = first SNP of the range in d_G / d_F.
 // `miss`: the range contains missing calls -> every product is run as (non-missing counts, mask) pair.
 void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0,
                     double* Hacc, bool accumulate, bool miss) {
   const int mode = miss ? tc::kNonMiss : tc::kPlain;
+  const bool emu_fill = miss && c->update && c->cfg.emu;  // (a range without missing calls has nothing to fill)
   unsigned long long* o_colmax = c->d_tcs;
   long long* o_csum = reinterpret_cast<long long*>(c->d_tcs + c->lp);
   unsigned long long* w_colmax = c->d_tcs + 2 * c->lp;
@@ -213,6 +248,8 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     PCA_CHECK_LAUNCH();
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
+    // EMU update pass: the missing calls hold clamp(U S V^T) instead of 0 — their FP64 terms, before W is sliced
+    if (emu_fill) EMU_KR_DISPATCH(emu_fix_g_kr, c, PG, loc0, nrows, snp0, w_colmax);
   }
   {
     Timed t(c, 1);
@@ -262,9 +299,11 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     if (fuse_sum) c->sum_done = true;
     c->tm.kernel_launches++;
     c->tm.gemm_h_launches++;
+    if (emu_fill) EMU_KR_DISPATCH(emu_fix_h_kr, c, PH, loc0, nrows, snp0, Hacc, fuse_sum ? c->sum_out : nullptr);
   }
   c->tc_ranges++;
   if (miss) c->tc_miss_ranges++;
+  if (emu_fill) c->tc_emu_ranges++;
 }
 
 }  // namespace pcaone
