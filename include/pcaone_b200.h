@@ -35,7 +35,8 @@ enum { PCAONE_SVD_SSVD = 1, PCAONE_SVD_WINSVD = 2 };          /* --svd 1 / 2 (Cm
  * the tcgen05 int8 tensor cores — Omega / G are rounded once to s signed 8-bit slices per entry
  * (8s-1 bits against the column maximum) and the products are then exact integers; ranges with
  * missing genotypes run each product as a (non-missing count, missing mask) pair on the same
- * kernels (mean imputation); EMU update passes still run on the FP64 kernels. */
+ * kernels (mean imputation); EMU update passes add the fills of the missing calls in FP64 on top of
+ * those products (FilePlink.cpp:246-259). */
 enum { PCAONE_PREC_FP64 = 0, PCAONE_PREC_INT8X2 = 2, PCAONE_PREC_INT8X3 = 3, PCAONE_PREC_INT8X4 = 4 };
 enum { PCAONE_SRC_RESIDENT = 0, PCAONE_SRC_HOST = 1, PCAONE_SRC_FILE = 2, PCAONE_SRC_DENSE = 3, PCAONE_SRC_DOSAGE = 4, PCAONE_SRC_GL = 5 };
 
@@ -309,6 +310,7 @@ typedef struct pcaone_timers {
   uint64_t tc_miss_ranges;         /* of tc_ranges: ranges with missing calls (count + mask GEMM pairs) */
   uint64_t cache_hits;             /* streamed blocks served from the HBM tile cache instead of the host */
   uint64_t tc_emu_ranges;          /* of tc_miss_ranges: EMU update passes (FP64 correction over the missing calls) */
+  double emu_fix_ms;               /* k_emu_fix_g / k_emu_fix_h (inside gemm_g_ms / gemm_h_ms) */
 } pcaone_timers;
 int pcaone_get_timers(pcaone_ctx* ctx, pcaone_timers* out, int reset);
 int pcaone_enable_timing(pcaone_ctx* ctx, int on); /* CUDA-event timing around the GEMM kernels */

@@ -40,7 +40,7 @@ class Timers(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("omega_updates", C.c_uint64),
         ("tc_ranges", C.c_uint64), ("fp64_ranges", C.c_uint64), ("tc_g_ms", C.c_double), ("tc_h_ms", C.c_double),
         ("ld_ms", C.c_double), ("ld_tiles", C.c_uint64), ("ld_pairs", C.c_uint64),
-        ("tc_miss_ranges", C.c_uint64), ("cache_hits", C.c_uint64), ("tc_emu_ranges", C.c_uint64),
+        ("tc_miss_ranges", C.c_uint64), ("cache_hits", C.c_uint64), ("tc_emu_ranges", C.c_uint64), ("emu_fix_ms", C.c_double),
     ]
 
 

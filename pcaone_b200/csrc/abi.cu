@@ -162,7 +162,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
                   (void*)c->d_dense, (void*)c->d_P, (void*)c->d_dos, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch,
-                  (void*)c->d_flipbuf, (void*)c->d_cnt, (void*)c->d_cache_pg, (void*)c->d_cache_ph})
+                  (void*)c->d_flipbuf, (void*)c->d_cnt, (void*)c->d_cache_pg, (void*)c->d_cache_ph, (void*)c->d_emu_us})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);

@@ -86,6 +86,7 @@ struct pcaone_ctx {
          *d_Ucur = nullptr, *d_Upre = nullptr, *d_U = nullptr;
   double *d_G = nullptr, *d_V = nullptr, *d_Vpre = nullptr;
   double* d_S = nullptr;
+  double* d_emu_us = nullptr;  // U o S of the EMU fill (N x lp), emu_fix.cuh
   double* d_Hpart = nullptr;
   uint32_t max_splits = 1;
   bool have_usv = false, have_omg0 = false;

@@ -28,6 +28,7 @@ void resolve_timers(pcaone_ctx* c) {
       case 7: c->tm.tc_g_ms += ms; break;
       case 8: c->tm.tc_h_ms += ms; break;
       case 9: c->tm.ld_ms += ms; break;
+      case 10: c->tm.emu_fix_ms += ms; break;
     }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);

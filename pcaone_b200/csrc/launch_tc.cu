@@ -150,32 +150,63 @@ void tc_slice(pcaone_ctx* c, double* X, uint64_t r0, uint64_t r1, const unsigned
 // ---------------------------------------------------------------- EMU fill on the int8 route (emu_fix.cuh)
 bool emu_tc_supported(const pcaone_ctx* c) { return c->emu_tc && c->k <= emu::kMaxK; }
 
-#define EMU_KR_DISPATCH(FN, ...)                  \
-  do {                                            \
-    if (c->k <= 16) FN<16>(__VA_ARGS__);          \
-    else if (c->k <= 32) FN<32>(__VA_ARGS__);     \
-    else FN<emu::kMaxK>(__VA_ARGS__);             \
-  } while (0)
+// column tile of the correction kernels: l split into equal tiles of at most 24 columns, rounded up to 4
+static int emu_lt(int l) {
+  const int nt = (l + emu::kMaxLT - 1) / emu::kMaxLT;
+  return std::max(12, ((l + nt - 1) / nt + 3) / 4 * 4);
+}
 
-template <int KR>
-void emu_fix_g_kr(pcaone_ctx* c, const uint8_t* PG, uint64_t loc0, uint32_t nrows, uint64_t snp0, unsigned long long* w_colmax) {
+template <int KR, int LT>
+void emu_fix_g_t(pcaone_ctx* c, const uint8_t* PG, uint64_t loc0, uint32_t nrows, uint64_t snp0, unsigned long long* w_colmax) {
+  constexpr int SB = emu::sb_of(KR, LT);
+  constexpr size_t smem = emu::smem_bytes(KR, LT, SB, false);
   const uint32_t rt0 = (uint32_t)(loc0 / tc::kRowTile), rt1 = (uint32_t)((loc0 + nrows - 1) / tc::kRowTile);
-  const dim3 grid(rt1 - rt0 + 1, (unsigned)((c->l + emu::kLT - 1) / emu::kLT));
+  const dim3 grid(rt1 - rt0 + 1, (unsigned)((c->l + LT - 1) / LT));
   const uint32_t nkb = (uint32_t)tc_nkb_samples(c);
-  emu::k_emu_fix_g<KR><<<grid, emu::kThreads, emu::smem_g(KR), c->stream>>>(
-      PG, (uint64_t)nkb * tc::kChunkBytes, nkb, (uint32_t)c->N, loc0, nrows, c->d_U, c->lp, c->d_S, c->k,
-      c->d_V + snp0 * c->lp, c->lp, c->d_Omg, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax);
+  ensure_smem(c, emu::k_emu_fix_g<KR, LT, SB>, smem);
+  emu::k_emu_fix_g<KR, LT, SB><<<grid, emu::kThreads, smem, c->stream>>>(
+      PG, (uint64_t)nkb * tc::kChunkBytes, nkb, (uint32_t)c->N, loc0, nrows, c->d_emu_us, c->lp, c->k, c->d_V + snp0 * c->lp,
+      c->lp, c->d_Omg, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
 }
 
-template <int KR>
-void emu_fix_h_kr(pcaone_ctx* c, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0, double* Hacc, double* Hsum) {
+template <int KR, int LT>
+void emu_fix_h_t(pcaone_ctx* c, const uint8_t* PH, uint64_t loc0, uint32_t nrows, uint64_t snp0, double* Hacc, double* Hsum) {
+  constexpr int SB = emu::sb_of(KR, LT);
+  constexpr size_t smem = emu::smem_bytes(KR, LT, SB, true);
   const uint32_t nrt = (uint32_t)tc_nrt_samples(c);
-  const dim3 grid(nrt, (unsigned)((c->l + emu::kLT - 1) / emu::kLT));
-  emu::k_emu_fix_h<KR><<<grid, emu::kThreads, emu::smem_h(KR), c->stream>>>(
-      PH, nrt, (uint32_t)c->N, loc0, nrows, c->d_U, c->lp, c->d_S, c->k, c->d_V + snp0 * c->lp, c->lp,
-      c->d_G + snp0 * c->lp, c->lp, c->l, c->d_F + snp0, c->lut, Hacc, Hsum);
+  const dim3 grid(nrt, (unsigned)((c->l + LT - 1) / LT));
+  ensure_smem(c, emu::k_emu_fix_h<KR, LT, SB>, smem);
+  emu::k_emu_fix_h<KR, LT, SB><<<grid, emu::kThreads, smem, c->stream>>>(
+      PH, nrt, (uint32_t)c->N, loc0, nrows, c->d_emu_us, c->lp, c->k, c->d_V + snp0 * c->lp, c->lp, c->d_G + snp0 * c->lp,
+      c->lp, c->l, c->d_F + snp0, c->lut, Hacc, Hsum);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
+// register widths matched to k and to the column tile (the kernels are bound by the shared-memory reads per missing call)
+#define EMU_LT_DISPATCH(FN, KR_, ...)                        \
+  switch (emu_lt(c->l)) {                                    \
+    case 12: FN<KR_, 12>(__VA_ARGS__); break;                \
+    case 16: FN<KR_, 16>(__VA_ARGS__); break;                \
+    case 20: FN<KR_, 20>(__VA_ARGS__); break;                \
+    default: FN<KR_, 24>(__VA_ARGS__); break;                \
+  }
+#define EMU_DISPATCH(FN, ...)                                \
+  do {                                                       \
+    if (c->k <= 6) { EMU_LT_DISPATCH(FN, 6, __VA_ARGS__) }   \
+    else if (c->k <= 10) { EMU_LT_DISPATCH(FN, 10, __VA_ARGS__) } \
+    else if (c->k <= 16) { EMU_LT_DISPATCH(FN, 16, __VA_ARGS__) } \
+    else if (c->k <= 24) { EMU_LT_DISPATCH(FN, 24, __VA_ARGS__) } \
+    else if (c->k <= 32) { EMU_LT_DISPATCH(FN, 32, __VA_ARGS__) } \
+    else { EMU_LT_DISPATCH(FN, 56, __VA_ARGS__) }            \
+  } while (0)
+
+// U o S of the current fill, once per range (U, S are fixed while a computeUSV runs its epochs; N x k: negligible)
+static void emu_prepare(pcaone_ctx* c) {
+  if (!c->d_emu_us) dmalloc(&c->d_emu_us, c->N * c->lp);
+  emu::k_emu_scale_u<<<grid_for(c->N * c->lp, 256, c->sms), 256, 0, c->stream>>>(c->d_U, c->d_S, c->N, c->k, c->lp, c->d_emu_us);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
 }
@@ -249,7 +280,11 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     c->tm.gemm_g_launches++;
     c->tm.kernel_launches++;
     // EMU update pass: the missing calls hold clamp(U S V^T) instead of 0 — their FP64 terms, before W is sliced
-    if (emu_fill) EMU_KR_DISPATCH(emu_fix_g_kr, c, PG, loc0, nrows, snp0, w_colmax);
+    if (emu_fill) {
+      Timed te(c, 10);
+      emu_prepare(c);
+      EMU_DISPATCH(emu_fix_g_t, c, PG, loc0, nrows, snp0, w_colmax);
+    }
   }
   {
     Timed t(c, 1);
@@ -299,7 +334,10 @@ void range_gemms_tc(pcaone_ctx* c, const uint8_t* PG, const uint8_t* PH, uint64_
     if (fuse_sum) c->sum_done = true;
     c->tm.kernel_launches++;
     c->tm.gemm_h_launches++;
-    if (emu_fill) EMU_KR_DISPATCH(emu_fix_h_kr, c, PH, loc0, nrows, snp0, Hacc, fuse_sum ? c->sum_out : nullptr);
+    if (emu_fill) {
+      Timed te(c, 10);
+      EMU_DISPATCH(emu_fix_h_t, c, PH, loc0, nrows, snp0, Hacc, fuse_sum ? c->sum_out : nullptr);
+    }
   }
   c->tc_ranges++;
   if (miss) c->tc_miss_ranges++;

@@ -26,8 +26,8 @@
 // them runs every GEMM twice on the same machinery: once with u = 0 at the missing entries and
 // once with the 0/1 missing mask as the packed operand, whose product takes the missing entries
 // out of the centring term (see the finish kernels). The EMU fill (a different FP64 value per
-// missing entry) is not expressible this way: EMU update passes run on the FP64 DMMA kernels
-// (gemm_fp64.cuh) instead — still on the GPU.
+// missing entry) is added on top of these mean-imputed products by the FP64 correction kernels of
+// emu_fix.cuh, which read the same tiled operands.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"

@@ -5,7 +5,7 @@ cores and adds the missing calls' terms in FP64. Checked here:
   * one pass against the numpy restatement of read_block_update: G = X^T Omega and H = X G~ to the 23-bit
     operand rounding of the int8 route (1000x below what leaving the fill out would cost);
   * whole EM runs against the FP64 DMMA route of the same library, sSVD and winSVD, resident / cached / streamed
-    tiles, three register widths of the correction kernels (k <= 16, <= 32, <= 56), ragged N and M.
+    tiles, several register widths of the correction kernels (k <= 6 ... <= 56), ragged N and M.
 The live-reference comparison of the same route is tests/test_gpu_scale.py::test_configs3_shape_emu_vs_reference.
 """
 import os
@@ -91,7 +91,8 @@ CASES = [
     (2, 16, 5, 1003, 9001, 0.0, None),
     (2, 16, 5, 1003, 9001, 0.004, None),                              # streamed once, then the HBM tile cache
     (2, 16, 5, 1003, 9001, 0.004, {"PCAONE_TILE_CACHE": "0"}),       # streamed every pass (per-buffer tiles)
-    (1, 64, 20, 640, 5000, 0.0, None),                                # KR = 32
+    (1, 64, 13, 600, 4000, 0.0, None),                                # KR = 16, l = 26: two column tiles of 16
+    (1, 64, 20, 640, 5000, 0.0, None),                                # KR = 24
     (2, 8, 36, 520, 4100, 0.0, None),                                 # KR = 56, l = 72: three column tiles
 ]
 

@@ -200,23 +200,56 @@ def c3(args, out):
 
 
 def c4(args, out):
+    """configs[3]: EMU on N = 50k x M = 500k, 10 % missing calls, k = 10 (l = 20), winSVD in memory. Legs: the int8 route
+    with the FP64 correction over the missing calls (default), the same with PCAONE_EMU_TC=0 (update passes on the
+    FP64 DMMA kernels, what round 1 measured), and for the first a late update pass next to a late pass without the
+    fill (mean imputation only) with the per-kernel shares."""
     N, M, k = 50_000, int(500_000 * args.scale), 10
+    l = 2 * k
     packed = synth.torch_packed(N, M, k_pop=k + 4, miss=0.10, seed=4, device="cuda:0", chunk=4096)
-    p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, emu=True, precision=args.c4_prec)
-    d = halko.FileBed(p, packed=packed, nsamples=N)
-    op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
-    op.sync()
-    t0 = time.perf_counter()
-    iters = op.runEM()
-    secs = time.perf_counter() - t0
-    tm = op.timers(reset=True)
-    U = op.U
-    rec = {"config": "C4", "workload": f"EMU winSVD in-memory N={N} M={M} k={k} 10% missing, precision={args.c4_prec}",
-           "bytes_per_pass": M * packed.shape[1], "time_to_pcs_s": secs, "em_iterations": iters,
-           "missing_fraction": op.missing_count() / (N * M), "tc_ranges": int(tm.tc_ranges), "fp64_ranges": int(tm.fp64_ranges),
-           "U_orthonormality_err": float(np.abs(U.T @ U - np.eye(k)).max()), "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
-    op.close()
-    _emit(out, rec)
+    legs = [("int8x3 + FP64 correction over the missing calls", 3, "1"), ("update passes on the FP64 DMMA kernels", 3, "0")]
+    if args.c4_prec == 0:
+        legs = [("FP64 DMMA kernels throughout", 0, "1")]
+    for name, prec, sw in legs:
+        os.environ["PCAONE_EMU_TC"] = sw
+        p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, emu=True, precision=prec)
+        d = halko.FileBed(p, packed=packed, nsamples=N)
+        op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+        op.sync()
+        t0 = time.perf_counter()
+        iters = op.runEM()
+        secs = time.perf_counter() - t0
+        tm = op.timers(reset=True)
+        U = op.U
+        nmiss = op.missing_count()
+        rec = {"config": "C4", "workload": f"EMU winSVD in-memory N={N} M={M} k={k} 10% missing: {name}",
+               "bytes_per_pass": M * packed.shape[1], "time_to_pcs_s": secs, "em_iterations": iters,
+               "missing_fraction": nmiss / (N * M), "tc_ranges": int(tm.tc_ranges), "tc_emu_ranges": int(tm.tc_emu_ranges),
+               "fp64_ranges": int(tm.fp64_ranges), "kernel_launches": int(tm.kernel_launches),
+               "U_orthonormality_err": float(np.abs(U.T @ U - np.eye(k)).max()), "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
+        # one late epoch (pi >= 6: two half-range products, one Omega update) with and without the fill
+        op.enable_timing(True)
+        for label, upd in (("late_update_pass", True), ("late_plain_pass", False)):
+            op.setFlags(upd, False)
+            op.computeGandH(19, want=False)       # warm
+            op.sync()
+            op.timers(reset=True)
+            t0 = time.perf_counter()
+            op.computeGandH(20, want=False)
+            op.sync()
+            ms = 1e3 * (time.perf_counter() - t0)
+            t = op.timers(reset=True)
+            rec[label] = {"ms": ms, "gemm_g_ms": t.gemm_g_ms, "gemm_h_ms": t.gemm_h_ms, "tc_g_ms": t.tc_g_ms, "tc_h_ms": t.tc_h_ms,
+                          "emu_fix_ms": t.emu_fix_ms, "orth_ms": t.orth_ms, "tc_ranges": int(t.tc_ranges),
+                          "fp64_ranges": int(t.fp64_ranges), "gbs": M * packed.shape[1] / ms / 1e6}
+            if upd and t.emu_fix_ms > 0:
+                # FP64 work of the correction: per missing call and product a k-term dot and an l-term axpy
+                rec[label]["emu_fix_gflops"] = 2.0 * 2.0 * nmiss * (k + l) / t.emu_fix_ms / 1e6
+            if upd and t.fp64_ranges:
+                rec[label]["dmma_tflops"] = 2.0 * 2.0 * N * M * l / (t.gemm_g_ms + t.gemm_h_ms) / 1e9
+        op.close()
+        _emit(out, rec)
+    os.environ.pop("PCAONE_EMU_TC", None)
 
 
 def c5(args, out):
@@ -404,7 +437,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="multiply every M by this (debug)")
     ap.add_argument("--out", default="")
     ap.add_argument("--no-ref", action="store_true")
-    ap.add_argument("--c4-prec", type=int, default=0)
+    ap.add_argument("--c4-prec", type=int, default=3)
     args = ap.parse_args()
     _lib.load()
     fns = {"c1": c1, "c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "bgen": f_bgen, "beagle": f_beagle, "prune": f_prune,
