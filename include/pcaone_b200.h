@@ -298,6 +298,17 @@ int pcaone_dense_rsvd(pcaone_ctx* ctx, uint32_t p, uint32_t windows, int finder)
 int pcaone_ld_prune(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we,
                     uint64_t nwin, const double* af, double r2_tol, uint8_t* keep_out);
 
+/* ---- exact PCA (`--svd 3`, Main.cpp:180-217) and the PCAngsd GRM step (Halko.cpp:320-334) -----------
+ * pcaone_sample_covariance: K_out (nsamples x nsamples doubles, column-major, host) = X X^T for the context's
+ * source and pcaone_set_flags state — the reference's `data->G * data->G.transpose()` (the caller divides by
+ * nsnps, Main.cpp:187 / Halko.cpp:324). Computed as panels of k + oversamples unit vectors through the operator
+ * X (X^T .) on the FP64 kernels, whatever the context's GEMM precision; SNP-sharded contexts sum the panels.
+ * pcaone_sym_svd: SVD of a symmetric n x n host matrix on the device (one-sided Jacobi): S_out descending
+ * (= eigenvalues of a positive semi-definite A, what SelfAdjointEigenSolver returns in ascending order), U_out
+ * n x n column-major (= the eigenvectors; JacobiSVD's matrixU up to sign). sweeps_out may be NULL. */
+int pcaone_sample_covariance(pcaone_ctx* ctx, double* K_out);
+int pcaone_sym_svd(pcaone_ctx* ctx, const double* A, uint64_t n, double* U_out, double* S_out, int* sweeps_out);
+
 /* ---- measurement ------------------------------------------------------------------- */
 typedef struct pcaone_timers {
   double gemm_g_ms, gemm_h_ms, orth_ms, small_ms, h2d_ms, allreduce_ms, decode_ms;

@@ -204,6 +204,19 @@ class Ref:
                                      _p(keep), C.c_longlong(int(self.M))))
         return keep.astype(bool)
 
+    def ld_clump(self, filebim, assoc, fileout, colnames="CHR,BP,P", clump_bp=250000, clump_r2=0.5, p1=1e-4, p2=1e-2):
+        """the clump branch of run_ld_stuff (LD.cpp:505-540) on data->G -> writes `fileout` like the reference."""
+        self._chk(lib().ref_ld_clump(self.h, filebim.encode(), assoc.encode(), colnames.encode(), int(clump_bp),
+                                     C.c_double(clump_r2), C.c_double(p1), C.c_double(p2), fileout.encode()))
+
+    def full_pca(self, k):
+        """the FULL branch of main() (Main.cpp:180-217, --svd 3) -> U (N x k), svals, V (M x k), evals."""
+        k = min(int(k), int(self.N), int(self.M))
+        U, V = _f((int(self.N), k)), _f((int(self.M), k))
+        S, E = np.zeros(k), np.zeros(k)
+        self._chk(lib().ref_full_pca(self.h, k, _p(U), _p(S), _p(V), _p(E)))
+        return U, S, V, E
+
     def P(self):
         """Beagle input: the 2N x M likelihood matrix parse_beagle_file filled."""
         n = lib().ref_get_P(self.h, None)

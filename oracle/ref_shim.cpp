@@ -481,6 +481,57 @@ int ref_ld_prune(void* h, const char* filebim, int ld_bp, double r2_tol, const c
   });
 }
 
+// LD-based clumping of one association file on data->G (the clump branch of run_ld_stuff, LD.cpp:505-540):
+// the reference's own valid_assoc_file / get_snp_pos_bim / map_index_snps / get_target_snp_idx /
+// ld_clump_single_pheno; the result is the text file the reference writes.
+int ref_ld_clump(void* h, const char* filebim, const char* assoc, const char* colnames, int clump_bp, double clump_r2,
+                 double p1, double p2, const char* fileout) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    SNPld snp;
+    get_snp_pos_bim(snp, filebim);
+    const auto colidx = valid_assoc_file(assoc, colnames);
+    SNPld snp_t;
+    const std::string head = get_snp_pos_bim(snp_t, assoc, true, colidx);
+    const auto pvals = map_index_snps(assoc, colidx, p2);
+    Int2D idx_per_chr, bp_per_chr;
+    std::tie(idx_per_chr, bp_per_chr) = get_target_snp_idx(snp_t, snp);
+    ld_clump_single_pheno(fileout, head, clump_bp, clump_r2, p1, p2, c->data->G, idx_per_chr, bp_per_chr, pvals);
+  });
+}
+
+// The FULL branch of main() (Main.cpp:180-217, `--svd 3`) for nsamples <= nsnps, on this run's in-core data:
+// standardize_E, K = G G^T / nsnps, SelfAdjointEigenSolver, V = G^T U / svals, flip_UV — the reference's own
+// Data / Eigen / flip_UV calls (main() itself cannot be linked). U: N x k, V: M x k, column-major.
+int ref_full_pca(void* h, int k, double* U_out, double* svals_out, double* V_out, double* evals_out) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    Data* data = c->data;
+    if (data->nsamples > data->nsnps) throw std::runtime_error("ref_full_pca: the sample-covariance branch only");
+    data->standardize_E();
+    const Eigen::Index ncomp = std::min<Eigen::Index>(k, std::min<Eigen::Index>(data->G.rows(), data->G.cols()));
+    Mat2D K = (data->G * data->G.transpose()) / data->nsnps;
+    Eigen::SelfAdjointEigenSolver<Mat2D> eig(K);
+    if (eig.info() != Eigen::Success) throw std::runtime_error("eigendecomposition failed");
+    Mat1D evals(ncomp), svals(ncomp);
+    Mat2D U(data->nsamples, ncomp), V(data->nsnps, ncomp);
+    for (Eigen::Index i = 0; i < ncomp; ++i) {
+      const Eigen::Index idx = eig.eigenvalues().size() - 1 - i;
+      evals(i) = std::max(0.0, eig.eigenvalues()(idx));
+      U.col(i) = eig.eigenvectors().col(idx);
+    }
+    svals = (evals.array() * data->nsnps).sqrt();
+    V.noalias() = data->G.transpose() * U;
+    for (Eigen::Index i = 0; i < ncomp; ++i)
+      if (svals(i) > 0) V.col(i) /= svals(i);
+    flip_UV(U, V);
+    std::memcpy(U_out, U.data(), sizeof(double) * U.size());
+    std::memcpy(V_out, V.data(), sizeof(double) * V.size());
+    std::memcpy(svals_out, svals.data(), sizeof(double) * ncomp);
+    std::memcpy(evals_out, evals.data(), sizeof(double) * ncomp);
+  });
+}
+
 // Beagle input: the parsed likelihood matrix P (2N x M, column-major) as FileBeagle::read_all left it.
 long long ref_get_P(void* h, double* out) {
   RefCtx* c = (RefCtx*)h;

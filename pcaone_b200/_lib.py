@@ -107,6 +107,7 @@ def load():
         "pcaone_ld_r2_ex": [vp, C.POINTER(LdSource), u64, vp, vp, u64, vp, vp, dbl, vp],
         "pcaone_residuals_block": [vp, u64, u64, i32, vp], "pcaone_precision": [vp], "pcaone_comm_peer_export": [vp, vp], "pcaone_comm_peer_import": [vp, vp, i32],
         "pcaone_set_host_source2": [vp, vp, u64, u64], "pcaone_set_allreduce2": [vp, ALLREDUCE2_FN, vp],
+        "pcaone_sample_covariance": [vp, vp], "pcaone_sym_svd": [vp, vp, u64, vp, vp, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.pcaone_alloc_pinned.restype = C.c_int

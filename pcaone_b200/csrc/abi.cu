@@ -334,6 +334,15 @@ int pcaone_x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out) 
 
 int pcaone_perform_op(pcaone_ctx* c, const double* x_in, double* y_out) { CTX_GUARD(c, perform_op(c, x_in, y_out)); }
 
+int pcaone_sample_covariance(pcaone_ctx* c, double* K_out) { CTX_GUARD(c, sample_covariance(c, K_out)); }
+
+int pcaone_sym_svd(pcaone_ctx* c, const double* A, uint64_t n, double* U_out, double* S_out, int* sweeps_out) {
+  CTX_GUARD(c, {
+    const int sw = sym_svd(c, A, n, U_out, S_out);
+    if (sweeps_out) *sweeps_out = sw;
+  });
+}
+
 int pcaone_upload_dosage(pcaone_ctx* c, const float* dosage, uint64_t nsnps, int device_ptr) {
   CTX_GUARD(c, {
     if (nsnps != c->M) throw std::runtime_error("upload_dosage: nsnps does not match the context");

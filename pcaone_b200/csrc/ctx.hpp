@@ -308,6 +308,10 @@ void compute_usv(pcaone_ctx* c, int p, double tol);
 void run_em(pcaone_ctx* c, int* iters_out);
 void set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint32_t nblocks, uint32_t band_factor);
 void perform_op(pcaone_ctx* c, const double* x_in, double* y_out);
+void walk_ranges(pcaone_ctx* c);
+void allreduce_H(pcaone_ctx* c, double* H);
+void sample_covariance(pcaone_ctx* c, double* K_out);                                       // launch_cov.cu
+int sym_svd(pcaone_ctx* c, const double* A, uint64_t n, double* U_out, double* S_out);     // launch_cov.cu
 void xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, double* sqnorm);
 void x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out);
 void dense_onepass(pcaone_ctx* c, uint32_t p, uint32_t windows, int finder);

@@ -507,6 +507,40 @@ class RsvdOpData:
         F = np.ascontiguousarray(F, dtype=np.float64)
         self._chk(self.L.pcaone_set_F(self.h, _vp(F)))
 
+    def sampleCovariance(self):
+        """X X^T (N x N) for the current flags: `data->G * data->G.transpose()` of Main.cpp:187 / Halko.cpp:323,
+        FP64 GEMM panels on the device."""
+        K = _f((self.cols(), self.cols()))
+        self._chk(self.L.pcaone_sample_covariance(self.h, _vp(K)))
+        return K
+
+    def symSVD(self, A):
+        """SVD of a symmetric matrix on the device (one-sided Jacobi): (U, S) with S descending."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        n = A.shape[0]
+        U, S = _f((n, n)), np.zeros(n)
+        sw = C.c_int(0)
+        self._chk(self.L.pcaone_sym_svd(self.h, _vp(A), n, _vp(U), _vp(S), C.byref(sw)))
+        self.jacobi_sweeps = sw.value
+        return U, S
+
+    def exactPCA(self):
+        """`--svd 3` (Main.cpp:180-217): K = G G^T / nsnps on the standardised genotypes, its eigen-decomposition,
+        V = G^T U / sqrt(eval nsnps), flip_UV by the largest |U| entry. Sets U, S, V and returns the eigenvalues."""
+        self.setFlags(False, True)
+        N, M = self.cols(), self.rows()
+        ncomp = min(self.nk, N, M)
+        Uall, Sall = self.symSVD(self.sampleCovariance() / M)
+        evals = np.maximum(0.0, Sall[:ncomp])
+        U = np.asfortranarray(Uall[:, :ncomp])
+        svals = np.sqrt(evals * M)
+        V = self.xtTimes(U)
+        V[:, svals > 0] /= svals[svals > 0]
+        x = np.abs(U).argmax(axis=0)
+        sgn = np.where(U[x, np.arange(ncomp)] < 0, -1.0, 1.0)
+        self.U, self.S, self.V = np.asfortranarray(U * sgn), svals, np.asfortranarray(V * sgn)
+        return evals
+
     def xtTimes(self, A, want_sqnorm=False):
         """X^T A (M x c) [+ per-SNP squared norms]: Selection.cpp:16-34."""
         A = np.asfortranarray(A, dtype=np.float64)

@@ -132,12 +132,14 @@ Param::Param(int argc, char** argv) {
   off_path("", "inbreed", true);
   off_path("", "selection", true);
   val("", "ld-r2", "r2 cutoff for LD-based pruning (usually 0.2).", [this](const std::string& v) { ld_r2 = std::stod(v); });
-  off_path("", "clump", true);
-  off_path("", "clump-names", true);
-  off_path("", "clump-p1", true);
-  off_path("", "clump-p2", true);
-  off_path("", "clump-r2", true);
-  off_path("", "clump-bp", true);
+  val("", "clump", "assoc-like file with target variants and pvalues for clumping.", [this](const std::string& v) { clump = v; });
+  val("", "clump-names", "column names in assoc-like file for locating chr, pos and pvalue.",
+      [this](const std::string& v) { assoc_colnames = v; });
+  val("", "clump-p1", "significance threshold for index SNPs.", [this](const std::string& v) { clump_p1 = std::stod(v); });
+  val("", "clump-p2", "secondary significance threshold for clumped SNPs.", [this](const std::string& v) { clump_p2 = std::stod(v); });
+  val("", "clump-r2", "r2 cutoff for LD-based clumping.", [this](const std::string& v) { clump_r2 = std::stod(v); });
+  val("", "clump-bp", "physical distance threshold in bases for clumping.",
+      [this](const std::string& v) { clump_bp = (uint)std::stoul(v); });
   off_path("", "scale-factor", true);
   off_path("", "imaxiter", true);
   off_path("", "itol", true);
@@ -213,8 +215,10 @@ Param::Param(int argc, char** argv) {
       svd_t = SvdType::PCAoneAlg1;
     else if (svd == 2)
       svd_t = SvdType::PCAoneAlg2;
+    else if (svd == 3)
+      svd_t = SvdType::FULL;  // exact PCA: covariance GEMM + eigen-decomposition on the device (Main.cpp:180-217)
     else
-      throw std::invalid_argument("--svd 0 (IRAM) and 3 (full SVD) are outside the B200 randomized-SVD path; use --svd 1 or 2");
+      throw std::invalid_argument("--svd 0 (IRAM: the Spectra driver) is outside the B200 path; use --svd 1, 2 or 3");
     if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY)
       throw std::invalid_argument("please give the PLINK prefix with -b/--bfile, a BEAGLE file with -G/--beagle, or -B residuals for LD");
     genetic = true;
@@ -225,7 +229,7 @@ Param::Param(int argc, char** argv) {
       fileV = usvprefix + ".loadings";
       if (filebim.empty()) filebim = usvprefix + ".mbim";
     }
-    if (print_r2 || ld_r2 > 0) {  // Cmd.cpp:181-184
+    if (print_r2 || ld_r2 > 0 || !clump.empty()) {  // Cmd.cpp:181-184
       dopca = false;
       memory /= 2.0;
     }

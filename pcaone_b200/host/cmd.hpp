@@ -49,6 +49,12 @@ class Param {
   double ld_r2 = 0;
   bool ld = false;
   uint ld_bp = 1000000;
+  std::string clump;  // comma separated assoc-like files (Cmd.hpp:62-68)
+  std::string assoc_colnames = "CHR,BP,P";
+  double clump_p1 = 0.0001;
+  double clump_p2 = 0.01;
+  double clump_r2 = 0.5;
+  uint clump_bp = 250000;
   uint verbose = 1;
   int scale = SCALE_STANDARDIZE_GENETIC;
   bool printv = false;

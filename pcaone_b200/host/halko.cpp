@@ -4,6 +4,8 @@
 // pcaone_compute_usv / pcaone_run_em on the device.
 #include "halko.hpp"
 
+#include <cmath>
+
 #include <atomic>
 #include <condition_variable>
 #include <thread>
@@ -104,6 +106,49 @@ void run_pca_with_halko(Data* data, const Param& params, const std::function<voi
   if (data->shard.rank == 0) write_pca(data, rsvd, params);
   delete rsvd;
   cao.print(tick.date(), "PCAone - Randomized SVD done");
+}
+
+// --svd 3, Main.cpp:180-217: exact PCA through the sample covariance. K = G G^T / nsnps on the standardised genotypes
+// (pcaone_sample_covariance: FP64 GEMM panels on the device), its eigen-decomposition (pcaone_sym_svd: one-sided
+// Jacobi on the device), V = G^T U / sqrt(eval * nsnps) (pcaone_xt_times), flip_UV by the largest |U| entry.
+// The reference switches to the SNP x SNP covariance when nsamples > nsnps; the non-zero spectrum and its vectors are
+// the same, and only the N x N form is built here.
+void run_pca_full(Data* data, const Param& params) {
+  cao.print(tick.date(), "running exact PCA with in-core eigendecomposition (PLINK-like).");
+  const uint64 N = data->nsamples, M = data->nsnps;
+  const uint64 ncomp = std::min<uint64>(params.k, std::min(N, M));
+  data->check(pcaone_set_flags(data->ctx, 0, 1));  // standardize_E
+  Mat2D K(N, N), Uall(N, N);
+  Mat1D Sall(N);
+  data->check(pcaone_sample_covariance(data->ctx, K.data()));
+  for (auto& x : K.v) x /= (double)M;
+  int sweeps = 0;
+  data->check(pcaone_sym_svd(data->ctx, K.data(), N, Uall.data(), Sall.data(), &sweeps));
+  cao.print(tick.date(), "eigendecomposition of the", N, "x", N, "sample covariance on the device, Jacobi sweeps =", sweeps);
+  Mat1D evals(ncomp), svals(ncomp);
+  Mat2D U(N, ncomp), V(M, ncomp);
+  for (uint64 i = 0; i < ncomp; ++i) {
+    evals(i) = std::max(0.0, Sall(i));
+    svals(i) = std::sqrt(evals(i) * (double)M);
+    for (uint64 r = 0; r < N; ++r) U(r, i) = Uall(r, i);
+  }
+  data->check(pcaone_xt_times(data->ctx, U.data(), (uint32_t)ncomp, V.data(), nullptr));
+  for (uint64 i = 0; i < ncomp; ++i) {
+    if (svals(i) > 0)
+      for (uint64 r = 0; r < M; ++r) V(r, i) /= svals(i);
+    uint64 x = 0;  // flip_UV (Utils.cpp:118-133): the largest |U| entry of every component is positive
+    for (uint64 r = 1; r < N; ++r)
+      if (std::fabs(U(r, i)) > std::fabs(U(x, i))) x = r;
+    if (U(x, i) < 0) {
+      for (uint64 r = 0; r < N; ++r) U(r, i) = -U(r, i);
+      for (uint64 r = 0; r < M; ++r) V(r, i) = -V(r, i);
+    }
+  }
+  if (data->F.size() != M) {
+    data->F.resize(M);
+    data->check(pcaone_get_F(data->ctx, data->F.data()));
+  }
+  data->write_eigs_files(evals, svals, U, V);
 }
 
 void make_plink2_eigenvec_file(int K, const std::string& fout, const std::string& fin, const std::string& fam) {

@@ -30,7 +30,7 @@ int main(int argc, char* argv[]) {
   try {
     if (pcaone_device_count() == 0) cao.error("no CUDA device is visible: pcaone_b200 has no CPU fallback");
     // LD from a bed (Main.cpp:78-97): windows from the .bim, r2 on the device
-    if (params.print_r2 || params.ld_r2 > 0) {
+    if (params.print_r2 || params.ld_r2 > 0 || !params.clump.empty()) {
       params.memory = 0, params.out_of_core = false;  // Main.cpp:84
       params.perm = false;
       if (params.file_t == FileType::BINARY) {  // Main.cpp:149-150: -B file.residuals
@@ -42,7 +42,7 @@ int main(int argc, char* argv[]) {
       run_ld_stuff(&data, params);
       return bye();
     }
-    if (params.file_t == FileType::BINARY) cao.error("-B (binary residuals) is an LD input: give --print-r2 or --ld-r2");
+    if (params.file_t == FileType::BINARY) cao.error("-B (binary residuals) is an LD input: give --print-r2, --ld-r2 or --clump");
     if (params.file_t == FileType::BEAGLE) {  // Main.cpp:117-120 + Halko.cpp:290-311 (PCAngsd EM)
       FileBeagle data(params);
       data.tolmaf = params.tolmaf;
@@ -51,7 +51,13 @@ int main(int argc, char* argv[]) {
       cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
       return bye();
     }
-    if (params.gpus > 1) {
+    if (params.svd_t == SvdType::FULL) {
+      if (params.gpus > 1 || params.out_of_core) cao.error("--svd 3 runs in core on one GPU");
+      params.perm = false;
+      FileBed data(params);
+      data.prepare();
+      run_pca_full(&data, params);
+    } else if (params.gpus > 1) {
       run_pca_sharded(params);
     } else {
       FileBed data(params);

@@ -323,3 +323,99 @@ def test_cli_ld_two_step_through_residual_file(tmp_path):
     assert lines[0].split("\t")[-1] == "R2" and len(lines) == len(want) + 1
     got = np.array([float(x.split("\t")[-1]) for x in lines[1:]])
     assert np.abs(got - want).max() < 2e-5   # 6 decimals in the text + two independent RSVD runs behind the residuals
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["bed", "residuals"])
+def test_cli_ld_clump_vs_reference(tmp_path, source):
+    """--clump: <out>.p0.clump against the file the unmodified reference writes (ld_clump_single_pheno, LD.cpp:323-401,
+    with its bookkeeping of chromosome runs) for the same association table — from the centred genotypes of the bed and
+    from a `-B` residual file. The r2 values come from one banded tile Gram on the device (one forward window per
+    candidate), the greedy pass runs on the host."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M = 300, 3000
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=4, seed=36)
+    rng = np.random.default_rng(3)
+    assoc = str(tmp_path / "gwas.tsv")
+    keep = np.sort(rng.choice(M, size=2400, replace=False))        # the table lists a subset of the variants ...
+    pv = rng.uniform(0, 0.03, size=M) ** 2                          # ... about half of them under p2, a tenth under p1
+    with open(assoc, "w") as f:
+        f.write("SNP\tCHR\tBP\tBETA\tP\n")
+        for j, ln in enumerate(open(prefix + ".bim")):
+            if j in set(keep.tolist()):
+                c, rs, _, bp, _, _ = ln.split()
+                f.write(f"{rs}\t{c}\t{bp}\t{rng.normal():.4f}\t{pv[j]:.10g}\n")
+        f.write(f"rsX\t22\t999999999\t0.1\t1e-9\n")           # a position the bim does not have
+    args = dict(clump_bp=4000, clump_r2=0.02, p1=1e-4, p2=5e-4)
+    out = str(tmp_path / "o")
+    if source == "bed":
+        r = ref.Ref(f"PCAone -b {prefix} -k 2 -d 1 -o {tmp_path}/r -n 4", threads=4)
+        r.ld_clump(prefix + ".bim", assoc, str(tmp_path / "ref.clump"), **args)
+        r.close()
+        _run(["-b", prefix, "--clump", assoc, "--clump-bp", 4000, "--clump-r2", 0.02, "--clump-p1", 1e-4, "--clump-p2", 5e-4,
+              "-o", out])
+    else:
+        _run(["-b", prefix, "-k", 3, "-d", 1, "--ld", "-o", str(tmp_path / "pc")])
+        r = ref.Ref(f"PCAone -B {tmp_path}/pc.residuals -F {tmp_path}/pc.mbim --print-r2 -o {tmp_path}/r -n 4", threads=4)
+        r.ld_clump(str(tmp_path / "pc.mbim"), assoc, str(tmp_path / "ref.clump"), **args)
+        r.close()
+        _run(["-B", str(tmp_path / "pc.residuals"), "-F", str(tmp_path / "pc.mbim"), "--clump", assoc, "--clump-bp", 4000,
+              "--clump-r2", 0.02, "--clump-p1", 1e-4, "--clump-p2", 5e-4, "-o", out])
+    want = open(tmp_path / "ref.clump").read().splitlines()
+    got = open(out + ".p0.clump").read().splitlines()
+    assert want[0] == got[0] and want[0].endswith("\tSP2")
+    n_clumped = sum(1 for l in want[1:] if not l.endswith("NONE"))
+    assert len(want) > 30 and n_clumped > 5, (len(want), n_clumped)
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_cli_print_r2_with_usv_projection(tmp_path):
+    """-b + --USV + --print-r2: LD of (I - U U^T) G (LD.cpp:491-496) with U read from <prefix>.eigvecs, the projection
+    applied on the device; against the numpy restatement on the same U."""
+    from oracle import pcaone_oracle as orc
+    N, M = 300, 1500
+    prefix = str(tmp_path / "s")
+    packed = synth.write_bed(prefix, N, M, k_pop=4, seed=37)
+    pc = str(tmp_path / "pc")
+    _run(["-b", prefix, "-k", 3, "-d", 1, "-o", pc])
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "--USV", pc, "-F", prefix + ".bim", "--print-r2", "--ld-bp", 3000, "-o", out])
+    lines = gzip.open(out + ".ld.gz", "rt").read().splitlines()
+    r2 = np.array([float(l.split("\t")[6]) for l in lines[1:]])
+    U = np.loadtxt(pc + ".eigvecs", ndmin=2)
+    od = orc.OracleData(packed, N)
+    G = od.block(0, M - 1, False)
+    Gp = G - U @ (U.T @ G)
+    chrom = np.array([l.split()[0] for l in open(prefix + ".bim")])
+    pos = np.array([int(l.split()[3]) for l in open(prefix + ".bim")])
+    ws, we = orc.ld_windows(chrom, pos, 3000)
+    want = orc.ld_r2(Gp, ws, we)
+    assert r2.shape == want.shape
+    assert np.abs(r2 - want).max() < 2e-6  # std::to_string keeps 6 decimals
+    plain = orc.ld_r2(G, ws, we)
+    assert np.abs(plain - want).max() > 1e-3, "the projection must matter in this case"
+
+
+@pytest.mark.gpu
+def test_cli_svd3_exact_pca_vs_reference(tmp_path):
+    """--svd 3: .eigvals / .sigvals / .eigvecs / .loadings of the exact PCA against the reference's FULL branch."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, k = 320, 2500, 6
+    prefix = str(tmp_path / "s")
+    synth.write_bed(prefix, N, M, k_pop=5, seed=42)
+    r = ref.Ref(f"PCAone -b {prefix} -k {k} -d 1 -o {tmp_path}/r -n 8", threads=8)
+    Ur, Sr, Vr, Er = r.full_pca(k)
+    r.close()
+    out = str(tmp_path / "o")
+    _run(["-b", prefix, "-k", k, "--svd", 3, "-V", "-o", out])
+    U, S, V = _load(out, k, M)
+    np.testing.assert_allclose(S, Sr, rtol=2e-5)
+    np.testing.assert_allclose(np.loadtxt(out + ".eigvals"), Er, rtol=2e-5)
+    assert np.abs(U[:, :4] - Ur[:, :4]).max() < 2e-5 and np.abs(V[:, :4] - Vr[:, :4]).max() < 2e-5   # 6 significant digits
+    assert col_cos(U, Ur).min() > 0.99999 and col_cos(V, Vr).min() > 0.99999
