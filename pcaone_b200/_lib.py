@@ -62,6 +62,7 @@ SYMBOLS = [
     "pcaone_upload_gl", "pcaone_gl_em_maf",
     "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
     "pcaone_ld_r2_ex", "pcaone_residuals_block", "pcaone_precision", "pcaone_comm_peer_export", "pcaone_comm_peer_import",
+    "pcaone_sample_covariance", "pcaone_sym_svd",
 ]
 
 _lib = None
