@@ -273,7 +273,7 @@ int pcaone_upload_dosage(pcaone_ctx* ctx, const float* dosage, uint64_t nsnps, i
  * every computeUSV — from F, or on update passes from the individual allele frequencies of the current
  * U, S, V — and feed the dense FP64 products; pcaone_run_em (with emu = 0) is the PCAngsd EM loop,
  * pcaone_decode_block returns E blocks. precision = PCAONE_PREC_FP64, single GPU. The GRM step after
- * the loop (pcangsd_standardize_E + the N x N covariance, Halko.cpp:320-334) is not built. */
+ * the loop (pcangsd_standardize_E + the N x N covariance, Halko.cpp:320-334) is pcaone_gl_grm + pcaone_sym_svd. */
 int pcaone_upload_gl(pcaone_ctx* ctx, const double* P, uint64_t nsnps, int device_ptr);
 int pcaone_gl_em_maf(pcaone_ctx* ctx, uint32_t maxiter, double tolmaf, int* iters_out);
 
@@ -307,6 +307,12 @@ int pcaone_ld_prune(pcaone_ctx* ctx, const double* G, uint64_t nsnps, const int3
  * (= eigenvalues of a positive semi-definite A, what SelfAdjointEigenSolver returns in ascending order), U_out
  * n x n column-major (= the eigenvectors; JacobiSVD's matrixU up to sign). sweeps_out may be NULL. */
 int pcaone_sample_covariance(pcaone_ctx* ctx, double* K_out);
+/* The PCAngsd GRM step (Halko.cpp:320-326) after pcaone_run_em on a genotype-likelihood source: the expected
+ * genotypes are re-standardised with the individual allele frequencies of the final U, S, V
+ * (pcangsd_standardize_E, Data.cpp:364-407), C_out (nsamples x nsamples, column-major, host) = E E^T / nsnps with
+ * its diagonal replaced by Dc / nsnps; Dc_out (nsamples) may be NULL. pcaone_sym_svd(C) then gives the
+ * eigenvectors the reference writes to .eigvecs2 (JacobiSVD's matrixU, up to sign). */
+int pcaone_gl_grm(pcaone_ctx* ctx, double* C_out, double* Dc_out);
 int pcaone_sym_svd(pcaone_ctx* ctx, const double* A, uint64_t n, double* U_out, double* S_out, int* sweeps_out);
 
 /* ---- measurement ------------------------------------------------------------------- */

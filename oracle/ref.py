@@ -217,6 +217,13 @@ class Ref:
         self._chk(lib().ref_full_pca(self.h, k, _p(U), _p(S), _p(V), _p(E)))
         return U, S, V, E
 
+    def pcangsd_grm(self):
+        """the GRM step after run_em on a Beagle run (Halko.cpp:320-334) -> C (N x N), U2 (JacobiSVD matrixU), S2, Dc."""
+        n = int(self.N)
+        Cm, U2, S2, Dc = _f((n, n)), _f((n, n)), np.zeros(n), np.zeros(n)
+        self._chk(lib().ref_pcangsd_grm(self.h, _p(Cm), _p(U2), _p(S2), _p(Dc)))
+        return Cm, U2, S2, Dc
+
     def P(self):
         """Beagle input: the 2N x M likelihood matrix parse_beagle_file filled."""
         n = lib().ref_get_P(self.h, None)

@@ -532,6 +532,26 @@ int ref_full_pca(void* h, int k, double* U_out, double* svals_out, double* V_out
   });
 }
 
+// The GRM step of run_pca_with_halko for PCAngsd (Halko.cpp:320-334) after ref_run_em on a Beagle run: the
+// reference's own pcangsd_standardize_E, the covariance with its Dc diagonal, Eigen's JacobiSVD. C, U2: N x N.
+int ref_pcangsd_grm(void* h, double* C_out, double* U2_out, double* S2_out, double* Dc_out) {
+  RefCtx* c = (RefCtx*)h;
+  return guarded([&] {
+    Data* data = c->data;
+    data->pcangsd_standardize_E(c->op->U, c->op->S, c->op->V.transpose());
+    Mat2D C = data->G * data->G.transpose();
+    C.array() /= (double)data->nsnps;
+    C.diagonal() = data->Dc.array() / (double)data->nsnps;
+    Eigen::JacobiSVD<Mat2D> svd(C, Eigen::ComputeThinU | Eigen::ComputeThinV);
+    std::memcpy(C_out, C.data(), sizeof(double) * C.size());
+    Mat2D U2 = svd.matrixU();
+    std::memcpy(U2_out, U2.data(), sizeof(double) * U2.size());
+    Mat1D S2 = svd.singularValues();
+    std::memcpy(S2_out, S2.data(), sizeof(double) * S2.size());
+    std::memcpy(Dc_out, data->Dc.data(), sizeof(double) * data->Dc.size());
+  });
+}
+
 // Beagle input: the parsed likelihood matrix P (2N x M, column-major) as FileBeagle::read_all left it.
 long long ref_get_P(void* h, double* out) {
   RefCtx* c = (RefCtx*)h;

@@ -336,6 +336,8 @@ int pcaone_perform_op(pcaone_ctx* c, const double* x_in, double* y_out) { CTX_GU
 
 int pcaone_sample_covariance(pcaone_ctx* c, double* K_out) { CTX_GUARD(c, sample_covariance(c, K_out)); }
 
+int pcaone_gl_grm(pcaone_ctx* c, double* C_out, double* Dc_out) { CTX_GUARD(c, gl_grm(c, C_out, Dc_out)); }
+
 int pcaone_sym_svd(pcaone_ctx* c, const double* A, uint64_t n, double* U_out, double* S_out, int* sweeps_out) {
   CTX_GUARD(c, {
     const int sw = sym_svd(c, A, n, U_out, S_out);

@@ -310,6 +310,8 @@ void set_blocks(pcaone_ctx* c, const uint64_t* start, const uint64_t* stop, uint
 void perform_op(pcaone_ctx* c, const double* x_in, double* y_out);
 void walk_ranges(pcaone_ctx* c);
 void allreduce_H(pcaone_ctx* c, double* H);
+void gl_grm_standardize(pcaone_ctx* c, double* d_Dc);                                       // launch_fp64.cu
+void gl_grm(pcaone_ctx* c, double* C_out, double* Dc_out);                                  // launch_cov.cu
 void sample_covariance(pcaone_ctx* c, double* K_out);                                       // launch_cov.cu
 int sym_svd(pcaone_ctx* c, const double* A, uint64_t n, double* U_out, double* S_out);     // launch_cov.cu
 void xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out, double* sqnorm);

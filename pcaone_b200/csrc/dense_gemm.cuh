@@ -525,6 +525,46 @@ __global__ void k_gl_expected(const double* __restrict__ P, uint32_t N, uint64_t
   }
 }
 
+// pcangsd_standardize_E (Data.cpp:364-407): with the individual allele frequencies of the final U, S, V,
+//   E[j][i] = ((p1 + 2 p2) / pSum - 2 F_j) / sqrt(2 F_j (1 - F_j))      (the division only when the norm > kVarTol)
+//   Dc[i]  += ((0-2F)^2 p0 + (1-2F)^2 p1 + (2-2F)^2 p2) / pSum / (2 F_j (1 - F_j))
+// One thread per sample, blockIdx.y walks SNP slices: the diagonal sums stay in a register and reach memory as ONE
+// atomic per thread and slice.
+__global__ void __launch_bounds__(256) k_gl_grm(const double* __restrict__ P, uint32_t N, uint64_t rows,
+                                                uint64_t rows_per_slice, const double* __restrict__ F,
+                                                const double* __restrict__ U, int ldu, const double* __restrict__ S,
+                                                const double* __restrict__ V, int ldv, int k, double* __restrict__ E,
+                                                uint32_t ldd, double* __restrict__ Dc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint64_t j0 = (uint64_t)blockIdx.y * rows_per_slice, j1 = min(rows, j0 + rows_per_slice);
+  double dc = 0.0;
+  for (uint64_t j = j0; j < j1; ++j) {
+    const double f = F[j];
+    double pt = 0.0;
+    for (int r = 0; r < k; ++r) pt = __dadd_rn(pt, __dmul_rn(__dmul_rn(U[(uint64_t)i * ldu + r], S[r]), V[j * ldv + r]));
+    pt = __ddiv_rn(__dadd_rn(pt, __dmul_rn(2.0, f)), 2.0);
+    pt = fmin(fmax(pt, 1e-4), 1.0 - 1e-4);
+    const double2 g = reinterpret_cast<const double2*>(P + j * 2ull * N)[i];
+    const double omp = __dsub_rn(1.0, pt);
+    const double p0 = __dmul_rn(__dmul_rn(g.x, omp), omp);
+    const double p1 = __dmul_rn(__dmul_rn(__dmul_rn(g.y, 2.0), pt), omp);
+    const double p2 = __dmul_rn(__dmul_rn(__dsub_rn(__dsub_rn(1.0, g.x), g.y), pt), pt);
+    const double ps = __dadd_rn(__dadd_rn(p0, p1), p2);
+    const double tf = __dmul_rn(2.0, f);
+    const double norm = __dsqrt_rn(__dmul_rn(tf, __dsub_rn(1.0, f)));
+    double e = __dsub_rn(__ddiv_rn(__dadd_rn(p1, __dmul_rn(2.0, p2)), ps), tf);
+    if (norm > kVarTol) e = __ddiv_rn(e, norm);
+    E[j * ldd + i] = e;
+    const double d0 = __dsub_rn(0.0, tf), d1 = __dsub_rn(1.0, tf), d2 = __dsub_rn(2.0, tf);
+    double t = __dmul_rn(__dmul_rn(d0, d0), __ddiv_rn(p0, ps));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn(d1, d1), __ddiv_rn(p1, ps)));
+    t = __dadd_rn(t, __dmul_rn(__dmul_rn(d2, d2), __ddiv_rn(p2, ps)));
+    dc = __dadd_rn(dc, __ddiv_rn(t, __dmul_rn(tf, __dsub_rn(1.0, f))));
+  }
+  atomicAdd(&Dc[i], dc);
+}
+
 // col-major (rows x cols, ld = rows) -> row-major [rows][ldd], 32 x 32 tiles through shared memory
 __global__ void __launch_bounds__(256) k_dense_transpose_in(const double* __restrict__ src, uint64_t rows, uint64_t cols,
                                                              double* __restrict__ dst, uint32_t ldd) {

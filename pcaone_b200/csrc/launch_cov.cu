@@ -37,6 +37,28 @@ void sample_covariance(pcaone_ctx* c, double* K_out) {
   c->omega_img_valid = c->omega_colmax_valid = false;
 }
 
+// The PCAngsd GRM step (Halko.cpp:320-326): E <- pcangsd_standardize_E(U, S, V), C = E E^T / nsnps with the diagonal
+// replaced by Dc / nsnps. C_out: N x N column-major on the host; Dc_out (N) may be NULL. The dense operand of the
+// context holds the standardised E afterwards (the next computeUSV rebuilds it at pi = 0).
+void gl_grm(pcaone_ctx* c, double* C_out, double* Dc_out) {
+  double* d_Dc = nullptr;
+  try {
+    dmalloc(&d_Dc, c->N);
+    gl_grm_standardize(c, d_Dc);
+    std::vector<double> dc(c->N);
+    PCA_CUDA(cudaMemcpyAsync(dc.data(), d_Dc, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    sample_covariance(c, C_out);  // synchronises the stream
+    const double inv = 1.0 / (double)c->M;
+    for (uint64_t e = 0; e < c->N * c->N; ++e) C_out[e] *= inv;
+    for (uint64_t i = 0; i < c->N; ++i) C_out[i * c->N + i] = dc[i] * inv;
+    if (Dc_out) std::copy(dc.begin(), dc.end(), Dc_out);
+  } catch (...) {
+    cudaFree(d_Dc);
+    throw;
+  }
+  cudaFree(d_Dc);
+}
+
 // A (n x n symmetric, column-major, host) = U diag(S) V^T: S descending, U n x n column-major. One-sided Jacobi
 // on the device; returns the number of sweeps.
 int sym_svd(pcaone_ctx* c, const double* A, uint64_t n, double* U_out, double* S_out) {

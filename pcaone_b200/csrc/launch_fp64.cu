@@ -183,6 +183,20 @@ void gl_refresh(pcaone_ctx* c, uint64_t r0, uint64_t nrows, bool update, double*
   c->tm.kernel_launches++;
 }
 
+// pcangsd_standardize_E into the dense operand + the diagonal sums Dc (N doubles on the device, zeroed here)
+void gl_grm_standardize(pcaone_ctx* c, double* d_Dc) {
+  if (c->source != PCAONE_SRC_GL) throw std::runtime_error("gl_grm: the context has no genotype-likelihood source");
+  if (!c->af_done || !c->have_usv) throw std::runtime_error("gl_grm: run the PCAngsd EM (pcaone_run_em) first");
+  PCA_CUDA(cudaMemsetAsync(d_Dc, 0, c->N * sizeof(double), c->stream));
+  const uint32_t gx = (uint32_t)ceil_div(c->N, 256);
+  const uint32_t slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(c->M, (uint64_t)(4 * c->sms + gx - 1) / gx));
+  const uint64_t rps = (c->M + slices - 1) / slices;
+  k_gl_grm<<<dim3(gx, (unsigned)ceil_div(c->M, rps)), 256, 0, c->stream>>>(c->d_P, (uint32_t)c->N, c->M, rps, c->d_F, c->d_U, c->lp,
+                                                                          c->d_S, c->d_V, c->lp, c->k, c->d_dense, c->ldd, d_Dc);
+  PCA_CHECK_LAUNCH();
+  c->tm.kernel_launches++;
+}
+
 // ---------------------------------------------------------------- entry points of the dosage / GL / dense sources
 void dosage_allele_freq(pcaone_ctx* c) {
   k_dosage_af<<<grid_for(c->M * 32, 256, c->sms), 256, 0, c->stream>>>(c->d_dos, c->ldf, (uint32_t)c->N, c->M, c->d_F,

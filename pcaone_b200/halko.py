@@ -514,6 +514,12 @@ class RsvdOpData:
         self._chk(self.L.pcaone_sample_covariance(self.h, _vp(K)))
         return K
 
+    def grm(self):
+        """PCAngsd GRM step (Halko.cpp:320-326) after runEM on a FileBeagle source: (C, Dc)."""
+        Cm, Dc = _f((self.cols(), self.cols())), np.zeros(self.cols())
+        self._chk(self.L.pcaone_gl_grm(self.h, _vp(Cm), _vp(Dc)))
+        return Cm, Dc
+
     def symSVD(self, A):
         """SVD of a symmetric matrix on the device (one-sided Jacobi): (U, S) with S descending."""
         A = np.asfortranarray(A, dtype=np.float64)

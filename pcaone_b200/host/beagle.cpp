@@ -1,5 +1,7 @@
 #include "beagle.hpp"
 
+#include <sstream>
+
 #include <zlib.h>
 
 #include <cstdlib>
@@ -72,7 +74,14 @@ void FileBeagle::read_all() {
   gzFile fp = gzopen(params.filein.c_str(), "r");
   if (!fp) cao.error("can not open " + params.filein);
   std::string line;
-  gz_line(fp, line);  // header
+  gz_line(fp, line);  // header: marker allele1 allele2, then three columns per sample
+  {
+    samples.clear();
+    std::istringstream hs(line);
+    std::string tok;
+    for (uint64 col = 0; hs >> tok; ++col)
+      if (col >= 3 && col % 3 == 0) samples.push_back(tok);
+  }
   std::vector<uint64> logical_of(nsnps);  // perm[logical] = original
   for (uint64 l = 0; l < nsnps; ++l) logical_of[perm.empty() ? l : perm[l]] = l;
   for (uint64 j = 0; j < nsnps; ++j) {

@@ -22,6 +22,7 @@ class FileBeagle : public Data {
   void attach_stream_source() override;        // out-of-core PCAngsd does not exist in the reference either
 
   double tolmaf = 1e-6;  // --tol-maf
+  std::vector<std::string> samples;  // first name of every sample triple of the header (parse_beagle_samples, Utils.cpp:652-669)
 };
 
 }  // namespace pcaone_host

@@ -151,6 +151,38 @@ void run_pca_full(Data* data, const Param& params) {
   data->write_eigs_files(evals, svals, U, V);
 }
 
+// The GRM step of PCAngsd (Halko.cpp:320-334) after the EM loop: covariance of the re-standardised expected
+// genotypes with its Dc diagonal (pcaone_gl_grm) -> <out>.cov; its SVD (pcaone_sym_svd, on the device) -> all N
+// eigenvectors in <out>.eigvecs2 with the sample names of the BEAGLE header (write_eigvecs2_beagle, Utils.cpp:671-683).
+void run_pcangsd_grm(Data* data, const Param& params, const std::vector<std::string>& samples) {
+  cao.print(tick.date(), "estimate GRM for pcangsd");
+  const uint64 N = data->nsamples;
+  Mat2D C(N, N), U2(N, N);
+  Mat1D S2(N);
+  data->check(pcaone_gl_grm(data->ctx, C.data(), nullptr));
+  {
+    std::ofstream fcov(params.fileout + ".cov");
+    if (!fcov.is_open()) cao.error("can not open " + params.fileout + ".cov");
+    for (uint64 i = 0; i < N; ++i) {
+      for (uint64 j = 0; j < N; ++j) fcov << (j ? " " : "") << C(i, j);
+      fcov << "\n";
+    }
+  }
+  int sweeps = 0;
+  data->check(pcaone_sym_svd(data->ctx, C.data(), N, U2.data(), S2.data(), &sweeps));
+  std::ofstream feig2(params.fileout + ".eigvecs2");
+  if (!feig2.is_open()) cao.error("can not open " + params.fileout + ".eigvecs2");
+  feig2 << "#FID\tIID";
+  for (uint64 i = 0; i < N; ++i) feig2 << "\tPC" << i + 1;
+  feig2 << "\n";
+  for (uint64 i = 0; i < N; ++i) {
+    const std::string name = i < samples.size() ? samples[i] : "Ind" + std::to_string(i);
+    feig2 << name << "\t" << name << "\t";
+    for (uint64 j = 0; j < N; ++j) feig2 << (j ? " " : "") << U2(i, j);
+    feig2 << "\n";
+  }
+}
+
 void make_plink2_eigenvec_file(int K, const std::string& fout, const std::string& fin, const std::string& fam) {
   std::ifstream ifam(fam), ifin(fin);
   std::ofstream ofs(fout);

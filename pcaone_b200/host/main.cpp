@@ -48,6 +48,7 @@ int main(int argc, char* argv[]) {
       data.tolmaf = params.tolmaf;
       data.prepare();
       run_pca_with_halko(&data, params);
+      if (params.pcangsd) run_pcangsd_grm(&data, params, data.samples);
       cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
       return bye();
     }

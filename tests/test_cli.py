@@ -225,6 +225,14 @@ def test_cli_beagle_pcangsd_vs_reference_golden(tmp_path):
     assert U.shape[0] == N and V.shape == (M, k)
     assert np.max(np.abs(S - g["S"]) / g["S"]) < 1e-5
     assert col_cos(U, g["U"]).min() > 0.9999 and col_cos(V, g["V"]).min() > 0.9999
+    # the GRM step (Halko.cpp:320-334): <out>.cov and the N eigenvectors of it in <out>.eigvecs2
+    q = golden("pcangsd_grm")
+    Cm = np.loadtxt(out + ".cov")
+    assert Cm.shape == (N, N) and np.abs(Cm - q["C"]).max() < 2e-5 * np.abs(q["C"]).max()
+    rows = open(out + ".eigvecs2").read().splitlines()
+    assert rows[0].split("\t")[:3] == ["#FID", "IID", "PC1"] and len(rows) == N + 1 and rows[1].split("\t")[0] == "Ind0"
+    E2 = np.array([[float(x) for x in r.split("\t")[2].split()] for r in rows[1:]])
+    assert E2.shape == (N, N) and col_cos(E2[:, :3], q["U2"][:, :3]).min() > 0.9999
     # winSVD with the in-core shuffle runs too and finds the same top PCs
     out2 = str(tmp_path / "o2")
     _run(["-G", bgl, "-k", k, "-d", 2, "-w", 8, "-o", out2, "--maxiter", 4, "-V"])

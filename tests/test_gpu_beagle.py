@@ -83,3 +83,32 @@ def test_beagle_maf_filter_and_errors():
         halko.FileBeagle(halko.Param(k=3, svd=1, memory=0.001, precision=_lib.PREC_FP64), P)
     with pytest.raises(RuntimeError):
         halko.FileBeagle(halko.Param(k=3, svd=1, precision=_lib.PREC_INT8X3), P)
+
+
+def test_pcangsd_grm_vs_reference_golden():
+    """The GRM step after the EM (Halko.cpp:320-334): pcangsd_standardize_E + N x N covariance with the Dc diagonal on
+    the device, then the symmetric SVD on the device, against the unmodified reference (pcangsd_grm.npz)."""
+    g, q = golden("pcangsd_small"), golden("pcangsd_grm")
+    k = int(g["k"])
+    p = halko.Param(k=k, svd=1, maxp=int(g["maxp"]), tol=0.0, maxiter=int(g["maxiter"]), precision=_lib.PREC_FP64)
+    d = halko.FileBeagle(p, g["P"])
+    d.prepare()
+    op = halko.NormalRsvdOpData(d, p.k, p.oversamples)
+    op.setOmg(g["omega"])
+    op.runEM()
+    # (1) from the reference's own U, S, V: the step in isolation
+    op.setUSV(q["U"], q["S"], q["V"])
+    Cm, Dc = op.grm()
+    assert np.abs(Dc - q["Dc"]).max() <= 1e-12 * np.abs(q["Dc"]).max()
+    assert np.abs(Cm - q["C"]).max() <= 1e-12 * np.abs(q["C"]).max()
+    U2, S2 = op.symSVD(Cm)
+    assert np.abs(S2 - q["S2"]).max() <= 1e-12 * q["S2"][0]
+    assert col_cos(U2[:, :4], q["U2"][:, :4]).min() > 1 - 1e-10      # the separated leading vectors, up to sign
+    assert np.abs(U2.T @ U2 - np.eye(U2.shape[0])).max() < 1e-12
+    sg = np.sign(np.sum((q["C"] @ U2) * U2, axis=0))
+    assert np.abs(q["C"] - (U2 * (S2 * sg)) @ U2.T).max() <= 1e-12 * S2[0]
+    # (2) end to end from this library's own EM result
+    op.runEM()
+    C2, _ = op.grm()
+    assert np.abs(C2 - q["C"]).max() <= 1e-9 * np.abs(q["C"]).max()
+    op.close()

@@ -244,3 +244,14 @@ def test_pcangsd_restatement_vs_reference():
     U, S, V, iters = orc.run_emu(oo, int(g["maxp"]), 0.0, maxiter=int(g["maxiter"]), tolem=1e-5, final_standardize=False)
     assert iters == int(g["iters"])
     assert_usv_close(U, S, V, g["U"], g["S"], g["V"], eig_rtol=1e-10, min_corr=1 - 1e-10)
+
+
+def test_pcangsd_grm_restatement_vs_reference():
+    """numpy restatement of the GRM step against the unmodified reference (tests/golden/pcangsd_grm.npz, written by
+    tests/golden/make_golden_grm.py from oracle/_ref on the beagle.gz of pcangsd_small.npz)."""
+    g, q = golden("pcangsd_small"), golden("pcangsd_grm")
+    Cm, Dc = orc.pcangsd_grm(g["P"], g["F"], q["U"], q["S"], q["V"])
+    assert np.abs(Dc - q["Dc"]).max() <= 1e-12 * np.abs(q["Dc"]).max()
+    assert np.abs(Cm - q["C"]).max() <= 1e-12 * np.abs(q["C"]).max()
+    w = np.sort(np.abs(np.linalg.eigvalsh(q["C"])))[::-1]
+    assert np.abs(w - q["S2"]).max() <= 1e-12 * w[0]
