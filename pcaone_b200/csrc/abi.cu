@@ -133,6 +133,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     if (const char* e = getenv("PCAONE_ORTH_ONE_SHOT")) c->one_shot_q = atoi(e);
     if (const char* e = getenv("PCAONE_OMEGA_SKIP2")) c->omega_skip2 = atoi(e);
     if (const char* e = getenv("PCAONE_EMU_TC")) c->emu_tc = atoi(e);
+    if (const char* e = getenv("PCAONE_EMU_SPLIT")) c->emu_split = atoi(e);
     PCA_CUDA(cudaHostAlloc((void**)&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     PCA_CUDA(cudaHostAlloc((void**)&c->h_scal, 64 * sizeof(double), cudaHostAllocDefault));
     c->part_doubles = (size_t)(2 * c->sms + 8) * 128 * c->lp;
@@ -162,7 +163,7 @@ void pcaone_destroy(pcaone_ctx* c) {
                   (void*)c->d_raw[1], (void*)c->d_blk[0], (void*)c->d_blk[1], (void*)c->d_PG, (void*)c->d_PH, (void*)c->d_PGb[0],
                   (void*)c->d_PGb[1], (void*)c->d_PHb[0], (void*)c->d_PHb[1], (void*)c->d_BimgO, (void*)c->d_BimgW,
                   (void*)c->d_dense, (void*)c->d_P, (void*)c->d_dos, (void*)c->d_Racc, (void*)c->d_Racc2, (void*)c->d_BimgD, (void*)c->d_tcs, (void*)c->d_Fpart, (void*)c->d_jscratch,
-                  (void*)c->d_flipbuf, (void*)c->d_cnt, (void*)c->d_cache_pg, (void*)c->d_cache_ph, (void*)c->d_emu_us})
+                  (void*)c->d_flipbuf, (void*)c->d_cnt, (void*)c->d_cache_pg, (void*)c->d_cache_ph, (void*)c->d_emu_us, (void*)c->d_emu_part})
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);

@@ -87,6 +87,9 @@ struct pcaone_ctx {
   double *d_G = nullptr, *d_V = nullptr, *d_Vpre = nullptr;
   double* d_S = nullptr;
   double* d_emu_us = nullptr;  // U o S of the EMU fill (N x lp), emu_fix.cuh
+  double* d_emu_part = nullptr;  // per-slice partial sums of k_emu_fix_g on short ranges
+  size_t emu_part_cap = 0;
+  int emu_split = 1;  // slice the sample axis of k_emu_fix_g on short ranges (PCAONE_EMU_SPLIT=0: never)
   double* d_Hpart = nullptr;
   uint32_t max_splits = 1;
   bool have_usv = false, have_omg0 = false;

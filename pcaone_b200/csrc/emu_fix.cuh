@@ -104,11 +104,16 @@ __global__ void __launch_bounds__(kThreads)
 k_emu_fix_g(const uint8_t* __restrict__ PG, uint64_t stride_rt, uint32_t nkb, uint32_t N, uint64_t loc0, uint32_t nrows,
             const double* __restrict__ US, int ldu, int k, const double* __restrict__ V, int ldv,
             const double* __restrict__ Omg, int lp, int l, const double* __restrict__ F, LutParams lut,
-            double* __restrict__ G, unsigned long long* __restrict__ colmax) {
+            double* __restrict__ G, unsigned long long* __restrict__ colmax, uint32_t kb_per_split,
+            double* __restrict__ part) {
   constexpr int KP = pitch_of(KR), LTP = pitch_of(LT);
   extern __shared__ __align__(16) double sm[];
   double* Us = sm;                  // [SB * 64][KP]
   double* Os = sm + SB * kKB * KP;  // [SB * 64][LTP]
+  // blockIdx.z: slice of the sample axis (ranges of a few row tiles would otherwise run on a few SMs); the slices'
+  // sums go to part[z][row][col] and k_emu_reduce_g adds them in order
+  const uint32_t kb_begin = blockIdx.z * kb_per_split;
+  const uint32_t kb_end = min(nkb, kb_begin + kb_per_split);
   const int tid = threadIdx.x;
   const uint32_t rt = (uint32_t)(loc0 / kThreads) + blockIdx.x;
   const int c0 = blockIdx.y * LT;
@@ -134,11 +139,11 @@ k_emu_fix_g(const uint8_t* __restrict__ PG, uint64_t stride_rt, uint32_t nkb, ui
 #pragma unroll
     for (int b = 0; b < SB; ++b) {
       dst[b] = make_uint4(0, 0, 0, 0);
-      if (live && kb0 + b < nkb) dst[b] = *reinterpret_cast<const uint4*>(prow + (uint64_t)(kb0 + b) * (kThreads * 16));
+      if (live && kb0 + b < kb_end) dst[b] = *reinterpret_cast<const uint4*>(prow + (uint64_t)(kb0 + b) * (kThreads * 16));
     }
   };
-  load_codes(0, q);
-  for (uint32_t kb0 = 0; kb0 < nkb; kb0 += SB) {
+  load_codes(kb_begin, q);
+  for (uint32_t kb0 = kb_begin; kb0 < kb_end; kb0 += SB) {
     __syncthreads();  // the previous group's rows are consumed
     const long long s0 = (long long)kb0 * kKB;
     stage_rows<KR, KP>(Us, US, ldu, s0, SB * kKB, 0, (long long)N, 0, k, tid);
@@ -162,6 +167,15 @@ k_emu_fix_g(const uint8_t* __restrict__ PG, uint64_t stride_rt, uint32_t nkb, ui
 #pragma unroll
     for (int b = 0; b < SB; ++b) q[b] = qn[b];
   }
+  if (part) {  // sliced sample axis: partial sums only
+    if (live) {
+      double* o = part + ((uint64_t)blockIdx.z * nrows + (uint64_t)jr) * lp + c0;
+#pragma unroll
+      for (int cc = 0; cc < LT; ++cc)
+        if (c0 + cc < l) o[cc] = acc[cc];
+    }
+    return;
+  }
   // write-out + column maxima of W = s o G for the slicing that follows (bounds from above are enough)
   __syncthreads();
   double* red = sm;  // [4 warps][LT]
@@ -183,6 +197,32 @@ k_emu_fix_g(const uint8_t* __restrict__ PG, uint64_t stride_rt, uint32_t nkb, ui
   if (tid < LT && c0 + tid < l) {
     const double mx = fmax(fmax(red[tid], red[LT + tid]), fmax(red[2 * LT + tid], red[3 * LT + tid]));
     if (mx > 0.0) atomicMax(&colmax[c0 + tid], (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+// G[row][c] += sum_z part[z][row][c] (z in order) and the column maxima of W = s o G; one thread per column pair of a row
+__global__ void __launch_bounds__(256) k_emu_reduce_g(const double* __restrict__ part, uint32_t nsplit, uint32_t nrows, int lp,
+                                                      int l, const double* __restrict__ F, LutParams lut,
+                                                      double* __restrict__ G, unsigned long long* __restrict__ colmax) {
+  __shared__ double s_m[256];
+  const int rpp = 256 / lp;                       // rows per pass of the block (lp <= 128)
+  const int g0 = threadIdx.x / lp, c = threadIdx.x - g0 * lp;
+  double m = 0.0;
+  if (g0 < rpp && c < l) {
+    for (uint64_t row = (uint64_t)blockIdx.x * rpp + g0; row < nrows; row += (uint64_t)gridDim.x * rpp) {
+      double a = 0.0;
+      for (uint32_t z = 0; z < nsplit; ++z) a += part[((uint64_t)z * nrows + row) * lp + c];
+      const double gn = G[row * lp + c] + a;
+      G[row * lp + c] = gn;
+      m = fmax(m, fabs(gn * snp_scale(F[row], lut)));
+    }
+  }
+  s_m[threadIdx.x] = m;
+  __syncthreads();
+  if (g0 == 0 && c < l) {
+    double v = 0.0;
+    for (int q = 0; q < rpp; ++q) v = fmax(v, s_m[q * lp + c]);
+    if (v > 0.0) atomicMax(&colmax[c], (unsigned long long)__double_as_longlong(v));
   }
 }
 

@@ -161,14 +161,40 @@ void emu_fix_g_t(pcaone_ctx* c, const uint8_t* PG, uint64_t loc0, uint32_t nrows
   constexpr int SB = emu::sb_of(KR, LT);
   constexpr size_t smem = emu::smem_bytes(KR, LT, SB, false);
   const uint32_t rt0 = (uint32_t)(loc0 / tc::kRowTile), rt1 = (uint32_t)((loc0 + nrows - 1) / tc::kRowTile);
-  const dim3 grid(rt1 - rt0 + 1, (unsigned)((c->l + LT - 1) / LT));
   const uint32_t nkb = (uint32_t)tc_nkb_samples(c);
+  const uint32_t nblk = (rt1 - rt0 + 1) * (uint32_t)((c->l + LT - 1) / LT);
+  // a range of a few row tiles (a winSVD window) would run on a few SMs, every block walking the whole sample axis:
+  // slice that axis until about two waves of blocks exist, at least four barrier groups per slice
+  uint32_t nsplit = 1;
+  if (c->emu_split && nblk < 2u * c->sms) nsplit = std::min<uint32_t>((2u * c->sms + nblk - 1) / nblk, std::max<uint32_t>(1, nkb / (4 * SB)));
+  uint32_t kb_per = (nkb + nsplit - 1) / nsplit;
+  kb_per = (kb_per + SB - 1) / SB * SB;
+  nsplit = (nkb + kb_per - 1) / kb_per;
+  double* part = nullptr;
+  if (nsplit > 1) {
+    const size_t need = (size_t)nsplit * nrows * c->lp;
+    if (need > c->emu_part_cap) {
+      if (c->d_emu_part) cudaFree(c->d_emu_part);
+      c->d_emu_part = nullptr;
+      dmalloc(&c->d_emu_part, need);
+      c->emu_part_cap = need;
+    }
+    part = c->d_emu_part;
+  }
+  const dim3 grid(rt1 - rt0 + 1, (unsigned)((c->l + LT - 1) / LT), nsplit);
   ensure_smem(c, emu::k_emu_fix_g<KR, LT, SB>, smem);
   emu::k_emu_fix_g<KR, LT, SB><<<grid, emu::kThreads, smem, c->stream>>>(
       PG, (uint64_t)nkb * tc::kChunkBytes, nkb, (uint32_t)c->N, loc0, nrows, c->d_emu_us, c->lp, c->k, c->d_V + snp0 * c->lp,
-      c->lp, c->d_Omg, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax);
+      c->lp, c->d_Omg, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax, kb_per, part);
   PCA_CHECK_LAUNCH();
   c->tm.kernel_launches++;
+  if (part) {
+    const int rpp = 256 / c->lp;
+    emu::k_emu_reduce_g<<<(unsigned)std::min<uint64_t>((nrows + rpp - 1) / rpp, (uint64_t)c->sms * 8), 256, 0, c->stream>>>(
+        part, nsplit, nrows, c->lp, c->l, c->d_F + snp0, c->lut, c->d_G + snp0 * c->lp, w_colmax);
+    PCA_CHECK_LAUNCH();
+    c->tm.kernel_launches++;
+  }
 }
 
 template <int KR, int LT>

@@ -210,12 +210,15 @@ def c4(args, out):
     legs = [("int8x3 + FP64 correction over the missing calls", 3, "1"), ("update passes on the FP64 DMMA kernels", 3, "0")]
     if args.c4_prec == 0:
         legs = [("FP64 DMMA kernels throughout", 0, "1")]
+    legs = legs[:args.c4_legs]
     for name, prec, sw in legs:
         os.environ["PCAONE_EMU_TC"] = sw
         p = halko.Param(k=k, svd=2, bands=64, maxp=20, tol=1e-4, no_shuffle=True, emu=True, precision=prec)
         d = halko.FileBed(p, packed=packed, nsamples=N)
         op = halko.FancyRsvdOpData(d, p.k, p.oversamples)
+        op.runEM()                       # warm-up: module load, tile build, buffers
         op.sync()
+        op.timers(reset=True)
         t0 = time.perf_counter()
         iters = op.runEM()
         secs = time.perf_counter() - t0
@@ -229,18 +232,20 @@ def c4(args, out):
                "U_orthonormality_err": float(np.abs(U.T @ U - np.eye(k)).max()), "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
         # one late epoch (pi >= 6: two half-range products, one Omega update) with and without the fill
         op.enable_timing(True)
-        for label, upd in (("late_update_pass", True), ("late_plain_pass", False)):
+        for label, upd, pi in (("late_update_pass", True, 20), ("late_plain_pass", False, 20), ("first_update_pass", True, 0),
+                               ("first_plain_pass", False, 0)):
+            # pi = 0: the first epoch of a computeUSV, 64 windows with an Omega update after each
             op.setFlags(upd, False)
-            op.computeGandH(19, want=False)       # warm
+            op.computeGandH(19 if pi else 0, want=False)       # warm
             op.sync()
             op.timers(reset=True)
             t0 = time.perf_counter()
-            op.computeGandH(20, want=False)
+            op.computeGandH(pi, want=False)
             op.sync()
             ms = 1e3 * (time.perf_counter() - t0)
             t = op.timers(reset=True)
             rec[label] = {"ms": ms, "gemm_g_ms": t.gemm_g_ms, "gemm_h_ms": t.gemm_h_ms, "tc_g_ms": t.tc_g_ms, "tc_h_ms": t.tc_h_ms,
-                          "emu_fix_ms": t.emu_fix_ms, "orth_ms": t.orth_ms, "tc_ranges": int(t.tc_ranges),
+                          "emu_fix_ms": t.emu_fix_ms, "orth_ms": t.orth_ms, "tc_ranges": int(t.tc_ranges), "kernel_launches": int(t.kernel_launches),
                           "fp64_ranges": int(t.fp64_ranges), "gbs": M * packed.shape[1] / ms / 1e6}
             if upd and t.emu_fix_ms > 0:
                 # FP64 work of the correction: per missing call and product a k-term dot and an l-term axpy
@@ -438,6 +443,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--c4-prec", type=int, default=3)
+    ap.add_argument("--c4-legs", type=int, default=2, help="c4: 1 = the int8 route only, 2 = also the FP64 DMMA update passes")
     args = ap.parse_args()
     _lib.load()
     fns = {"c1": c1, "c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "bgen": f_bgen, "beagle": f_beagle, "prune": f_prune,
