@@ -39,7 +39,11 @@ __host__ __device__ constexpr int pitch_of(int W) { return ((W / 2) | 1) * 2; }
 __host__ __device__ constexpr size_t smem_bytes(int KR, int LT, int SB, bool hside) {
   return (size_t)SB * kKB * (pitch_of(KR) + pitch_of(LT) + (hside ? 3 : 0)) * sizeof(double);
 }
-// k-blocks per barrier: as many as keep two blocks per SM resident
+// k-blocks per barrier: as many as keep two blocks per SM resident. Measured at configs[3] (115 ms of correction per
+// update pass): two k-blocks per barrier with four resident blocks instead of three, 127 ms; ONE loop over a row's
+// missing calls per group instead of one per 16-entry word (ncu: 16.7 of 32 lanes active), with the word picked from
+// registers by selects, 127 ms as well — the LSU data pipe (63 % of its peak wavefronts in ncu) is the limit, not the
+// lane utilisation.
 __host__ __device__ constexpr int sb_of(int KR, int LT) {
   return smem_bytes(KR, LT, 4, true) <= 100 * 1024 ? 4 : smem_bytes(KR, LT, 2, true) <= 100 * 1024 ? 2 : 1;
 }
