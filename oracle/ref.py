@@ -252,6 +252,23 @@ class Ref:
         return out, ws, we
 
 
+def write_bgen(path, probs, bit_depth=8):
+    """probs: (M, N, 3) genotype probabilities (NaN triple = missing) -> a layout-2 zlib BGEN file written by the
+    writer of the reference's vendored bgen library."""
+    probs = np.ascontiguousarray(probs, dtype=np.float64)
+    M, N, _ = probs.shape
+    if lib().ref_write_bgen(path.encode(), C.c_longlong(N), C.c_longlong(M), _p(probs), int(bit_depth)):
+        raise RuntimeError(lib().ref_last_error().decode())
+
+
+def bgen_dosages(path, N, M):
+    """the minor-allele dosages FileBgen::read_all sees, (M, N) float32, NaN = missing."""
+    out = np.zeros((M, N), dtype=np.float32)
+    if lib().ref_bgen_dosages(path.encode(), _p(out), C.c_longlong(N), C.c_longlong(M)):
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out
+
+
 def init_omega(rows, cols, seed=112, gaussian=True):
     out = _f((rows, cols))
     lib().ref_init_omega(C.c_longlong(rows), C.c_longlong(cols), int(seed), int(gaussian), _p(out))

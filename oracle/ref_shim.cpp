@@ -34,6 +34,8 @@
 #include "Data.hpp"
 #include "FileBeagle.hpp"
 #include "FileBinary.hpp"
+#include "FileBgen.hpp"
+#include "bgen/writer.h"
 #include "FilePlink.hpp"
 #include "Arnoldi.hpp"
 #include "Halko.hpp"
@@ -126,8 +128,10 @@ void* ref_open(const char* cmdline) {
       }
     } else if (params.file_t == FileType::BEAGLE) {
       c->data = new FileBeagle(params);   // genotype likelihoods; read_all runs emMAF_with_GL and builds E
+    } else if (params.file_t == FileType::BGEN) {
+      c->data = new FileBgen(params);     // the reference's own BGEN reader (external/bgen)
     } else {
-      throw std::runtime_error("ref_shim: only --bfile / --binary / --beagle inputs are driven by the oracle");
+      throw std::runtime_error("ref_shim: only --bfile / --binary / --beagle / --bgen inputs are driven by the oracle");
     }
     c->data->prepare();
   });
@@ -549,6 +553,40 @@ int ref_pcangsd_grm(void* h, double* C_out, double* U2_out, double* S2_out, doub
     Mat1D S2 = svd.singularValues();
     std::memcpy(S2_out, S2.data(), sizeof(double) * S2.size());
     std::memcpy(Dc_out, data->Dc.data(), sizeof(double) * data->Dc.size());
+  });
+}
+
+// A BGEN file (layout 2, zlib, unphased diploid, bit_depth bits per probability) written with the writer of the
+// reference's vendored library: probs = [nsnps][nsamples][3] genotype probabilities, NaN triples = missing.
+int ref_write_bgen(const char* path, long long nsamples, long long nsnps, const double* probs, int bit_depth) {
+  return guarded([&] {
+    std::string p(path), free_data;
+    std::vector<std::string> samples;
+    for (long long i = 0; i < nsamples; ++i) samples.push_back("s" + std::to_string(i));
+    bgen::CppBgenWriter w(p, (std::uint32_t)nsamples, free_data, 1, 2, samples);
+    std::vector<std::string> alleles{"A", "C"};
+    std::vector<double> g((size_t)3 * nsamples);
+    for (long long j = 0; j < nsnps; ++j) {
+      std::string varid = "v" + std::to_string(j), rsid = "rs" + std::to_string(j), chrom = "1";
+      std::uint32_t pos = (std::uint32_t)(100 * (j + 1));
+      w.write_variant_header(varid, rsid, chrom, pos, alleles, (std::uint32_t)nsamples);
+      std::copy(probs + (size_t)3 * nsamples * j, probs + (size_t)3 * nsamples * (j + 1), g.begin());
+      w.add_genotype_data(2, g.data(), (std::uint32_t)g.size(), (std::uint8_t)2, false, (std::uint8_t)bit_depth);
+    }
+  });
+}
+
+// The dosages FileBgen::read_all sees (FileBgen.cpp:24-26: next_var().minor_allele_dosage), SNP-major floats,
+// NaN = missing: read with the same library calls.
+int ref_bgen_dosages(const char* path, float* out, long long nsamples, long long nsnps) {
+  return guarded([&] {
+    bgen::CppBgenReader bg(path, "", true);
+    if ((long long)bg.header.nsamples != nsamples || (long long)bg.header.nvariants != nsnps)
+      throw std::runtime_error("ref_bgen_dosages: size mismatch");
+    for (long long j = 0; j < nsnps; ++j) {
+      auto var = bg.next_var();
+      var.minor_allele_dosage(out + (size_t)j * nsamples);
+    }
   });
 }
 

@@ -5,8 +5,10 @@ the FP64 tensor-core products (csrc/dense_gemm.cuh k_dos_g / k_dos_h).
 Pins: (1) the numpy restatement of FileBgen.cpp:15-110 (oracle.dense_from_dosage); (2) on HARD-CALL
 dosages (d = 2 x half-dosage of a bed code) the dosage path must reproduce the PLINK-bed path, whose
 results are pinned to the unmodified reference by tests/golden: same F bit for bit, same decoded
-block, same U, S, V. The reference's own BGEN reader needs its bundled bgen library and a .bgen
-container and is not compiled here, so fractional dosages are pinned by (1) only."""
+block, same U, S, V; (3) FRACTIONAL dosages against the unmodified reference reading a real .bgen container:
+the reference's FileBgen + its vendored bgen library are compiled into oracle/_ref, the file is written with that
+library's own writer, and the dosages handed to the device are the ones its reader returns
+(test_fractional_dosages_vs_reference_bgen_reader)."""
 import numpy as np
 import pytest
 
@@ -111,3 +113,43 @@ def test_dosage_maf_filter_and_errors():
     de.prepare()
     with pytest.raises(RuntimeError, match="emu"):
         halko.NormalRsvdOpData(de, 3, pe.oversamples)
+
+
+@pytest.mark.parametrize("bit_depth", [8, 16])
+def test_fractional_dosages_vs_reference_bgen_reader(tmp_path, bit_depth):
+    """A layout-2 .bgen with fractional genotype probabilities and missing samples, read by the unmodified reference
+    (FileBgen::read_all, FileBgen.cpp:15-72 on the vendored bgen reader): allele frequencies, the centred matrix and
+    U, S, V of the same run on the device from the dosages that reader returns."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    N, M, k = 240, 1800, 4
+    rng = np.random.default_rng(77)
+    codes = np.concatenate([c for _, c in synth.balding_nichols_codes(N, M, k_pop=5, seed=78)])      # (M, N)
+    g = np.array([2, 0, 1, 0])[codes]
+    P = np.zeros((M, N, 3))
+    for q in range(3):
+        P[:, :, q] = np.where(g == q, 0.85, 0.075)
+    P = 0.7 * P + 0.3 * rng.dirichlet([8, 8, 8], size=(M, N))
+    P /= P.sum(-1, keepdims=True)
+    P[rng.random((M, N)) < 0.03] = np.nan
+    path = str(tmp_path / "f.bgen")
+    ref.write_bgen(path, P, bit_depth=bit_depth)
+    dos = ref.bgen_dosages(path, N, M)
+    assert np.isnan(dos).sum() == np.isnan(P[:, :, 0]).sum()
+    frac = np.abs(dos - np.round(dos))
+    assert np.nanmean(frac > 0.05) > 0.5, "the case must be about fractional dosages"
+    r = ref.Ref(f"PCAone --bgen {path} -k {k} -d 1 -o {tmp_path}/r -n 4 --maxp 5 --tol-rsvd 0", threads=4)
+    Fr, Gr = r.F(), r.dataG()
+    r.new_op()
+    Ur, Sr, Vr = r.compute_usv(5, 0.0)
+    r.close()
+    op, d, p = _op(dos, k=k, svd=1, maxp=5, tol=0.0)
+    F = op.F()
+    assert np.max(np.abs(F - Fr) / Fr) < 1e-14
+    X = op.read_block(0, M - 1, False)
+    assert np.abs(X - Gr).max() <= 1e-14                      # dosage / 2 - F, NaN -> 0
+    op.setFlags(False, True)
+    op.computeUSV(5, 0.0)
+    assert_usv_close(op.U, op.S, op.V, Ur, Sr, Vr, eig_rtol=1e-9, min_corr=1 - 1e-9)
+    op.close()

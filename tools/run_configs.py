@@ -226,7 +226,7 @@ def c4(args, out):
         U = op.U
         nmiss = op.missing_count()
         rec = {"config": "C4", "workload": f"EMU winSVD in-memory N={N} M={M} k={k} 10% missing: {name}",
-               "bytes_per_pass": M * packed.shape[1], "time_to_pcs_s": secs, "em_iterations": iters,
+               "bytes_per_pass": M * packed.shape[1], "time_to_pcs_s": secs, "genotypes_per_s": N * M / secs, "em_iterations": iters,
                "missing_fraction": nmiss / (N * M), "tc_ranges": int(tm.tc_ranges), "tc_emu_ranges": int(tm.tc_emu_ranges),
                "fp64_ranges": int(tm.fp64_ranges), "kernel_launches": int(tm.kernel_launches),
                "U_orthonormality_err": float(np.abs(U.T @ U - np.eye(k)).max()), "eigvals_top5": (op.S[:5] ** 2 / M).tolist()}
@@ -255,6 +255,33 @@ def c4(args, out):
         op.close()
         _emit(out, rec)
     os.environ.pop("PCAONE_EMU_TC", None)
+    # CPU baseline: the unmodified reference (oracle/_ref) on a bounded sample of the same workload — an EMU update pass
+    # (read_block_update + the two products, Halko.cpp:188-222 in core) on 2,048 samples x 32,768 SNPs with 10 % missing
+    try:
+        from oracle import ref
+        if ref.available() and not args.no_cpu:
+            import tempfile
+            ns, ms = 2048, 32768
+            pk = synth.torch_packed(ns, ms, k_pop=k + 4, miss=0.10, seed=4, device="cuda:0", chunk=4096).cpu().numpy()
+            tmp = tempfile.mkdtemp(prefix="c4_cpu_")
+            synth.write_bed_from_packed(os.path.join(tmp, "s"), pk, ns)
+            thr = os.cpu_count() or 1
+            r = ref.Ref(f"PCAone -b {tmp}/s -k {k} -d 2 -S --emu -o {tmp}/o -n {thr}", threads=thr)
+            r.new_op()
+            t0 = time.perf_counter()
+            r.run_em()
+            em_s = time.perf_counter() - t0
+            r.set_flags(True, False)
+            r.time_gandh(19)
+            ts = [r.time_gandh(20) for _ in range(3)]
+            r.close()
+            _emit(out, {"config": "C4-cpu", "workload": f"reference EMU (oracle/_ref, {thr} threads) on {ns} x {ms}, 10 % missing, k = {k}",
+                        "em_run_s": em_s, "genotypes_per_s": ns * ms / em_s,
+                        "late_pass_s": min(ts), "gbs_per_late_pass": ms * pk.shape[1] / min(ts) / 1e9,
+                        "note": "in core the reference fills the missing calls once per computeUSV (fit_with_pi at pi = 0), so its late pass is two dense GEMMs; compare whole EM runs per genotype",
+                        "cores": thr, "sample": f"{ns} samples x {ms} SNPs of the same population model"})
+    except Exception as e:  # the baseline is a side note: never fail the config run on it
+        print("# c4 cpu baseline skipped:", e)
 
 
 def c5(args, out):
@@ -443,6 +470,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--c4-prec", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     ap.add_argument("--c4-legs", type=int, default=2, help="c4: 1 = the int8 route only, 2 = also the FP64 DMMA update passes")
     args = ap.parse_args()
     _lib.load()
