@@ -99,7 +99,8 @@ def main():
                                for _, c in synth.balding_nichols_codes(N, M, k_pop=8, seed=10, miss=0.05)])
     # ---- SNP-sharded: sSVD, winSVD (FP64 and int8 routes), EMU
     for svd, bands, maxp, emu, prec in ((1, 64, 4, False, _lib.PREC_FP64), (2, 16, 6, False, _lib.PREC_FP64),
-                                        (2, 16, 6, False, _lib.PREC_INT8X3), (1, 64, 3, True, _lib.PREC_FP64)):
+                                        (2, 16, 6, False, _lib.PREC_INT8X3), (1, 64, 3, True, _lib.PREC_FP64),
+                                        (1, 64, 3, True, _lib.PREC_INT8X3)):
         src = packed_m if emu else packed
         op, idx = run_snp(svd, src, N, k, bands, maxp, rank, world, local, kw, emu, prec)
         Vfull = np.zeros((M, k))
