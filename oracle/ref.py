@@ -252,12 +252,13 @@ class Ref:
         return out, ws, we
 
 
-def write_bgen(path, probs, bit_depth=8):
-    """probs: (M, N, 3) genotype probabilities (NaN triple = missing) -> a layout-2 zlib BGEN file written by the
-    writer of the reference's vendored bgen library."""
+def write_bgen(path, probs, bit_depth=8, compression=1, layout=2):
+    """probs: (M, N, 3) genotype probabilities (NaN triple = missing) -> a BGEN file (layout 1 / 2, compression
+    0 none / 1 zlib / 2 zstd) written by the writer of the reference's vendored bgen library."""
     probs = np.ascontiguousarray(probs, dtype=np.float64)
     M, N, _ = probs.shape
-    if lib().ref_write_bgen(path.encode(), C.c_longlong(N), C.c_longlong(M), _p(probs), int(bit_depth)):
+    if lib().ref_write_bgen(path.encode(), C.c_longlong(N), C.c_longlong(M), _p(probs), int(bit_depth), int(compression),
+                            int(layout)):
         raise RuntimeError(lib().ref_last_error().decode())
 
 

@@ -556,14 +556,15 @@ int ref_pcangsd_grm(void* h, double* C_out, double* U2_out, double* S2_out, doub
   });
 }
 
-// A BGEN file (layout 2, zlib, unphased diploid, bit_depth bits per probability) written with the writer of the
+// A BGEN file (layout 1 or 2; compression 0 none / 1 zlib / 2 zstd; unphased diploid, bit_depth bits per probability) written with the writer of the
 // reference's vendored library: probs = [nsnps][nsamples][3] genotype probabilities, NaN triples = missing.
-int ref_write_bgen(const char* path, long long nsamples, long long nsnps, const double* probs, int bit_depth) {
+int ref_write_bgen(const char* path, long long nsamples, long long nsnps, const double* probs, int bit_depth, int compression,
+                   int layout) {
   return guarded([&] {
     std::string p(path), free_data;
     std::vector<std::string> samples;
     for (long long i = 0; i < nsamples; ++i) samples.push_back("s" + std::to_string(i));
-    bgen::CppBgenWriter w(p, (std::uint32_t)nsamples, free_data, 1, 2, samples);
+    bgen::CppBgenWriter w(p, (std::uint32_t)nsamples, free_data, (uint32_t)compression, (uint32_t)layout, samples);
     std::vector<std::string> alleles{"A", "C"};
     std::vector<double> g((size_t)3 * nsamples);
     for (long long j = 0; j < nsnps; ++j) {

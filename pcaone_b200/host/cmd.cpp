@@ -116,7 +116,10 @@ Param::Param(int argc, char** argv) {
     file_t = FileType::BINARY;
   });
   off_path("c", "csv", true);
-  off_path("g", "bgen", true);
+  val("g", "bgen", "path of BGEN file compressed by gzip/zstd.", [this](const std::string& v) {
+    filein = v;
+    file_t = FileType::BGEN;
+  });
   val("G", "beagle", "path of BEAGLE file compressed by gzip (genotype likelihoods, PCAngsd algorithm).",
       [this](const std::string& v) {
         filein = v;
@@ -219,8 +222,8 @@ Param::Param(int argc, char** argv) {
       svd_t = SvdType::FULL;  // exact PCA: covariance GEMM + eigen-decomposition on the device (Main.cpp:180-217)
     else
       throw std::invalid_argument("--svd 0 (IRAM: the Spectra driver) is outside the B200 path; use --svd 1, 2 or 3");
-    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY)
-      throw std::invalid_argument("please give the PLINK prefix with -b/--bfile, a BEAGLE file with -G/--beagle, or -B residuals for LD");
+    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY && file_t != FileType::BGEN)
+      throw std::invalid_argument("please give the PLINK prefix with -b/--bfile, a BGEN file with -g/--bgen, a BEAGLE file with -G/--beagle, or -B residuals for LD");
     genetic = true;
     if (!usvprefix.empty()) {
       fileU = usvprefix + ".eigvecs";
@@ -247,6 +250,14 @@ Param::Param(int argc, char** argv) {
       if (print_r2 || ld) throw std::invalid_argument("LD options need PLINK input on the B200 path");
       if (gpus > 1) throw std::invalid_argument("--gpus > 1 is not available for BEAGLE input");
       precision = "fp64";  // genotype likelihoods run on the FP64 kernels
+    }
+    if (file_t == FileType::BGEN) {
+      if (out_of_core) throw std::invalid_argument("not supporting -m option (out-of-core) for BGEN input on the B200 path");
+      if (emu) throw std::invalid_argument("--emu is not available for BGEN input");
+      if (print_r2 || ld || ld_r2 > 0 || !clump.empty()) throw std::invalid_argument("LD options need PLINK input on the B200 path");
+      if (gpus > 1) throw std::invalid_argument("--gpus > 1 is not available for BGEN input");
+      if (svd_t == SvdType::FULL) throw std::invalid_argument("--svd 3 needs PLINK input on the B200 path");
+      precision = "fp64";  // float dosages run on the FP64 kernels
     }
     if (bands < 4 || bands % 2 != 0)
       throw std::invalid_argument("the -w/--batches must be a power of 2 and the minimun is 4.");

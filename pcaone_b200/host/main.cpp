@@ -5,6 +5,7 @@
 #include <thread>
 
 #include "beagle.hpp"
+#include "bgen.hpp"
 #include "halko.hpp"
 #include "ld.hpp"
 
@@ -49,6 +50,13 @@ int main(int argc, char* argv[]) {
       data.prepare();
       run_pca_with_halko(&data, params);
       if (params.pcangsd) run_pcangsd_grm(&data, params, data.samples);
+      cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
+      return bye();
+    }
+    if (params.file_t == FileType::BGEN) {  // Main.cpp:113-116: dosages, in core
+      FileBgen data(params);
+      data.prepare();
+      run_pca_with_halko(&data, params);
       cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
       return bye();
     }

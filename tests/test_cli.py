@@ -35,7 +35,7 @@ def test_cli_binary_is_built_and_prints_reference_flags():
 def test_cli_rejects_bad_options(tmp_path):
     assert _run(["-b", "x", "-w", "3"], ok=False).returncode != 0            # Cmd.cpp:228 bands rule
     assert _run(["-b", "x", "--svd", "0"], ok=False).returncode != 0          # IRAM is off the GPU path
-    r = _run(["-b", "x", "--bgen", "y"], ok=False)
+    r = _run(["-b", "x", "--pgen", "y"], ok=False)
     assert r.returncode != 0 and "outside the B200" in r.stderr
     assert _run(["--beagle", "x.gz", "--emu"], ok=False).returncode != 0
     assert _run(["-b", "x", "-k", "abc"], ok=False).returncode != 0
@@ -427,3 +427,34 @@ def test_cli_svd3_exact_pca_vs_reference(tmp_path):
     np.testing.assert_allclose(np.loadtxt(out + ".eigvals"), Er, rtol=2e-5)
     assert np.abs(U[:, :4] - Ur[:, :4]).max() < 2e-5 and np.abs(V[:, :4] - Vr[:, :4]).max() < 2e-5   # 6 significant digits
     assert col_cos(U, Ur).min() > 0.99999 and col_cos(V, Vr).min() > 0.99999
+
+
+@pytest.mark.gpu
+def test_cli_bgen_vs_reference(tmp_path):
+    """--bgen: the front-end parses the container itself (host/bgen.cpp) and runs the dosage path on the device;
+    U, S, V against the unmodified reference reading the same file with its vendored bgen library."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    N, M, k = 220, 1600, 4
+    rng = np.random.default_rng(91)
+    codes = np.concatenate([c for _, c in synth.balding_nichols_codes(N, M, k_pop=5, seed=92)])
+    g = np.array([2, 0, 1, 0])[codes]
+    P = np.zeros((M, N, 3))
+    for q in range(3):
+        P[:, :, q] = np.where(g == q, 0.85, 0.075)
+    P = 0.7 * P + 0.3 * rng.dirichlet([8, 8, 8], size=(M, N))
+    P /= P.sum(-1, keepdims=True)
+    P[rng.random((M, N)) < 0.02] = np.nan
+    path = str(tmp_path / "f.bgen")
+    ref.write_bgen(path, P, bit_depth=16, compression=2)
+    r = ref.Ref(f"PCAone --bgen {path} -k {k} -d 1 -o {tmp_path}/r -n 4 --maxp 6 --tol-rsvd 0", threads=4)
+    r.new_op()
+    Ur, Sr, Vr = r.compute_usv(6, 0.0)
+    r.close()
+    out = str(tmp_path / "o")
+    _run(["--bgen", path, "-k", k, "-d", 1, "--maxp", 6, "--tol-rsvd", 0, "-V", "-o", out])
+    U, S, V = _load(out, k, M)
+    np.testing.assert_allclose(S, Sr, rtol=2e-5)
+    assert col_cos(U, Ur).min() > 0.99999 and col_cos(V, Vr).min() > 0.99999
+    assert _run(["--bgen", path, "--emu", "-o", out], ok=False).returncode != 0

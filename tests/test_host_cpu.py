@@ -102,3 +102,41 @@ def test_synth_bed_roundtrip(tmp_path):
         synth.read_bed(prefix)
     with pytest.raises(RuntimeError):
         halko.FileBed(halko.Param(filein=prefix, k=2, svd=1))
+
+
+@pytest.mark.parametrize("bit_depth,compression,layout", [(8, 1, 2), (16, 1, 2), (5, 1, 2), (8, 2, 2), (8, 0, 2), (16, 1, 1)])
+def test_bgen_reader_vs_reference_library(tmp_path, bit_depth, compression, layout):
+    """The front-end's own BGEN reader (host/bgen.cpp: header, zlib / zstd blocks, layout 1 and 2 packing, minor-allele
+    rule) against the dosages the reference's vendored bgen library returns for the same file, written with that
+    library's writer. Bit for bit except the 8-bit fast path of the library, whose tail samples come from a table of
+    7-decimal literals (2.4e-7)."""
+    import subprocess
+    from oracle import ref
+    dump = os.path.join(ROOT, "pcaone_b200", "bin", "bgen_dump")
+    if not ref.available() or not os.path.exists(dump):
+        pytest.skip("needs oracle/_ref and pcaone_b200/bin/bgen_dump")
+    rng = np.random.default_rng(11)
+    N, M = 157, 260
+    f = rng.uniform(0.05, 0.95, M)                      # both orientations of the minor allele
+    g = rng.binomial(2, f[:, None], size=(M, N))
+    P = np.zeros((M, N, 3))
+    for q in range(3):
+        P[:, :, q] = np.where(g == q, 0.85, 0.075)
+    P = 0.7 * P + 0.3 * rng.dirichlet([8, 8, 8], size=(M, N))
+    P /= P.sum(-1, keepdims=True)
+    P[rng.random((M, N)) < 0.03] = np.nan
+    P[5] = [1.0, 0.0, 0.0]                              # a monomorphic variant: af = 0 after the minor-allele swap, dropped
+    path = str(tmp_path / "t.bgen")
+    ref.write_bgen(path, P, bit_depth=bit_depth, compression=compression, layout=layout)
+    want = ref.bgen_dosages(path, N, M)
+    af = np.nanmean(want / 2.0, axis=1)
+    want = want[af > 0]
+    r = subprocess.run([dump, "--bgen", path, "-S", "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    raw = open(str(tmp_path / "o.dosages"), "rb").read()
+    m, n = (int(x) for x in np.frombuffer(raw[:16], dtype=np.uint64))
+    got = np.frombuffer(raw[16:], dtype=np.float32).reshape(m, n)
+    assert (m, n) == want.shape and m == M - 1
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    tol = 3e-7 if (bit_depth == 8 and layout == 2) else 0.0
+    assert np.nanmax(np.abs(got - want)) <= tol
