@@ -289,6 +289,11 @@ int pcaone_gl_em_maf(pcaone_ctx* ctx, uint32_t maxiter, double tolmaf, int* iter
  * V = nsnps x k (G * svd.matrixU()): RsvdOne::matrixU() is V here when rows >= cols, else U.
  * finder: 1 = QR (implemented); 2 = LU range finder (RSVD.hpp:150-153) is rejected. */
 int pcaone_upload_dense(pcaone_ctx* ctx, const double* A, uint64_t rows, uint64_t cols);
+/* The in-core `data->G` of a non-genetic input (FileCsv::read_all, FileCsv.cpp:10-62): G is nsamples x nsnps doubles,
+ * column-major (Eigen), already normalised / standardised by the host; never transposed, whatever the shape. The
+ * context is created with that nsamples / nsnps and precision = PCAONE_PREC_FP64; computeGandH / computeUSV then run
+ * on it like on any source (no allele frequencies, pcaone_set_flags(update = 0, standardize = 0)). */
+int pcaone_upload_dense_data(pcaone_ctx* ctx, const double* G);
 int pcaone_dense_rsvd(pcaone_ctx* ctx, uint32_t p, uint32_t windows, int finder);
 
 /* LD pruning (ld_prune_big, LD.cpp:240-268 — SURVEY 8f-2): the same banded r2 tiles, kept on the

@@ -35,6 +35,7 @@
 #include "FileBeagle.hpp"
 #include "FileBinary.hpp"
 #include "FileBgen.hpp"
+#include "FileCsv.hpp"
 #include "bgen/writer.h"
 #include "FilePlink.hpp"
 #include "Arnoldi.hpp"
@@ -128,10 +129,12 @@ void* ref_open(const char* cmdline) {
       }
     } else if (params.file_t == FileType::BEAGLE) {
       c->data = new FileBeagle(params);   // genotype likelihoods; read_all runs emMAF_with_GL and builds E
+    } else if (params.file_t == FileType::CSV) {
+      c->data = new FileCsv(params);      // zstd-compressed CSV, in core (Main.cpp:160-161)
     } else if (params.file_t == FileType::BGEN) {
       c->data = new FileBgen(params);     // the reference's own BGEN reader (external/bgen)
     } else {
-      throw std::runtime_error("ref_shim: only --bfile / --binary / --beagle / --bgen inputs are driven by the oracle");
+      throw std::runtime_error("ref_shim: only --bfile / --binary / --beagle / --bgen / --csv inputs are driven by the oracle");
     }
     c->data->prepare();
   });

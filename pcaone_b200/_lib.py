@@ -62,7 +62,7 @@ SYMBOLS = [
     "pcaone_upload_gl", "pcaone_gl_em_maf",
     "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
     "pcaone_ld_r2_ex", "pcaone_residuals_block", "pcaone_precision", "pcaone_comm_peer_export", "pcaone_comm_peer_import",
-    "pcaone_sample_covariance", "pcaone_sym_svd", "pcaone_gl_grm",
+    "pcaone_sample_covariance", "pcaone_sym_svd", "pcaone_gl_grm", "pcaone_upload_dense_data",
 ]
 
 _lib = None
@@ -108,7 +108,7 @@ def load():
         "pcaone_ld_r2_ex": [vp, C.POINTER(LdSource), u64, vp, vp, u64, vp, vp, dbl, vp],
         "pcaone_residuals_block": [vp, u64, u64, i32, vp], "pcaone_precision": [vp], "pcaone_comm_peer_export": [vp, vp], "pcaone_comm_peer_import": [vp, vp, i32],
         "pcaone_set_host_source2": [vp, vp, u64, u64], "pcaone_set_allreduce2": [vp, ALLREDUCE2_FN, vp],
-        "pcaone_sample_covariance": [vp, vp], "pcaone_gl_grm": [vp, vp, vp], "pcaone_sym_svd": [vp, vp, u64, vp, vp, vp],
+        "pcaone_sample_covariance": [vp, vp], "pcaone_upload_dense_data": [vp, vp], "pcaone_gl_grm": [vp, vp, vp], "pcaone_sym_svd": [vp, vp, u64, vp, vp, vp],
     }
     L.pcaone_alloc_pinned.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.pcaone_alloc_pinned.restype = C.c_int

@@ -320,6 +320,22 @@ int pcaone_upload_dense(pcaone_ctx* c, const double* A, uint64_t rows, uint64_t 
   });
 }
 
+int pcaone_upload_dense_data(pcaone_ctx* c, const double* G) {
+  CTX_GUARD(c, {
+    if (c->cfg.precision != PCAONE_PREC_FP64) throw std::runtime_error("upload_dense_data: the dense source runs in FP64");
+    if (c->cfg.world > 1) throw std::runtime_error("upload_dense_data: single-GPU only");
+    c->ldd = (uint32_t)round_up(c->N, 8);
+    if (!c->d_dense) dmalloc(&c->d_dense, c->M * (size_t)c->ldd);
+    // column j of the column-major N x M matrix is row j of the feature-major operand, re-pitched to ldd
+    PCA_CUDA(cudaMemsetAsync(c->d_dense, 0, c->M * (size_t)c->ldd * sizeof(double), c->stream));
+    PCA_CUDA(cudaMemcpy2DAsync(c->d_dense, (size_t)c->ldd * sizeof(double), G, c->N * sizeof(double), c->N * sizeof(double),
+                               c->M, cudaMemcpyHostToDevice, c->stream));
+    PCA_CUDA(cudaStreamSynchronize(c->stream));
+    c->tm.h2d_bytes += c->M * c->N * sizeof(double);
+    c->source = PCAONE_SRC_DENSE;
+  });
+}
+
 int pcaone_ld_prune(pcaone_ctx* c, const double* G, uint64_t nsnps, const int32_t* ws, const int32_t* we, uint64_t nwin,
                     const double* af, double r2_tol, uint8_t* keep_out) {
   CTX_GUARD(c, {

@@ -115,7 +115,10 @@ Param::Param(int argc, char** argv) {
     filein = v;
     file_t = FileType::BINARY;
   });
-  off_path("c", "csv", true);
+  val("c", "csv", "path of comma seperated CSV file compressed by zstd.", [this](const std::string& v) {
+    filein = v;
+    file_t = FileType::CSV;
+  });
   val("g", "bgen", "path of BGEN file compressed by gzip/zstd.", [this](const std::string& v) {
     filein = v;
     file_t = FileType::BGEN;
@@ -222,9 +225,9 @@ Param::Param(int argc, char** argv) {
       svd_t = SvdType::FULL;  // exact PCA: covariance GEMM + eigen-decomposition on the device (Main.cpp:180-217)
     else
       throw std::invalid_argument("--svd 0 (IRAM: the Spectra driver) is outside the B200 path; use --svd 1, 2 or 3");
-    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY && file_t != FileType::BGEN)
+    if (file_t != FileType::PLINK && file_t != FileType::BEAGLE && file_t != FileType::BINARY && file_t != FileType::BGEN && file_t != FileType::CSV)
       throw std::invalid_argument("please give the PLINK prefix with -b/--bfile, a BGEN file with -g/--bgen, a BEAGLE file with -G/--beagle, or -B residuals for LD");
-    genetic = true;
+    genetic = file_t != FileType::CSV;
     if (!usvprefix.empty()) {
       fileU = usvprefix + ".eigvecs";
       fileE = usvprefix + ".eigvals";
@@ -250,6 +253,14 @@ Param::Param(int argc, char** argv) {
       if (print_r2 || ld) throw std::invalid_argument("LD options need PLINK input on the B200 path");
       if (gpus > 1) throw std::invalid_argument("--gpus > 1 is not available for BEAGLE input");
       precision = "fp64";  // genotype likelihoods run on the FP64 kernels
+    }
+    if (file_t == FileType::CSV) {
+      if (out_of_core) throw std::invalid_argument("not supporting -m option (out-of-core) for CSV input on the B200 path");
+      if (emu || pcangsd) throw std::invalid_argument("--emu / --pcangsd do not apply to CSV input");
+      if (print_r2 || ld || ld_r2 > 0 || !clump.empty()) throw std::invalid_argument("LD options need PLINK input on the B200 path");
+      if (gpus > 1) throw std::invalid_argument("--gpus > 1 is not available for CSV input");
+      if (svd_t == SvdType::FULL) throw std::invalid_argument("--svd 3 needs PLINK input on the B200 path");
+      precision = "fp64";  // a dense FP64 matrix runs on the FP64 kernels
     }
     if (file_t == FileType::BGEN) {
       if (out_of_core) throw std::invalid_argument("not supporting -m option (out-of-core) for BGEN input on the B200 path");

@@ -6,6 +6,7 @@
 
 #include "beagle.hpp"
 #include "bgen.hpp"
+#include "csv.hpp"
 #include "halko.hpp"
 #include "ld.hpp"
 
@@ -50,6 +51,13 @@ int main(int argc, char* argv[]) {
       data.prepare();
       run_pca_with_halko(&data, params);
       if (params.pcangsd) run_pcangsd_grm(&data, params, data.samples);
+      cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
+      return bye();
+    }
+    if (params.file_t == FileType::CSV) {  // Main.cpp:160-161: a dense matrix, in core
+      FileCsv data(params);
+      data.prepare();
+      run_pca_with_halko(&data, params);
       cao.print(tick.date(), "total elapsed reading time: ", data.readtime, " seconds");
       return bye();
     }

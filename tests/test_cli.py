@@ -458,3 +458,36 @@ def test_cli_bgen_vs_reference(tmp_path):
     np.testing.assert_allclose(S, Sr, rtol=2e-5)
     assert col_cos(U, Ur).min() > 0.99999 and col_cos(V, Vr).min() > 0.99999
     assert _run(["--bgen", path, "--emu", "-o", out], ok=False).returncode != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale,svd", [(0, 1), (1, 2), (2, 1), (2, 2)])
+def test_cli_csv_vs_reference(tmp_path, scale, svd):
+    """--csv: a zstd-compressed count matrix (features x samples), the -C normalisations and the per-feature
+    standardisation on the host, the dense FP64 products on the device; U, S, V against the unmodified reference's
+    FileCsv on the same file. More samples than features too (the operand is never transposed)."""
+    import pyarrow as pa
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    for N, M in ((120, 900), (700, 300)):
+        rng = np.random.default_rng(7 + scale + N)
+        grp = rng.integers(0, 3, size=N)
+        prog = rng.gamma(2.0, 2.0, size=(M, 3))
+        cnt = rng.poisson(prog[:, grp] * np.exp(rng.normal(0, 0.4, size=(1, N))))
+        path = str(tmp_path / f"c{N}.csv.zst")
+        text = "".join(",".join(str(int(x)) for x in row) + "\n" for row in cnt)
+        open(path, "wb").write(pa.Codec("zstd").compress(text.encode(), asbytes=True))
+        k = 3
+        r = ref.Ref(f"PCAone --csv {path} -k {k} -d {svd} -S -w 8 -C {scale} -o {tmp_path}/r -n 4 --maxp 7 --tol-rsvd 0", threads=4)
+        r.new_op()
+        Ur, Sr, Vr = r.compute_usv(7, 0.0)
+        r.close()
+        out = str(tmp_path / f"o{N}")
+        _run(["--csv", path, "-k", k, "-d", svd, "-S", "-w", 8, "-C", scale, "--maxp", 7, "--tol-rsvd", 0, "-V", "-o", out])
+        U, S, V = np.loadtxt(out + ".eigvecs", ndmin=2), np.loadtxt(out + ".sigvals", ndmin=1), np.loadtxt(out + ".loadings", ndmin=2)
+        assert U.shape == (N, k) and V.shape == (M, k)
+        np.testing.assert_allclose(S, Sr, rtol=2e-5)
+        assert col_cos(U, Ur).min() > 0.99999 and col_cos(V, Vr).min() > 0.99999
+    assert _run(["--csv", path, "-C", 3, "-o", out], ok=False).returncode != 0
+    assert _run(["--csv", path, "--emu", "-o", out], ok=False).returncode != 0
