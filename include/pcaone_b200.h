@@ -252,6 +252,11 @@ int pcaone_perform_op(pcaone_ctx* ctx, const double* x_in, double* y_out);
  * (FP64 kernels on every source). */
 int pcaone_xt_times(pcaone_ctx* ctx, const double* A, uint32_t ncols, double* out, double* sqnorm);
 int pcaone_x_times(pcaone_ctx* ctx, const double* B, uint32_t ncols, double* out);
+/* out (nsamples x ncols) = C B with C the missing-call indicator of the packed source (C(i, j) = 1 iff the call of
+ * sample i at SNP j is missing: the `data->C` of the reference) and B nsnps x ncols — the per-sample correction of
+ * the normal equations of `--project 2` (solve_projection_scores, Projection.cpp:159-179: rows of V at the missing
+ * calls are left out of each sample's least-squares problem). Same kernels as pcaone_x_times, decode table {0,1,0,0}. */
+int pcaone_mask_times(pcaone_ctx* ctx, const double* B, uint32_t ncols, double* out);
 
 /* ---- BGEN-style dosages (FileBgen::read_all / read_block_initial, FileBgen.cpp:15-168) ----------
  * The host keeps the container parsing (`var.minor_allele_dosage`, FileBgen.cpp:26) and hands over

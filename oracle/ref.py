@@ -252,6 +252,13 @@ class Ref:
         return out, ws, we
 
 
+def run_projection(cmdline, threads=4):
+    """the projection branch of main() (Main.cpp:95-107) on a PLINK input: writes <out>.eigvecs like the reference."""
+    lib().ref_set_threads(int(threads))
+    if lib().ref_run_projection(cmdline.encode()):
+        raise RuntimeError("reference failed: " + lib().ref_last_error().decode())
+
+
 def write_bgen(path, probs, bit_depth=8, compression=1, layout=2):
     """probs: (M, N, 3) genotype probabilities (NaN triple = missing) -> a BGEN file (layout 1 / 2, compression
     0 none / 1 zlib / 2 zstd) written by the writer of the reference's vendored bgen library."""

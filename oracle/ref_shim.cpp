@@ -36,6 +36,7 @@
 #include "FileBinary.hpp"
 #include "FileBgen.hpp"
 #include "FileCsv.hpp"
+#include "Projection.hpp"
 #include "bgen/writer.h"
 #include "FilePlink.hpp"
 #include "Arnoldi.hpp"
@@ -591,6 +592,24 @@ int ref_bgen_dosages(const char* path, float* out, long long nsamples, long long
       auto var = bg.next_var();
       var.minor_allele_dosage(out + (size_t)j * nsamples);
     }
+  });
+}
+
+// The projection branch of main() (Main.cpp:95-107) for PLINK input: Param from the command line, FileBed,
+// the reference's own run_projection (Projection.cpp:188-309), which writes <out>.eigvecs.
+int ref_run_projection(const char* cmdline) {
+  return guarded([&] {
+    auto toks = split_ws(cmdline);
+    std::vector<char*> argv;
+    for (auto& t : toks) argv.push_back(const_cast<char*>(t.c_str()));
+    Param params((int)argv.size(), argv.data());
+    if (cao.cao.is_open()) cao.cao.close();
+    cao.cao.open(params.fileout + ".log");
+    cao.is_screen = false;
+    if (params.file_t != FileType::PLINK || params.project < 1) throw std::runtime_error("ref_run_projection: -b ... --project 1|2");
+    Data* data = new FileBed(params);
+    run_projection(data, params);
+    delete data;
   });
 }
 

@@ -62,7 +62,7 @@ SYMBOLS = [
     "pcaone_upload_gl", "pcaone_gl_em_maf",
     "pcaone_comm_unique_id", "pcaone_comm_init", "pcaone_comm_attach", "pcaone_set_host_source2", "pcaone_set_allreduce2",
     "pcaone_ld_r2_ex", "pcaone_residuals_block", "pcaone_precision", "pcaone_comm_peer_export", "pcaone_comm_peer_import",
-    "pcaone_sample_covariance", "pcaone_sym_svd", "pcaone_gl_grm", "pcaone_upload_dense_data",
+    "pcaone_sample_covariance", "pcaone_sym_svd", "pcaone_gl_grm", "pcaone_upload_dense_data", "pcaone_mask_times",
 ]
 
 _lib = None
@@ -101,7 +101,7 @@ def load():
         "pcaone_shuffle_indices": [u64, vp], "pcaone_ld_r2": [vp, vp, u64, vp, vp, u64, vp],
         "pcaone_get_timers": [vp, C.POINTER(Timers), i32], "pcaone_enable_timing": [vp, i32],
         "pcaone_upload_dense": [vp, vp, u64, u64], "pcaone_dense_rsvd": [vp, u32, u32, i32],
-        "pcaone_upload_dosage": [vp, vp, u64, i32], "pcaone_perform_op": [vp, vp, vp], "pcaone_xt_times": [vp, vp, u32, vp, vp], "pcaone_x_times": [vp, vp, u32, vp],
+        "pcaone_upload_dosage": [vp, vp, u64, i32], "pcaone_perform_op": [vp, vp, vp], "pcaone_xt_times": [vp, vp, u32, vp, vp], "pcaone_x_times": [vp, vp, u32, vp], "pcaone_mask_times": [vp, vp, u32, vp],
         "pcaone_upload_gl": [vp, vp, u64, i32], "pcaone_gl_em_maf": [vp, u32, dbl, vp],
         "pcaone_ld_prune": [vp, vp, u64, vp, vp, u64, vp, dbl, vp],
         "pcaone_comm_unique_id": [vp], "pcaone_comm_init": [vp, vp, i32, i32], "pcaone_comm_attach": [vp, vp],

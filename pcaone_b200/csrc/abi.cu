@@ -86,6 +86,7 @@ int pcaone_create(const pcaone_config* cfg, pcaone_ctx** out) {
     c->pitch = (uint32_t)round_up(c->bpr, 16);
     c->lut.sqrt_ploidy = sqrt((double)cfg->ploidy);
     c->lut.standardize = 0;
+    c->lut.mask = 0;
     cudaDeviceProp prop;
     PCA_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     c->sms = prop.multiProcessorCount;
@@ -348,6 +349,25 @@ int pcaone_xt_times(pcaone_ctx* c, const double* A, uint32_t ncols, double* out,
   CTX_GUARD(c, xt_times(c, A, ncols, out, sqnorm));
 }
 int pcaone_x_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out) { CTX_GUARD(c, x_times(c, B, ncols, out)); }
+
+int pcaone_mask_times(pcaone_ctx* c, const double* B, uint32_t ncols, double* out) {
+  CTX_GUARD(c, {
+    if (c->source != PCAONE_SRC_RESIDENT && c->source != PCAONE_SRC_HOST && c->source != PCAONE_SRC_FILE)
+      throw std::runtime_error("mask_times: needs a packed genotype source");
+    const int upd = c->update;
+    c->lut.mask = 1;
+    c->update = 0;  // the indicator of the calls themselves, never an EMU fill
+    try {
+      x_times(c, B, ncols, out);
+    } catch (...) {
+      c->lut.mask = 0;
+      c->update = upd;
+      throw;
+    }
+    c->lut.mask = 0;
+    c->update = upd;
+  });
+}
 
 int pcaone_perform_op(pcaone_ctx* c, const double* x_in, double* y_out) { CTX_GUARD(c, perform_op(c, x_in, y_out)); }
 

@@ -36,6 +36,7 @@ struct SnpLut {
 struct LutParams {
   double sqrt_ploidy;  // sqrt((double)ploidy) rounded on the host like the reference
   int standardize;     // standardize && scale == -9
+  int mask;            // 1: decode the missing-call indicator (code 01 -> 1, everything else 0) instead of genotypes
 };
 
 __device__ __forceinline__ double snp_scale(double F, const LutParams& p) {
@@ -50,6 +51,13 @@ __device__ __forceinline__ double snp_scale(double F, const LutParams& p) {
 __device__ __forceinline__ SnpLut make_lut(double F, const LutParams& p) {
   const double s = snp_scale(F, p);
   SnpLut t;
+  if (p.mask) {  // the C matrix of the reference (missing calls), for the per-sample normal equations of --project 2
+    t.v[0] = 0.0;
+    t.v[1] = 1.0;
+    t.v[2] = 0.0;
+    t.v[3] = 0.0;
+    return t;
+  }
   t.v[0] = __dmul_rn(__dsub_rn(1.0, F), s);  // code 00: BED2GENO 1.0
   t.v[1] = 0.0;                              // code 01: missing -> mean-imputed 0
   t.v[2] = __dmul_rn(__dsub_rn(0.5, F), s);  // code 10: 0.5

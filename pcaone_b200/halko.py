@@ -562,6 +562,13 @@ class RsvdOpData:
         self._chk(self.L.pcaone_x_times(self.h, _vp(B), B.shape[1], _vp(out)))
         return out
 
+    def maskTimes(self, B):
+        """C B (N x c) with C the missing-call indicator (the reference's data->C): Projection.cpp:159-179."""
+        B = np.asfortranarray(B, dtype=np.float64)
+        out = _f((self.cols(), B.shape[1]))
+        self._chk(self.L.pcaone_mask_times(self.h, _vp(B), B.shape[1], _vp(out)))
+        return out
+
     def setUSV(self, U, S, V):
         U = np.asfortranarray(U, dtype=np.float64)
         V = np.asfortranarray(V, dtype=np.float64)

@@ -132,7 +132,8 @@ Param::Param(int argc, char** argv) {
   val("", "tol-maf", "tolerance for MAF estimation by EM.", [this](const std::string& v) { tolmaf = std::stod(v); });
   off_path("", "hardcall", false);
   off_path("", "maf", true);
-  off_path("", "project", true);
+  val("", "project", "project the new samples onto the existing PCs (--USV). 1: by multiplying the loadings; 2: by solving g = V x per sample over its called SNPs (takes missing genotypes).",
+      [this](const std::string& v) { project = std::stoi(v); });
   off_path("", "project-bootstrap", true);
   off_path("", "project-bootstrap-save", false);
   off_path("", "inbreed", true);
@@ -234,6 +235,15 @@ Param::Param(int argc, char** argv) {
       fileS = usvprefix + ".sigvals";
       fileV = usvprefix + ".loadings";
       if (filebim.empty()) filebim = usvprefix + ".mbim";
+    }
+    if (project != 0) {  // Cmd.cpp:187-194
+      if (project < 1 || project > 2)
+        throw std::invalid_argument("--project supports 1 or 2 on the B200 path (3, the GL-aware EM projection, is not built)");
+      if (fileV.empty() || fileS.empty()) throw std::invalid_argument("please use --USV together with --project");
+      if (file_t != FileType::PLINK) throw std::invalid_argument("--project needs PLINK input on the B200 path");
+      if (gpus > 1) throw std::invalid_argument("--project runs on one GPU");
+      dopca = false, out_of_core = false;
+      memory = 0;
     }
     if (print_r2 || ld_r2 > 0 || !clump.empty()) {  // Cmd.cpp:181-184
       dopca = false;

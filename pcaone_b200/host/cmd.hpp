@@ -34,6 +34,7 @@ class Param {
   uint bands = 64;
   bool genetic = true;
   bool dopca = true;
+  int project = 0;  // --project 1 | 2 (Projection.cpp:188-246)
   bool perm = false;
   uint maxiter = 100;
   double tolem = 1e-5;

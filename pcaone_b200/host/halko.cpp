@@ -5,6 +5,7 @@
 #include "halko.hpp"
 
 #include <cmath>
+#include <iomanip>
 
 #include <atomic>
 #include <condition_variable>
@@ -149,6 +150,133 @@ void run_pca_full(Data* data, const Param& params) {
     data->check(pcaone_get_F(data->ctx, data->F.data()));
   }
   data->write_eigs_files(evals, svals, U, V);
+}
+
+// --project 1 | 2 (Projection.cpp:188-246): new samples onto the PCs of a reference panel (--USV: .sigvals, .loadings,
+// .mbim). Allele frequencies come from the panel's .mbim (Data.cpp:17-31), the genotypes are standardised with them,
+//   1: U = G (V S^-1)                                                  one product on the device
+//   2: per sample, least squares of g_i = (V S) x over the SNPs it was called at (solve_projection_scores, :159-179):
+//      normal equations A_i x = b_i, b = G W on the device, A_i = W^T W - (missing-call indicator) x (products of the
+//      columns of W) on the device (pcaone_mask_times), the N small K x K solves (Cholesky) on the host.
+// The SNPs of the target must be those of the .mbim, in order (the reference also matches subsets and flipped
+// alleles; that bookkeeping is not built).
+void run_projection(Data* data, const Param& params) {
+  cao.print(tick.date(), "run projection");
+  const uint64 N = data->nsamples, M = data->nsnps;
+  {  // identical SNP sets, allele frequencies of the panel
+    std::ifstream fb(params.filein + ".bim"), fm(params.filebim);
+    if (!fb.is_open()) cao.error("can not open " + params.filein + ".bim");
+    if (!fm.is_open()) cao.error("can not open " + params.filebim);
+    cao.print(tick.date(), "read allele frequency from .mbim file: " + params.filebim);
+    Mat1D F(M);
+    std::string lb, lm;
+    uint64 j = 0;
+    while (std::getline(fm, lm)) {
+      if (!std::getline(fb, lb) || j >= M) cao.error("the .bim and the .mbim list different SNPs: only identical SNP sets are supported by --project here");
+      std::istringstream ib(lb), im(lm);
+      std::string tb[6], tm[7];
+      for (auto& t : tb) ib >> t;
+      for (auto& t : tm) im >> t;
+      if (tm[6].empty()) cao.error("the input file is not valid!\n => " + params.filebim);
+      if (tb[0] != tm[0] || tb[3] != tm[3] || tb[4] != tm[4] || tb[5] != tm[5])
+        cao.error("the .bim and the .mbim list different SNPs: only identical SNP sets are supported by --project here");
+      F(j++) = std::stod(tm[6]);
+    }
+    if (j != M || std::getline(fb, lb)) cao.error("the .bim and the .mbim list different SNPs: only identical SNP sets are supported by --project here");
+    data->check(pcaone_set_F(data->ctx, F.data()));
+  }
+  data->check(pcaone_set_flags(data->ctx, 0, 1));  // standardize_E (Projection.cpp:216)
+  cao.print(tick.date(), "start parsing V:", params.fileV, ", S:", params.fileS);
+  std::vector<double> S;
+  {
+    std::ifstream fs(params.fileS);
+    if (!fs.is_open()) cao.error("can not open " + params.fileS);
+    std::string line;
+    while (std::getline(fs, line))
+      if (!line.empty() && line[0] != '#') S.push_back(std::stod(line));
+  }
+  const uint64 K = std::min<uint64>(S.size(), params.k);
+  if (K == 0) cao.error("no singular values in " + params.fileS);
+  Mat2D V(M, K);
+  {
+    std::ifstream fv(params.fileV);
+    if (!fv.is_open()) cao.error("can not open " + params.fileV);
+    std::string line;
+    for (uint64 j = 0; j < M; ++j) {
+      if (!std::getline(fv, line)) cao.error("the number of rows of " + params.fileV + " does not match the SNPs");
+      std::istringstream is(line);
+      for (uint64 x = 0; x < K; ++x)
+        if (!(is >> V(j, x))) cao.error("too few columns in " + params.fileV);
+    }
+  }
+  Mat2D U(N, K);
+  uint64 nmiss = 0;
+  data->check(pcaone_missing_count(data->ctx, &nmiss));
+  if (params.project == 1) {
+    if (nmiss > 0) cao.warn("there are missing genotypes. recommend using --project 2 or 3.");
+    for (uint64 x = 0; x < K; ++x)
+      for (uint64 j = 0; j < M; ++j) V(j, x) /= S[x];
+    data->check(pcaone_x_times(data->ctx, V.data(), (uint32_t)K, U.data()));
+  } else {
+    if (nmiss == 0) cao.warn("there is no missing genotypes");
+    for (uint64 x = 0; x < K; ++x)
+      for (uint64 j = 0; j < M; ++j) V(j, x) *= S[x];
+    Mat2D b(N, K);
+    data->check(pcaone_x_times(data->ctx, V.data(), (uint32_t)K, b.data()));
+    // the K (K + 1) / 2 column products of W through the missing-call indicator, in panels of k + oversamples columns
+    const uint64 T = K * (K + 1) / 2, panel = params.k + params.oversamples;
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;
+    for (uint32_t a = 0; a < K; ++a)
+      for (uint32_t c = a; c < K; ++c) pairs.push_back({a, c});
+    Mat2D Mz(N, T);
+    for (uint64 t0 = 0; t0 < T; t0 += panel) {
+      const uint64 nc = std::min<uint64>(panel, T - t0);
+      Mat2D Z(M, nc), out(N, nc);
+      for (uint64 t = 0; t < nc; ++t)
+        for (uint64 j = 0; j < M; ++j) Z(j, t) = V(j, pairs[t0 + t].first) * V(j, pairs[t0 + t].second);
+      data->check(pcaone_mask_times(data->ctx, Z.data(), (uint32_t)nc, out.data()));
+      std::copy(out.v.begin(), out.v.end(), Mz.v.begin() + (size_t)t0 * N);
+    }
+    std::vector<double> A0(T, 0.0);
+    for (uint64 t = 0; t < T; ++t)
+      for (uint64 j = 0; j < M; ++j) A0[t] += V(j, pairs[t].first) * V(j, pairs[t].second);
+    std::vector<double> A(K * K), y(K);
+    for (uint64 i = 0; i < N; ++i) {
+      for (uint64 t = 0; t < T; ++t) {
+        const double v = A0[t] - Mz(i, t);
+        A[pairs[t].first * K + pairs[t].second] = A[pairs[t].second * K + pairs[t].first] = v;
+      }
+      // Cholesky A = L L^T in place (lower), then the two triangular solves
+      for (uint64 c = 0; c < K; ++c) {
+        double d = A[c * K + c];
+        for (uint64 q = 0; q < c; ++q) d -= A[c * K + q] * A[c * K + q];
+        if (!(d > 0)) cao.error("--project 2: a sample has too few called SNPs for the requested number of PCs");
+        d = std::sqrt(d);
+        A[c * K + c] = d;
+        for (uint64 r = c + 1; r < K; ++r) {
+          double v = A[r * K + c];
+          for (uint64 q = 0; q < c; ++q) v -= A[r * K + q] * A[c * K + q];
+          A[r * K + c] = v / d;
+        }
+      }
+      for (uint64 r = 0; r < K; ++r) {
+        double v = b(i, r);
+        for (uint64 q = 0; q < r; ++q) v -= A[r * K + q] * y[q];
+        y[r] = v / A[r * K + r];
+      }
+      for (uint64 r = K; r-- > 0;) {
+        double v = y[r];
+        for (uint64 q = r + 1; q < K; ++q) v -= A[q * K + r] * U(i, q);
+        U(i, r) = v / A[r * K + r];
+      }
+    }
+  }
+  std::ofstream outu(params.fileout + ".eigvecs");
+  outu << std::setprecision(6);
+  for (uint64 i = 0; i < N; ++i) {
+    for (uint64 x = 0; x < K; ++x) outu << (x ? "\t" : "") << U(i, x);
+    outu << "\n";
+  }
 }
 
 // The GRM step of PCAngsd (Halko.cpp:320-334) after the EM loop: covariance of the re-standardised expected

@@ -72,6 +72,7 @@ class FancyRsvdOpData : public RsvdOpData {
 // Halko.cpp:271-345. `gather_v` (multi-GPU jobs) turns this shard's V rows into the whole
 // job's V on the writing rank; single-GPU callers leave it empty.
 void run_pca_full(Data* data, const Param& params);  // --svd 3 (Main.cpp:180-217)
+void run_projection(Data* data, const Param& params);  // --project 1 | 2 (Projection.cpp:188-246, :305-308)
 void run_pcangsd_grm(Data* data, const Param& params, const std::vector<std::string>& samples);  // Halko.cpp:320-334
 void run_pca_with_halko(Data* data, const Param& params,
                         const std::function<void(RsvdOpData*)>& before_write = nullptr);

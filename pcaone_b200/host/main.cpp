@@ -44,6 +44,13 @@ int main(int argc, char* argv[]) {
       run_ld_stuff(&data, params);
       return bye();
     }
+    if (params.project > 0) {  // Main.cpp:95-107
+      params.perm = false;
+      FileBed data(params);
+      data.prepare();
+      run_projection(&data, params);
+      return bye();
+    }
     if (params.file_t == FileType::BINARY) cao.error("-B (binary residuals) is an LD input: give --print-r2, --ld-r2 or --clump");
     if (params.file_t == FileType::BEAGLE) {  // Main.cpp:117-120 + Halko.cpp:290-311 (PCAngsd EM)
       FileBeagle data(params);
