@@ -19,6 +19,7 @@ class FileCsv : public Data {
   void read_block_initial(uint64 start_idx, uint64 stop_idx, bool standardize) override;
   void read_block_update(uint64, uint64, const Mat2D&, const Mat1D&, const Mat2D&, bool) override {}
   void attach_stream_source() override { cao.error("not supporting -m (out-of-core) for CSV input on the B200 path"); }
+  const Mat2D& matrix() const { return X; }  // what read_all uploads (tests)
 
  private:
   Mat2D X;  // nsamples x nsnps after normalisation, logical (permuted) feature order

@@ -140,3 +140,32 @@ def test_bgen_reader_vs_reference_library(tmp_path, bit_depth, compression, layo
     assert np.array_equal(np.isnan(got), np.isnan(want))
     tol = 3e-7 if (bit_depth == 8 and layout == 2) else 0.0
     assert np.nanmax(np.abs(got - want)) <= tol
+
+
+@pytest.mark.parametrize("scale", [0, 1, 2])
+def test_csv_reader_vs_reference(tmp_path, scale):
+    """The front-end's CSV reader (host/csv.cpp: zstd stream, parsing, -C normalisation, per-feature standardisation)
+    against the data->G the reference's FileCsv::read_all builds from the same file (FileCsv.cpp:10-62)."""
+    import subprocess
+    import pyarrow as pa
+    from oracle import ref
+    dump = os.path.join(ROOT, "pcaone_b200", "bin", "csv_dump")
+    if not ref.available() or not os.path.exists(dump):
+        pytest.skip("needs oracle/_ref and pcaone_b200/bin/csv_dump")
+    rng = np.random.default_rng(5 + scale)
+    N, M = 77, 310
+    cnt = rng.poisson(rng.gamma(2.0, 2.0, size=(M, 1)) * np.exp(rng.normal(0, 0.5, size=(1, N))))
+    cnt[7] = 3                                             # a constant feature: sd = 0, left centred only
+    path = str(tmp_path / "c.csv.zst")
+    text = "".join(",".join(str(int(x)) for x in row) + "\n" for row in cnt)
+    open(path, "wb").write(pa.Codec("zstd").compress(text.encode(), asbytes=True))
+    r = ref.Ref(f"PCAone --csv {path} -k 3 -d 1 -C {scale} -o {tmp_path}/r -n 2", threads=2)
+    want = r.dataG()
+    r.close()
+    q = subprocess.run([dump, "--csv", path, "-C", str(scale), "-S", "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert q.returncode == 0, q.stderr[-500:]
+    raw = open(str(tmp_path / "o.matrix"), "rb").read()
+    n, m = (int(x) for x in np.frombuffer(raw[:16], dtype=np.uint64))
+    got = np.frombuffer(raw[16:], dtype=np.float64).reshape(m, n).T
+    assert (n, m) == (N, M) == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
