@@ -99,3 +99,38 @@ def test_bgen_dosage_semantics_vs_reference(tmp_path):
     assert np.abs(od.F - Fr).max() <= 1e-15
     X = od.block(0, M - 1, False)
     assert np.abs(X - Gr).max() <= 1e-15
+
+
+def test_clump_restatement_vs_reference(tmp_path):
+    """oracle.ld_clump against the .clump file the unmodified reference writes (LD.cpp:323-401, :505-540)."""
+    ref = _ref()
+    N, M = 200, 2200
+    prefix = str(tmp_path / "s")
+    pk = synth.write_bed(prefix, N, M, k_pop=4, seed=36)
+    rng = np.random.default_rng(3)
+    keep = set(np.sort(rng.choice(M, size=1800, replace=False)).tolist())
+    pv = rng.uniform(0, 0.03, size=M) ** 2
+    assoc = str(tmp_path / "gwas.tsv")
+    lines, a_chr, a_bp, a_p = [], [], [], []
+    bim = [l.split() for l in open(prefix + ".bim")]
+    with open(assoc, "w") as f:
+        f.write("SNP\tCHR\tBP\tBETA\tP\n")
+        for j, t in enumerate(bim):
+            if j in keep:
+                ln = f"{t[1]}\t{t[0]}\t{t[3]}\t{rng.normal():.4f}\t{pv[j]:.10g}"
+                f.write(ln + "\n")
+                lines.append(ln)
+                a_chr.append(t[0])
+                a_bp.append(int(t[3]))
+                a_p.append(float(f"{pv[j]:.10g}"))
+    args = dict(clump_bp=4000, clump_r2=0.02, p1=1e-4, p2=5e-4)
+    r = ref.Ref(f"PCAone -b {prefix} -k 2 -d 1 -o {tmp_path}/r -n 2", threads=2)
+    r.ld_clump(prefix + ".bim", assoc, str(tmp_path / "ref.clump"), **args)
+    r.close()
+    want = open(tmp_path / "ref.clump").read().splitlines()
+    od = orc.OracleData(pk, N)
+    G = od.block(0, M - 1, False)
+    got = orc.ld_clump(G, [t[0] for t in bim], [int(t[3]) for t in bim], lines, a_chr, a_bp, a_p, args["clump_bp"],
+                       args["clump_r2"], args["p1"], args["p2"])
+    assert len(want) > 20 and sum(1 for l in want[1:] if not l.endswith("NONE")) > 5
+    assert got == want[1:]
